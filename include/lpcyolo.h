@@ -1,0 +1,151 @@
+/*
+ * lpcyolo.h - C ABI of liblpcyolo.so: the B200 (sm_100a) kernels behind the LPC-YOLO / YOLOv10
+ * inference hot path.
+ *
+ * The reference (a fork of ultralytics 8.1.34) has no FFI / plugin boundary of its own: the path is
+ * pure Python on torch ATen.  This header therefore *defines* the boundary:
+ * each entry point below replaces one group of ATen calls made by a reference module and cites it
+ * (paths relative to the reference's ultralytics/ directory).  The Python host code in
+ * lpc-yolo_b200/ binds these with ctypes (lpc-yolo_b200/_lib.py); INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer owned by the caller.  The library never allocates device
+ *     memory, never synchronises and keeps no global state besides a per-process TMA descriptor
+ *     cache and the last-error string (thread local).
+ *   - Activations are NHWC "views": element (n,y,x,c) of a view with pixel pitch `ld` lives at
+ *     ptr[((n*H + y)*W + x)*ld + c].  ld >= C lets a layer read or write a channel slice of a wider
+ *     buffer, which is how chunk/cat (block.py:229-231), Concat (conv.py:331) and the detect head's
+ *     cat (head.py:76) are made free.
+ *   - dtype: LPC_BF16 (storage bf16, fp32 accumulate; the production mode) or LPC_F32 (fp32 storage
+ *     and arithmetic on CUDA cores; the validation mode, 1e-5 of the reference).
+ *   - `stream` is a cudaStream_t passed as void*.
+ *   - Return value: 0 on success, negative LPC_E_* otherwise; lpc_last_error() gives the text.
+ */
+#ifndef LPCYOLO_H_
+#define LPCYOLO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LPC_ABI_VERSION 1
+
+enum { LPC_BF16 = 0, LPC_F32 = 1 };
+/* per-layer activation, read from the reference module's actual `.act` (SURVEY.md finding 1):
+ * conv.Conv -> SiLU (conv.py:39), block.Conv -> Mish (block.py:4920), act=False -> identity,
+ * ChannelAttention / SPCA gates -> sigmoid (conv.py:286, block.py:5740), SPCA squeeze -> ReLU. */
+enum { LPC_ACT_NONE = 0, LPC_ACT_SILU = 1, LPC_ACT_MISH = 2, LPC_ACT_SIGMOID = 3, LPC_ACT_RELU = 4 };
+enum {
+  LPC_OK = 0,
+  LPC_E_ARG = -1,         /* bad shape / alignment / null pointer */
+  LPC_E_UNSUPPORTED = -2, /* valid request the kernels do not cover */
+  LPC_E_CUDA = -3,        /* a CUDA runtime / driver call failed */
+  LPC_E_WORKSPACE = -4    /* workspace too small */
+};
+
+int lpc_abi_version(void);
+const char* lpc_last_error(void);
+/* compute capability of the current device as major*10+minor (100 on B200); <0 on error. */
+int lpc_device_arch(void);
+/* number of kernels this library has launched in this process (bench.py reports it as gpu_launches). */
+unsigned long long lpc_launch_count(void);
+
+/* ---- dense convolution -------------------------------------------------------------------------
+ * y = act(conv2d(x, w) + bias) [* chan_scale[n,c]] [+ res]
+ * replaces nn.Conv2d + BatchNorm2d (folded on the host: utils/torch_utils.py:171-198) + activation in
+ * conv.Conv.forward (conv.py:48-54) and block.Conv.forward (block.py:4922-4926); `res` is the
+ * Bottleneck / PSA / SPCA shortcut add (block.py:340, :813-814, :5749); `chan_scale` ([B,Cout] fp32) is
+ * SPCA's `spatial * attn` gate (block.py:5748).
+ *
+ * lpc_conv2d_direct: CUDA-core implicit GEMM, any k/stride/pad, both dtypes.
+ *   w: [k*k][Cin][Cout] in the activation dtype; bias: [Cout] fp32 or NULL.
+ * lpc_conv2d_tc: tcgen05 / TMEM implicit GEMM fed by TMA, bf16 only, k in {1,2,3}, stride in {1,2}
+ *   (k=2 requires stride 2 pad 0: the space_to_depth + 1x1 fold, block.py:4069 + :222).
+ *   w: [Cout][Kpad] bf16, K-major, k index = tap*Cin + cin, zero padded to Kpad (lpc_conv2d_tc_kpad).
+ *   Requires Cin % 16 == 0, Cout % 16 == 0, x_ld % 8 == 0, 16-byte aligned pointers.
+ */
+int lpc_conv2d_direct(int dtype, const void* x, int x_ld, int B, int H, int W, int Cin,
+                      const void* w, const float* bias, int k, int stride, int pad, int Cout,
+                      void* y, int y_ld, int act, const float* chan_scale,
+                      const void* res, int res_ld, void* stream);
+int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int Cin,
+                  const void* w, const float* bias, int k, int stride, int pad, int Cout,
+                  void* y, int y_ld, int act, const float* chan_scale,
+                  const void* res, int res_ld, void* stream);
+/* K padding rule of the tcgen05 weight layout; returns Kpad (multiple of 64) or <0. */
+int lpc_conv2d_tc_kpad(int Cin, int k);
+/* 1 if lpc_conv2d_tc accepts this shape, else 0. */
+int lpc_conv2d_tc_supported(int Cin, int Cout, int k, int stride, int pad, int x_ld, int y_ld);
+
+/* ---- depthwise convolution ---------------------------------------------------------------------
+ * groups == C convs: CIB / RepVGGDW (block.py:700-756; the 3x3 branch is merged into the 7x7 on the
+ * host as RepVGGDW.fuse does, :714-733), SCDown.cv2 (:822), Attention.pe (:780), LPC.cv2 5x5 (:5806),
+ * SPCA dilated 3x3 d=1,2,3 (:5728-5731), v10Detect cls branch (head.py:504-505).
+ * w: [k*k][C] fp32; bias [C] fp32 or NULL; k in {3,5,7}; stride in {1,2}; C % 8 == 0. */
+int lpc_dwconv2d(int dtype, const void* x, int x_ld, int B, int H, int W, int C,
+                 const float* w, const float* bias, int k, int stride, int pad, int dil,
+                 void* y, int y_ld, int act, const void* res, int res_ld, void* stream);
+
+/* ---- SPPF pooling (block.py:171-176): y[:, 0:C]=m(x), [C:2C]=m(m(x)), [2C:3C]=m(m(m(x))) with
+ * m = MaxPool2d(5,1,2), computed in one pass as 5x5 / 9x9 / 13x13 windows (-inf padding). */
+int lpc_sppf_pool(int dtype, const void* x, int x_ld, int B, int H, int W, int C,
+                  void* y, int y_ld, void* stream);
+
+/* ---- PSA attention core (block.py:783-793): out[n, i, h*hd+d] = sum_j softmax_j(scale q_i.k_j) v[j,d].
+ * qkv holds, per pixel, [q: heads*kd | k: heads*kd | v: heads*hd] (the host permutes the qkv conv's
+ * output channels from the reference's per-head interleave, block.py:787). N = H*W tokens. */
+int lpc_psa_attention(int dtype, const void* qkv, int qkv_ld, int B, int N, int heads, int kd, int hd,
+                      void* out, int out_ld, void* stream);
+
+/* ---- neck glue (nn.Upsample(None,2,'nearest'), Concat conv.py:331, space_to_depth block.py:4069,
+ * LPC channel de-interleave block.py:5819-5825) */
+int lpc_upsample2x(int dtype, const void* x, int x_ld, int B, int H, int W, int C, void* y, int y_ld, void* stream);
+int lpc_copy_channels(int dtype, const void* x, int x_ld, long long npix, int C, void* y, int y_ld, void* stream);
+int lpc_space_to_depth(int dtype, const void* x, int x_ld, int B, int H, int W, int C, void* y, int y_ld, void* stream);
+int lpc_channel_deinterleave(int dtype, const void* x, int x_ld, long long npix, int C, void* y, int y_ld, void* stream);
+/* fp32 NCHW image batch -> NHWC view (channels c >= C zero filled up to Cpad). predictor.py:115-133. */
+int lpc_pack_input(int dtype, const float* x_nchw, int B, int C, int H, int W, void* y, int y_ld, int Cpad, void* stream);
+
+/* ---- CBAM / SPCA pooled gates (conv.py:278-320, block.py:5735-5747) */
+int lpc_global_avgpool(int dtype, const void* x, int x_ld, int B, int HW, int C, float* out, void* stream);
+/* out[b] = act2(W2 . act1(W1 . in[b] + b1) + b2); W2 may be NULL (single layer). W row-major [Cout][Cin]. */
+int lpc_channel_mlp(const float* in, int B, int C0, const float* W1, const float* b1, int C1, int act1,
+                    const float* W2, const float* b2, int C2, int act2, float* out, void* stream);
+/* stats[b,p,0] = mean_c(x*ca), stats[b,p,1] = max_c(x*ca) */
+int lpc_cbam_stats(int dtype, const void* x, int x_ld, int B, int HW, int C, const float* ca, float* stats, void* stream);
+/* y = x * ca * sigmoid(conv_kxk(stats, w)) ; w: [2][k][k] fp32 (cin-major as nn.Conv2d(2,1,k)) */
+int lpc_cbam_apply(int dtype, const void* x, int x_ld, int B, int H, int W, int C, const float* ca,
+                   const float* stats, const float* w, int k, void* y, int y_ld, void* stream);
+
+/* ---- v10Detect tail ------------------------------------------------------------------------------
+ * raw[l]: level-l head map, NHWC view with 4*16 box-distribution channels then nc class logits
+ * (head.py:76 cat order); level l has (H0>>l) x (W0>>l) cells and stride strides[l].
+ *
+ * lpc_v10_decode: Detect.inference (head.py:45-71) = DFL (block.py:57-60) + make_anchors
+ *   (utils/tal.py:294-306) + dist2bbox xywh (tal.py:309-319) + sigmoid -> y[B][4+nc][A] fp32.
+ * lpc_v10_decode_topk: the same fused with ops.v10postprocess (utils/ops.py:851-864), xywh2xyxy
+ *   (ops.py:402-421) and clip_boxes (ops.py:305-324; skipped when img_h<=0):
+ *   dets[B][K][6] = x1,y1,x2,y2,score,label sorted by score desc; anchor_idx[B][K] (may be NULL).
+ *   Ties in score are ordered by ascending (anchor*nc + class).  Requires A*nc >= K, K <= 1024.
+ * lpc_v10_postprocess: ops.v10postprocess on an already decoded preds[B][A][4+nc] fp32 tensor with
+ *   arbitrary strides (elements): boxes[B][K][4] (gathered, unchanged), scores[B][K], labels[B][K] i64.
+ */
+size_t lpc_v10_topk_workspace_bytes(int B, int A, int K);
+int lpc_v10_decode(int dtype, const void* raw0, const void* raw1, const void* raw2, int ld,
+                   int B, int H0, int W0, int nc, const float* strides3_host, float* y, void* stream);
+int lpc_v10_decode_topk(int dtype, const void* raw0, const void* raw1, const void* raw2, int ld,
+                        int B, int H0, int W0, int nc, const float* strides3_host, int K,
+                        int img_h, int img_w, void* workspace, size_t ws_bytes,
+                        float* dets, int* anchor_idx, void* stream);
+int lpc_v10_postprocess(const float* preds, long long stride_b, long long stride_a, long long stride_c,
+                        int B, int A, int nc, int K, void* workspace, size_t ws_bytes,
+                        float* boxes, float* scores, long long* labels, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LPCYOLO_H_ */

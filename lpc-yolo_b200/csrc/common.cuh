@@ -1,0 +1,118 @@
+// common.cuh - shared device/host helpers for liblpcyolo (sm_100a).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/lpcyolo.h"
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing -------------------------------------------------------------------------------
+void lpc_set_error(const char* fmt, ...);
+#define LPC_FAIL(code, ...)      \
+  do {                           \
+    lpc_set_error(__VA_ARGS__);  \
+    return (code);               \
+  } while (0)
+#define LPC_REQUIRE(cond, ...)                  \
+  do {                                          \
+    if (!(cond)) LPC_FAIL(LPC_E_ARG, __VA_ARGS__); \
+  } while (0)
+void lpc_count_launch();
+#define LPC_CHECK_LAUNCH(name)                                                            \
+  do {                                                                                    \
+    lpc_count_launch();                                                                   \
+    cudaError_t e__ = cudaGetLastError();                                                 \
+    if (e__ != cudaSuccess) LPC_FAIL(LPC_E_CUDA, "%s: %s", name, cudaGetErrorString(e__)); \
+  } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- scalar conversions ---------------------------------------------------------------------------
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// ---- 16-byte vectors: 8 bf16 or 4 float --------------------------------------------------------------
+template <typename T> struct Vec;
+template <> struct Vec<bf16> {
+  static constexpr int N = 8;
+  uint4 raw;
+  __device__ __forceinline__ void unpack(float* f) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 t = __bfloat1622float2(h[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+  __device__ __forceinline__ void pack(const float* f) {
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  }
+};
+template <> struct Vec<float> {
+  static constexpr int N = 4;
+  uint4 raw;
+  __device__ __forceinline__ void unpack(float* f) const {
+    const float* p = reinterpret_cast<const float*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) f[i] = p[i];
+  }
+  __device__ __forceinline__ void pack(const float* f) {
+    float* p = reinterpret_cast<float*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = f[i];
+  }
+};
+template <typename T> __device__ __forceinline__ Vec<T> ldg_vec(const T* p) {
+  Vec<T> v;
+  v.raw = __ldg(reinterpret_cast<const uint4*>(p));
+  return v;
+}
+template <typename T> __device__ __forceinline__ Vec<T> ld_vec(const T* p) {
+  Vec<T> v;
+  v.raw = *reinterpret_cast<const uint4*>(p);
+  return v;
+}
+template <typename T> __device__ __forceinline__ void st_vec(T* p, const Vec<T>& v) {
+  *reinterpret_cast<uint4*>(p) = v.raw;
+}
+
+// ---- activations -------------------------------------------------------------------------------------
+// PRECISE=true (fp32 validation mode): expf + IEEE division.  PRECISE=false (bf16 mode): ex2.approx /
+// rcp.approx, ~2 ulp, far below bf16 rounding.
+template <bool PRECISE> __device__ __forceinline__ float exp_(float x) { return PRECISE ? expf(x) : __expf(x); }
+template <bool PRECISE> __device__ __forceinline__ float div_(float a, float b) { return PRECISE ? a / b : __fdividef(a, b); }
+
+template <bool PRECISE> __device__ __forceinline__ float sigmoid_(float x) {
+  return div_<PRECISE>(1.0f, 1.0f + exp_<PRECISE>(-x));
+}
+template <bool PRECISE> __device__ __forceinline__ float silu_(float x) {
+  return div_<PRECISE>(x, 1.0f + exp_<PRECISE>(-x));
+}
+// mish(x) = x*tanh(softplus(x)) = x*n/(n+2) with n = e^x (e^x + 2)   (one exp, one divide)
+template <bool PRECISE> __device__ __forceinline__ float mish_(float x) {
+  if (x > 20.0f) return x;
+  float e = exp_<PRECISE>(x);
+  float n = e * (e + 2.0f);
+  return x * div_<PRECISE>(n, n + 2.0f);
+}
+template <bool PRECISE> __device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case LPC_ACT_SILU: return silu_<PRECISE>(v);
+    case LPC_ACT_MISH: return mish_<PRECISE>(v);
+    case LPC_ACT_SIGMOID: return sigmoid_<PRECISE>(v);
+    case LPC_ACT_RELU: return fmaxf(v, 0.0f);
+    default: return v;
+  }
+}
+template <typename T> struct Precise { static constexpr bool value = false; };
+template <> struct Precise<float> { static constexpr bool value = true; };

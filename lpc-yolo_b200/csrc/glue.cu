@@ -1,0 +1,292 @@
+// glue.cu - bandwidth-bound neck glue and pooled-attention gates (NHWC, 128-bit vector accesses).
+//   upsample2x / copy_channels / space_to_depth / channel_deinterleave / pack_input      (K7)
+//   global_avgpool / channel_mlp / cbam_stats / cbam_apply                              (K8)
+#include "common.cuh"
+
+namespace {
+
+// y[n, y, x, :] = x[n, y/2, x/2, :]
+template <typename T>
+__global__ void upsample2x_kernel(const T* __restrict__ x, int x_ld, int B, int H, int W, int C, T* __restrict__ y, int y_ld) {
+  constexpr int V = Vec<T>::N;
+  const int cvecs = C / V;
+  const long long total = (long long)B * H * W * cvecs;  // one thread per INPUT vector, writes 4 outputs
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cv = (int)(idx % cvecs);
+  long long p = idx / cvecs;
+  const int ix = (int)(p % W);
+  long long t = p / W;
+  const int iy = (int)(t % H);
+  const int n = (int)(t / H);
+  Vec<T> v = ldg_vec<T>(x + p * x_ld + cv * V);
+  const int Wo = 2 * W;
+  T* o = y + (((long long)n * 2 * H + 2 * iy) * Wo + 2 * ix) * y_ld + cv * V;
+  st_vec<T>(o, v);
+  st_vec<T>(o + y_ld, v);
+  st_vec<T>(o + (long long)Wo * y_ld, v);
+  st_vec<T>(o + (long long)Wo * y_ld + y_ld, v);
+}
+
+template <typename T>
+__global__ void copy_channels_kernel(const T* __restrict__ x, int x_ld, long long npix, int C, T* __restrict__ y, int y_ld) {
+  constexpr int V = Vec<T>::N;
+  const int cvecs = C / V;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= npix * cvecs) return;
+  const int cv = (int)(idx % cvecs);
+  const long long p = idx / cvecs;
+  st_vec<T>(y + p * y_ld + cv * V, ldg_vec<T>(x + p * x_ld + cv * V));
+}
+
+// out[n, oy, ox, q*C + c] = x[n, 2*oy + (q&1), 2*ox + (q>>1), c]   q = 0..3
+// (block.py:4070: [::2,::2], [1::2,::2], [::2,1::2], [1::2,1::2] -> row parity varies fastest)
+template <typename T>
+__global__ void space_to_depth_kernel(const T* __restrict__ x, int x_ld, int B, int H, int W, int C, T* __restrict__ y, int y_ld) {
+  constexpr int V = Vec<T>::N;
+  const int cvecs = C / V;
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)B * Ho * Wo * 4 * cvecs;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cv = (int)(idx % cvecs);
+  long long t = idx / cvecs;
+  const int q = (int)(t & 3);
+  t >>= 2;
+  const int ox = (int)(t % Wo);
+  t /= Wo;
+  const int oy = (int)(t % Ho);
+  const int n = (int)(t / Ho);
+  const int iy = 2 * oy + (q & 1), ix = 2 * ox + (q >> 1);
+  Vec<T> v = ldg_vec<T>(x + ((long long)(n * H + iy) * W + ix) * x_ld + cv * V);
+  st_vec<T>(y + ((long long)(n * Ho + oy) * Wo + ox) * y_ld + q * C + cv * V, v);
+}
+
+// y[p, j] = x[p, 2j], y[p, C/2 + j] = x[p, 2j+1]
+template <typename T>
+__global__ void deinterleave_kernel(const T* __restrict__ x, int x_ld, long long npix, int C, T* __restrict__ y, int y_ld) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= npix * C) return;
+  const int c = (int)(idx % C);
+  const long long p = idx / C;
+  const int src = c < C / 2 ? 2 * c : 2 * (c - C / 2) + 1;
+  y[p * y_ld + c] = x[p * x_ld + src];
+}
+
+template <typename T>
+__global__ void pack_input_kernel(const float* __restrict__ x, int B, int C, int H, int W, T* __restrict__ y, int y_ld, int Cpad) {
+  const long long total = (long long)B * H * W;
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= total) return;
+  const long long hw = (long long)H * W;
+  const int n = (int)(p / hw);
+  const long long r = p - n * hw;
+  for (int c = 0; c < Cpad; ++c) {
+    float v = c < C ? __ldg(x + ((long long)n * C + c) * hw + r) : 0.f;
+    y[p * y_ld + c] = from_f<T>(v);
+  }
+}
+
+// out[b, c] = mean over HW.  grid (C/32 rounded, B): block 256 = 8 pixel lanes x 32 channels.
+template <typename T>
+__global__ void global_avgpool_kernel(const T* __restrict__ x, int x_ld, int HW, int C, float* __restrict__ out) {
+  __shared__ float part[8][33];
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int lane_p = threadIdx.x >> 5;
+  float s = 0.f;
+  if (c < C) {
+    const T* base = x + (long long)b * HW * x_ld + c;
+    for (int p = lane_p; p < HW; p += 8) s += to_f(base[(long long)p * x_ld]);
+  }
+  part[lane_p][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (threadIdx.x < 32 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x];
+    out[(long long)b * C + c] = t / (float)HW;
+  }
+}
+
+// tiny per-image MLP on pooled vectors; one block per image.
+__global__ void channel_mlp_kernel(const float* __restrict__ in, int C0, const float* __restrict__ W1,
+                                   const float* __restrict__ b1, int C1, int act1, const float* __restrict__ W2,
+                                   const float* __restrict__ b2, int C2, int act2, float* __restrict__ out) {
+  extern __shared__ float sm[];
+  float* v0 = sm;
+  float* v1 = sm + C0;
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < C0; i += blockDim.x) v0[i] = in[(long long)b * C0 + i];
+  __syncthreads();
+  for (int o = threadIdx.x; o < C1; o += blockDim.x) {
+    float s = b1 ? b1[o] : 0.f;
+    const float* wr = W1 + (long long)o * C0;
+    for (int i = 0; i < C0; ++i) s = fmaf(wr[i], v0[i], s);
+    s = apply_act<true>(s, act1);
+    if (W2) v1[o] = s; else out[(long long)b * C1 + o] = s;
+  }
+  if (!W2) return;
+  __syncthreads();
+  for (int o = threadIdx.x; o < C2; o += blockDim.x) {
+    float s = b2 ? b2[o] : 0.f;
+    const float* wr = W2 + (long long)o * C1;
+    for (int i = 0; i < C1; ++i) s = fmaf(wr[i], v1[i], s);
+    out[(long long)b * C2 + o] = apply_act<true>(s, act2);
+  }
+}
+
+// one warp per pixel: mean_c and max_c of x*ca
+template <typename T>
+__global__ void cbam_stats_kernel(const T* __restrict__ x, int x_ld, int B, int HW, int C, const float* __restrict__ ca,
+                                  float* __restrict__ stats) {
+  const long long gp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gp >= (long long)B * HW) return;
+  const int b = (int)(gp / HW);
+  const T* px = x + gp * x_ld;
+  const float* cab = ca + (long long)b * C;
+  float s = 0.f, m = -INFINITY;
+  for (int c = lane; c < C; c += 32) {
+    float v = to_f(px[c]) * cab[c];
+    s += v;
+    m = fmaxf(m, v);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  }
+  if (lane == 0) {
+    stats[gp * 2] = s / (float)C;
+    stats[gp * 2 + 1] = m;
+  }
+}
+
+// one warp per pixel: gate = sigmoid(conv_kxk(stats)); y = x*ca*gate
+template <typename T>
+__global__ void cbam_apply_kernel(const T* __restrict__ x, int x_ld, int B, int H, int W, int C, const float* __restrict__ ca,
+                                  const float* __restrict__ stats, const float* __restrict__ w, int k,
+                                  T* __restrict__ y, int y_ld) {
+  const long long gp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long HW = (long long)H * W;
+  if (gp >= (long long)B * HW) return;
+  const int b = (int)(gp / HW);
+  const int r = (int)(gp - (long long)b * HW);
+  const int oy = r / W, ox = r - oy * W;
+  const int pad = k / 2;
+  float s = 0.f;
+  for (int t = lane; t < k * k; t += 32) {
+    const int ky = t / k, kx = t - ky * k;
+    const int iy = oy - pad + ky, ix = ox - pad + kx;
+    if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+    const float* st = stats + ((long long)b * HW + (long long)iy * W + ix) * 2;
+    s = fmaf(st[0], w[t], s);
+    s = fmaf(st[1], w[k * k + t], s);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float gate = sigmoid_<true>(s);
+  const T* px = x + gp * x_ld;
+  T* py = y + gp * y_ld;
+  const float* cab = ca + (long long)b * C;
+  for (int c = lane; c < C; c += 32) py[c] = from_f<T>(to_f(px[c]) * cab[c] * gate);
+}
+
+template <typename T> int vec_of() { return Vec<T>::N; }
+
+}  // namespace
+
+#define DISPATCH_T(dtype, CALL_F32, CALL_BF16, name)                   \
+  if ((dtype) == LPC_F32) { CALL_F32; }                                \
+  else if ((dtype) == LPC_BF16) { CALL_BF16; }                         \
+  else LPC_FAIL(LPC_E_ARG, name ": unknown dtype %d", (dtype));        \
+  LPC_CHECK_LAUNCH(name);                                              \
+  return LPC_OK;
+
+static int check_vec(const char* name, int dtype, int C, int x_ld, int y_ld, const void* x, const void* y) {
+  const int V = dtype == LPC_F32 ? 4 : 8;
+  if (C % V || x_ld % V || y_ld % V) LPC_FAIL(LPC_E_ARG, "%s: C and pitches must be multiples of %d", name, V);
+  if (!aligned16(x) || !aligned16(y)) LPC_FAIL(LPC_E_ARG, "%s: pointers must be 16-byte aligned", name);
+  if (!x || !y) LPC_FAIL(LPC_E_ARG, "%s: null pointer", name);
+  return LPC_OK;
+}
+
+extern "C" int lpc_upsample2x(int dtype, const void* x, int x_ld, int B, int H, int W, int C, void* y, int y_ld, void* stream) {
+  if (int e = check_vec("upsample2x", dtype, C, x_ld, y_ld, x, y)) return e;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int V = dtype == LPC_F32 ? 4 : 8;
+  const int g = cdiv((long long)B * H * W * (C / V), 256);
+  DISPATCH_T(dtype, (upsample2x_kernel<float><<<g, 256, 0, s>>>((const float*)x, x_ld, B, H, W, C, (float*)y, y_ld)),
+             (upsample2x_kernel<bf16><<<g, 256, 0, s>>>((const bf16*)x, x_ld, B, H, W, C, (bf16*)y, y_ld)), "upsample2x")
+}
+
+extern "C" int lpc_copy_channels(int dtype, const void* x, int x_ld, long long npix, int C, void* y, int y_ld, void* stream) {
+  if (int e = check_vec("copy_channels", dtype, C, x_ld, y_ld, x, y)) return e;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int V = dtype == LPC_F32 ? 4 : 8;
+  const int g = cdiv(npix * (C / V), 256);
+  DISPATCH_T(dtype, (copy_channels_kernel<float><<<g, 256, 0, s>>>((const float*)x, x_ld, npix, C, (float*)y, y_ld)),
+             (copy_channels_kernel<bf16><<<g, 256, 0, s>>>((const bf16*)x, x_ld, npix, C, (bf16*)y, y_ld)), "copy_channels")
+}
+
+extern "C" int lpc_space_to_depth(int dtype, const void* x, int x_ld, int B, int H, int W, int C, void* y, int y_ld, void* stream) {
+  if (int e = check_vec("space_to_depth", dtype, C, x_ld, y_ld, x, y)) return e;
+  LPC_REQUIRE(H % 2 == 0 && W % 2 == 0 && y_ld >= 4 * C, "space_to_depth: H, W must be even and y_ld >= 4C");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int V = dtype == LPC_F32 ? 4 : 8;
+  const int g = cdiv((long long)B * H * W * (C / V), 256);
+  DISPATCH_T(dtype, (space_to_depth_kernel<float><<<g, 256, 0, s>>>((const float*)x, x_ld, B, H, W, C, (float*)y, y_ld)),
+             (space_to_depth_kernel<bf16><<<g, 256, 0, s>>>((const bf16*)x, x_ld, B, H, W, C, (bf16*)y, y_ld)), "space_to_depth")
+}
+
+extern "C" int lpc_channel_deinterleave(int dtype, const void* x, int x_ld, long long npix, int C, void* y, int y_ld, void* stream) {
+  LPC_REQUIRE(x && y && C % 2 == 0 && x_ld >= C && y_ld >= C, "channel_deinterleave: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int g = cdiv(npix * C, 256);
+  DISPATCH_T(dtype, (deinterleave_kernel<float><<<g, 256, 0, s>>>((const float*)x, x_ld, npix, C, (float*)y, y_ld)),
+             (deinterleave_kernel<bf16><<<g, 256, 0, s>>>((const bf16*)x, x_ld, npix, C, (bf16*)y, y_ld)), "channel_deinterleave")
+}
+
+extern "C" int lpc_pack_input(int dtype, const float* x, int B, int C, int H, int W, void* y, int y_ld, int Cpad, void* stream) {
+  LPC_REQUIRE(x && y && C > 0 && Cpad >= C && y_ld >= Cpad, "pack_input: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int g = cdiv((long long)B * H * W, 256);
+  DISPATCH_T(dtype, (pack_input_kernel<float><<<g, 256, 0, s>>>(x, B, C, H, W, (float*)y, y_ld, Cpad)),
+             (pack_input_kernel<bf16><<<g, 256, 0, s>>>(x, B, C, H, W, (bf16*)y, y_ld, Cpad)), "pack_input")
+}
+
+extern "C" int lpc_global_avgpool(int dtype, const void* x, int x_ld, int B, int HW, int C, float* out, void* stream) {
+  LPC_REQUIRE(x && out && B > 0 && HW > 0 && C > 0 && x_ld >= C, "global_avgpool: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 g(cdiv(C, 32), B);
+  DISPATCH_T(dtype, (global_avgpool_kernel<float><<<g, 256, 0, s>>>((const float*)x, x_ld, HW, C, out)),
+             (global_avgpool_kernel<bf16><<<g, 256, 0, s>>>((const bf16*)x, x_ld, HW, C, out)), "global_avgpool")
+}
+
+extern "C" int lpc_channel_mlp(const float* in, int B, int C0, const float* W1, const float* b1, int C1, int act1,
+                               const float* W2, const float* b2, int C2, int act2, float* out, void* stream) {
+  LPC_REQUIRE(in && W1 && out && B > 0 && C0 > 0 && C1 > 0, "channel_mlp: bad argument");
+  LPC_REQUIRE((size_t)(C0 + C1) * 4 <= 48 * 1024, "channel_mlp: vectors too large");
+  channel_mlp_kernel<<<B, 256, (size_t)(C0 + C1) * 4, (cudaStream_t)stream>>>(in, C0, W1, b1, C1, act1, W2, b2, C2, act2, out);
+  LPC_CHECK_LAUNCH("channel_mlp");
+  return LPC_OK;
+}
+
+extern "C" int lpc_cbam_stats(int dtype, const void* x, int x_ld, int B, int HW, int C, const float* ca, float* stats, void* stream) {
+  LPC_REQUIRE(x && ca && stats && x_ld >= C, "cbam_stats: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int g = cdiv((long long)B * HW * 32, 256);
+  DISPATCH_T(dtype, (cbam_stats_kernel<float><<<g, 256, 0, s>>>((const float*)x, x_ld, B, HW, C, ca, stats)),
+             (cbam_stats_kernel<bf16><<<g, 256, 0, s>>>((const bf16*)x, x_ld, B, HW, C, ca, stats)), "cbam_stats")
+}
+
+extern "C" int lpc_cbam_apply(int dtype, const void* x, int x_ld, int B, int H, int W, int C, const float* ca,
+                              const float* stats, const float* w, int k, void* y, int y_ld, void* stream) {
+  LPC_REQUIRE(x && ca && stats && w && y && (k == 3 || k == 7), "cbam_apply: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int g = cdiv((long long)B * H * W * 32, 256);
+  DISPATCH_T(dtype, (cbam_apply_kernel<float><<<g, 256, 0, s>>>((const float*)x, x_ld, B, H, W, C, ca, stats, w, k, (float*)y, y_ld)),
+             (cbam_apply_kernel<bf16><<<g, 256, 0, s>>>((const bf16*)x, x_ld, B, H, W, C, ca, stats, w, k, (bf16*)y, y_ld)), "cbam_apply")
+}

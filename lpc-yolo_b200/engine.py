@@ -1,0 +1,235 @@
+"""Predict engine: the counterpart of the reference's ``YOLO(...).predict`` call chain for tensor sources
+(engine/model.py:385 ``Model.predict`` -> engine/predictor.py:208 ``stream_inference`` ->
+models/yolov10/predict.py:8 ``YOLOv10DetectionPredictor.postprocess`` -> engine/results.py ``Results``).
+
+Kept: argument names and defaults (conf=0.25, max_det=300, classes, half, device, verbose), the three stage
+timers reported in ``Results.speed`` (utils/ops.py:18-63 ``Profile``), the predictor callbacks, ``LoadTensor``'s
+input validation (data/loaders.py:441-502), ``Results.boxes.data`` = [n,6] (xyxy, conf, cls) on the device.
+
+Changed on purpose: the whole post-processing is one fused kernel pair and ONE host sync per batch (the
+reference syncs once per image, predict.py:27); ``Results.orig_img`` is converted to a uint8 HWC array lazily
+instead of copying the whole batch to the host on every call (predict.py:29-30).
+"""
+import time
+from collections import defaultdict
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from . import functional as F
+from .nn.tasks import YOLOv10DetectionModel
+
+DEFAULTS = dict(conf=0.25, max_det=300, classes=None, half=True, device=None, verbose=False, imgsz=640, batch=1,
+                augment=False, visualize=False, embed=None, stream=False, fp32=False)
+CALLBACK_EVENTS = ("on_predict_start", "on_predict_batch_start", "on_predict_postprocess_end", "on_predict_batch_end",
+                   "on_predict_end")
+
+
+class Profile:
+    """utils/ops.py:18-63: wall-clock stage timer with a device sync on both edges."""
+
+    def __init__(self, device=None):
+        self.t, self.dt, self.device = 0.0, 0.0, device
+
+    def __enter__(self):
+        self.start = self._time()
+        return self
+
+    def __exit__(self, *a):
+        self.dt = self._time() - self.start
+        self.t += self.dt
+
+    def _time(self):
+        if self.device is not None and torch.cuda.is_available():
+            torch.cuda.synchronize(self.device)
+        return time.time()
+
+
+class Boxes:
+    """engine/results.py Boxes: ``data`` [n,6] = x1,y1,x2,y2,conf,cls."""
+
+    def __init__(self, boxes, orig_shape):
+        assert boxes.shape[-1] == 6
+        self.data, self.orig_shape = boxes, orig_shape
+
+    xyxy = property(lambda s: s.data[:, :4])
+    conf = property(lambda s: s.data[:, 4])
+    cls = property(lambda s: s.data[:, 5])
+
+    @property
+    def xywh(self):
+        b = self.data[:, :4]
+        return torch.stack(((b[:, 0] + b[:, 2]) / 2, (b[:, 1] + b[:, 3]) / 2, b[:, 2] - b[:, 0], b[:, 3] - b[:, 1]), -1)
+
+    def __len__(self):
+        return self.data.shape[0]
+
+    def cpu(self):
+        return Boxes(self.data.cpu(), self.orig_shape)
+
+    def numpy(self):
+        return Boxes(self.data.cpu().numpy(), self.orig_shape)
+
+
+class Results:
+    """engine/results.py Results (detection fields only)."""
+
+    def __init__(self, orig_img, path, names, boxes=None):
+        self._orig = orig_img
+        self.orig_shape = tuple(orig_img.shape[-2:]) if torch.is_tensor(orig_img) else orig_img.shape[:2]
+        self.boxes = Boxes(boxes, self.orig_shape) if boxes is not None else None
+        self.names, self.path, self.speed = names, path, {"preprocess": None, "inference": None, "postprocess": None}
+
+    @property
+    def orig_img(self):
+        """uint8 HWC array as ops.convert_torch2numpy_batch (utils/ops.py:826-836) yields, built on demand."""
+        if torch.is_tensor(self._orig):
+            self._orig = (self._orig.permute(1, 2, 0).contiguous() * 255).clamp(0, 255).to(torch.uint8).cpu().numpy()
+        return self._orig
+
+    def __len__(self):
+        return len(self.boxes) if self.boxes is not None else 0
+
+
+def check_tensor_source(im, stride=32):
+    """data/loaders.py:463-487 LoadTensor._single_check."""
+    s = (f"torch.Tensor inputs should be BCHW i.e. shape(1, 3, 640, 640) divisible by stride {stride}. "
+         f"Input shape{tuple(im.shape)} is incompatible.")
+    if im.dim() != 4:
+        if im.dim() != 3:
+            raise ValueError(s)
+        im = im.unsqueeze(0)
+    if im.shape[2] % stride or im.shape[3] % stride:
+        raise ValueError(s)
+    return im
+
+
+class YOLOv10DetectionPredictor:
+    """engine/predictor.py BasePredictor + models/yolov10/predict.py for tensor sources."""
+
+    def __init__(self, overrides=None, _callbacks=None):
+        a = dict(DEFAULTS)
+        a.update(overrides or {})
+        self.args = SimpleNamespace(**a)
+        self.model = None
+        self.device = None
+        self.callbacks = _callbacks or defaultdict(list)
+        self.results = None
+        self.batch = None
+
+    def run_callbacks(self, event):
+        for cb in self.callbacks.get(event, []):
+            cb(self)
+
+    def add_callback(self, event, func):
+        self.callbacks[event].append(func)
+
+    def setup_model(self, model):
+        """predictor.py:295-310 / autobackend.py:141-151: move, 'fuse' (pack), pick the compute dtype.
+        ``half=True`` selects bf16 (the reference's switch means fp16; it has no bf16 switch)."""
+        dev = self.args.device
+        self.device = torch.device(dev if dev is not None else "cuda:0") if not isinstance(dev, torch.device) else dev
+        if self.device.type != "cuda":
+            raise F.LpcError("lpc-yolo_b200 predicts on CUDA devices only (no CPU fallback)")
+        self.model = model.to(self.device).eval()
+        self.model.compute_dtype = torch.float32 if (self.args.fp32 or not self.args.half) else torch.bfloat16
+        self.model.fuse()
+
+    def preprocess(self, im):
+        """predictor.py:115-133 for tensors: move to the device (no /255 for tensors)."""
+        im = check_tensor_source(im)
+        if not im.is_cuda:
+            im = (im.pin_memory() if not im.is_pinned() else im).to(self.device, non_blocking=True)
+        return im.float() if im.dtype != torch.float32 else im
+
+    def inference(self, im):
+        """predictor.py:135-142: backbone + neck + one2one head + fused decode/top-k -> [B,K,6]."""
+        return self.model.detect(im, self.args.max_det, clip=True)
+
+    def postprocess(self, preds, img, orig_imgs):
+        """models/yolov10/predict.py:22-38: confidence / class filter, wrap in Results.  preds are already
+        [B,K,6] xyxy (the export-mode contract, head.py:521-523), clipped to the image (scale_boxes is the
+        identity + clip when source and network sizes agree)."""
+        B = preds.shape[0]
+        if self.args.classes is None:
+            counts = (preds[..., 4] > self.args.conf).sum(1).tolist()        # scores are sorted: a prefix survives
+            per_img = [preds[i, :n] for i, n in enumerate(counts)]
+        else:
+            cls = torch.tensor(self.args.classes, device=preds.device, dtype=preds.dtype)
+            mask = (preds[..., 4] > self.args.conf) & (preds[..., 5:6] == cls.unsqueeze(0)).any(2)
+            per_img = [p[mask[i]] for i, p in enumerate(preds)]
+        names = self.model.names
+        return [Results(orig_imgs[i], f"image{i}.jpg", names, boxes=per_img[i]) for i in range(B)]
+
+    def __call__(self, source):
+        if self.model is None:
+            raise RuntimeError("setup_model() first")
+        self.run_callbacks("on_predict_start")
+        profilers = (Profile(self.device), Profile(self.device), Profile(self.device))
+        self.batch = source
+        self.run_callbacks("on_predict_batch_start")
+        with torch.no_grad():
+            with profilers[0]:
+                im = self.preprocess(source)
+            with profilers[1]:
+                preds = self.inference(im)
+            with profilers[2]:
+                self.results = self.postprocess(preds, im, im)
+        self.run_callbacks("on_predict_postprocess_end")
+        n = len(self.results)
+        for r in self.results:
+            r.speed = {"preprocess": profilers[0].dt * 1e3 / n, "inference": profilers[1].dt * 1e3 / n,
+                       "postprocess": profilers[2].dt * 1e3 / n}
+        self.run_callbacks("on_predict_batch_end")
+        self.run_callbacks("on_predict_end")
+        return self.results
+
+
+class YOLO:
+    """models/yolo/model.py:11 YOLO / models/yolov10/model.py:10 YOLOv10 facade, predict side."""
+
+    def __init__(self, model="yolov10n.yaml", task=None, verbose=False):
+        self.task = task or "detect"
+        self.overrides = {}
+        self.callbacks = defaultdict(list)
+        self.predictor = None
+        if isinstance(model, torch.nn.Module):
+            self.model = model
+        else:
+            if not str(model).endswith((".yaml", ".yml")):
+                raise NotImplementedError("only model YAMLs are loadable in this round (weights come via load_state_dict)")
+            self.model = YOLOv10DetectionModel(model, verbose=verbose)
+        self.names = self.model.names
+
+    def add_callback(self, event, func):
+        self.callbacks[event].append(func)
+
+    def load_state_dict(self, sd, strict=True):
+        return self.model.load_state_dict(sd, strict=strict)
+
+    def fuse(self):
+        self.model.fuse()
+        return self
+
+    def info(self, detailed=False, verbose=True):
+        return self.model.info(detailed, verbose)
+
+    def predict(self, source=None, stream=False, predictor=None, **kwargs):
+        """engine/model.py:385-441: defaults conf=0.25, then user kwargs."""
+        unknown = set(kwargs) - set(DEFAULTS)
+        if unknown:  # cfg/__init__.py:302-325 check_dict_alignment raises SyntaxError on unknown keys
+            raise SyntaxError(f"'{sorted(unknown)}' are not valid predict() arguments")
+        if not torch.is_tensor(source):
+            raise NotImplementedError("this round handles torch.Tensor sources [B,3,H,W] in [0,1] (LoadTensor contract)")
+        args = {**self.overrides, **kwargs}
+        if self.predictor is None or args != getattr(self, "_last_args", None):
+            self.predictor = (predictor or YOLOv10DetectionPredictor)(overrides=args, _callbacks=self.callbacks)
+            self.predictor.setup_model(self.model)
+            self._last_args = dict(args)
+        return self.predictor(source)
+
+    __call__ = predict
+
+
+YOLOv10 = YOLO

@@ -1,0 +1,276 @@
+"""Tensor-level wrappers over the C ABI.
+
+Activations are torch CUDA tensors of LOGICAL shape [B,C,H,W] and PHYSICAL layout NHWC, possibly a
+channel slice of a wider buffer (``buf[:, c0:c1]``): the kernels take (pointer, pixel pitch).  Keeping the
+logical shape NCHW keeps every reference module signature unchanged.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ACT_MISH, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SILU, BF16, F32, LpcError, check  # noqa: F401
+
+_DT = {torch.bfloat16: BF16, torch.float32: F32}
+
+
+def dt_code(dtype):
+    try:
+        return _DT[dtype]
+    except KeyError:
+        raise LpcError(f"unsupported activation dtype {dtype}; use torch.bfloat16 or torch.float32") from None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def new_act(B, Cc, H, W, dtype, device):
+    """Fresh NHWC activation with logical NCHW shape."""
+    return torch.empty((B, H, W, Cc), dtype=dtype, device=device).permute(0, 3, 1, 2)
+
+
+def view_of(t):
+    """-> (data_ptr, pitch) after checking that ``t`` is an NHWC view (size-1 dims are unconstrained)."""
+    if not t.is_cuda:
+        raise LpcError("lpc-yolo_b200 ops run on CUDA tensors only (there is no CPU fallback)")
+    B, Cc, H, W = t.shape
+    sB, sC, sH, sW = t.stride()
+    if W > 1:
+        ld = sW
+    elif H > 1:
+        ld = sH
+    elif B > 1:
+        ld = sB
+    else:
+        ld = Cc
+    ok = (Cc == 1 or sC == 1) and (W == 1 or sW == ld) and (H == 1 or sH == W * ld) and (B == 1 or sB == H * W * ld) and ld >= Cc
+    if not ok:
+        raise LpcError(f"tensor of shape {tuple(t.shape)} / strides {t.stride()} is not an NHWC view")
+    return t.data_ptr(), ld
+
+
+def is_nhwc_view(t):
+    try:
+        view_of(t)
+        return True
+    except LpcError:
+        return False
+
+
+def as_act(x, dtype):
+    """Boundary conversion for tensors that arrive NCHW-contiguous (tests, user code)."""
+    if x.dtype == dtype and is_nhwc_view(x):
+        return x
+    if x.dim() == 4 and x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] <= 4:
+        return pack_input(x, dtype)
+    y = new_act(*x.shape[:1], x.shape[1], x.shape[2], x.shape[3], dtype, x.device)
+    y.copy_(x)
+    return y
+
+
+def _fp(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+# ---------------------------------------------------------------------------------------------------------
+def pack_input(x, dtype, cpad=4):
+    """fp32 NCHW image batch -> NHWC activation with C padded to ``cpad`` (logical C stays x.shape[1])."""
+    B, Cc, H, W = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    buf = torch.empty((B, H, W, cpad), dtype=dtype, device=x.device)
+    check(_lib.lib().lpc_pack_input(dt_code(dtype), _fp(x), B, Cc, H, W, _fp(buf), cpad, cpad, _stream()), "pack_input")
+    return buf.permute(0, 3, 1, 2)[:, :Cc]
+
+
+def conv2d(x, pc, out=None, res=None, chan_scale=None):
+    """Dense conv through a PackedConv ``pc`` (see pack.py). Chooses tcgen05 when the shape allows."""
+    B, Cin, H, W = x.shape
+    assert Cin == pc.cin, (Cin, pc.cin)
+    Ho = (H + 2 * pc.p - pc.k) // pc.s + 1
+    Wo = (W + 2 * pc.p - pc.k) // pc.s + 1
+    if out is None:
+        out = new_act(B, pc.cout, Ho, Wo, x.dtype, x.device)
+    assert tuple(out.shape) == (B, pc.cout, Ho, Wo), (tuple(out.shape), (B, pc.cout, Ho, Wo))
+    xp, xld = view_of(x)
+    yp, yld = view_of(out)
+    rp, rld = (0, 0) if res is None else view_of(res)
+    L = _lib.lib()
+    use_tc = (pc.w_tc is not None and x.dtype == torch.bfloat16 and xp % 16 == 0 and yp % 16 == 0 and rp % 16 == 0
+              and rld % 8 == 0 and L.lpc_conv2d_tc_supported(Cin, pc.cout, pc.k, pc.s, pc.p, xld, yld))
+    if use_tc:
+        check(L.lpc_conv2d_tc(xp, xld, B, H, W, Cin, _fp(pc.w_tc), _fp(pc.bias), pc.k, pc.s, pc.p, pc.cout, yp, yld,
+                              pc.act, _fp(chan_scale), rp or None, rld, _stream()), "conv2d_tc")
+    else:
+        check(L.lpc_conv2d_direct(dt_code(x.dtype), xp, xld, B, H, W, Cin, _fp(pc.w_direct), _fp(pc.bias), pc.k, pc.s,
+                                  pc.p, pc.cout, yp, yld, pc.act, _fp(chan_scale), rp or None, rld, _stream()),
+              "conv2d_direct")
+    return out
+
+
+def dwconv2d(x, pd, out=None, res=None):
+    B, Cc, H, W = x.shape
+    ke = pd.d * (pd.k - 1) + 1
+    Ho = (H + 2 * pd.p - ke) // pd.s + 1
+    Wo = (W + 2 * pd.p - ke) // pd.s + 1
+    if out is None:
+        out = new_act(B, Cc, Ho, Wo, x.dtype, x.device)
+    assert tuple(out.shape) == (B, Cc, Ho, Wo)
+    xp, xld = view_of(x)
+    yp, yld = view_of(out)
+    rp, rld = (0, 0) if res is None else view_of(res)
+    check(_lib.lib().lpc_dwconv2d(dt_code(x.dtype), xp, xld, B, H, W, Cc, _fp(pd.w), _fp(pd.bias), pd.k, pd.s, pd.p, pd.d,
+                                  yp, yld, pd.act, rp or None, rld, _stream()), "dwconv2d")
+    return out
+
+
+def sppf_pool(x, out):
+    """out (3C channels) <- [pool5(x), pool9(x), pool13(x)]."""
+    B, Cc, H, W = x.shape
+    assert out.shape[1] == 3 * Cc
+    xp, xld = view_of(x)
+    yp, yld = view_of(out)
+    check(_lib.lib().lpc_sppf_pool(dt_code(x.dtype), xp, xld, B, H, W, Cc, yp, yld, _stream()), "sppf_pool")
+    return out
+
+
+def psa_attention(qkv, heads, kd, hd, out=None):
+    B, Ct, H, W = qkv.shape
+    assert Ct == heads * (2 * kd + hd)
+    if out is None:
+        out = new_act(B, heads * hd, H, W, qkv.dtype, qkv.device)
+    xp, xld = view_of(qkv)
+    yp, yld = view_of(out)
+    check(_lib.lib().lpc_psa_attention(dt_code(qkv.dtype), xp, xld, B, H * W, heads, kd, hd, yp, yld, _stream()), "psa_attention")
+    return out
+
+
+def upsample2x(x, out=None):
+    B, Cc, H, W = x.shape
+    if out is None:
+        out = new_act(B, Cc, 2 * H, 2 * W, x.dtype, x.device)
+    assert tuple(out.shape) == (B, Cc, 2 * H, 2 * W)
+    xp, xld = view_of(x)
+    yp, yld = view_of(out)
+    check(_lib.lib().lpc_upsample2x(dt_code(x.dtype), xp, xld, B, H, W, Cc, yp, yld, _stream()), "upsample2x")
+    return out
+
+
+def copy_channels(x, out):
+    B, Cc, H, W = x.shape
+    assert tuple(out.shape) == tuple(x.shape)
+    xp, xld = view_of(x)
+    yp, yld = view_of(out)
+    check(_lib.lib().lpc_copy_channels(dt_code(x.dtype), xp, xld, B * H * W, Cc, yp, yld, _stream()), "copy_channels")
+    return out
+
+
+def space_to_depth(x, out=None):
+    B, Cc, H, W = x.shape
+    if out is None:
+        out = new_act(B, 4 * Cc, H // 2, W // 2, x.dtype, x.device)
+    xp, xld = view_of(x)
+    yp, yld = view_of(out)
+    check(_lib.lib().lpc_space_to_depth(dt_code(x.dtype), xp, xld, B, H, W, Cc, yp, yld, _stream()), "space_to_depth")
+    return out
+
+
+def channel_deinterleave(x, out=None):
+    B, Cc, H, W = x.shape
+    if out is None:
+        out = new_act(B, Cc, H, W, x.dtype, x.device)
+    xp, xld = view_of(x)
+    yp, yld = view_of(out)
+    check(_lib.lib().lpc_channel_deinterleave(dt_code(x.dtype), xp, xld, B * H * W, Cc, yp, yld, _stream()), "channel_deinterleave")
+    return out
+
+
+def global_avgpool(x):
+    B, Cc, H, W = x.shape
+    out = torch.empty((B, Cc), dtype=torch.float32, device=x.device)
+    xp, xld = view_of(x)
+    check(_lib.lib().lpc_global_avgpool(dt_code(x.dtype), xp, xld, B, H * W, Cc, _fp(out), _stream()), "global_avgpool")
+    return out
+
+
+def channel_mlp(v, W1, b1, act1, W2=None, b2=None, act2=ACT_NONE):
+    B, C0 = v.shape
+    C1 = W1.shape[0]
+    C2 = W2.shape[0] if W2 is not None else 0
+    out = torch.empty((B, C2 if W2 is not None else C1), dtype=torch.float32, device=v.device)
+    check(_lib.lib().lpc_channel_mlp(_fp(v), B, C0, _fp(W1), _fp(b1), C1, act1, _fp(W2), _fp(b2), C2, act2, _fp(out), _stream()), "channel_mlp")
+    return out
+
+
+def cbam_spatial(x, ca, w7, k, out=None):
+    """y = x*ca*sigmoid(conv_kxk([mean_c(x*ca), max_c(x*ca)]))."""
+    B, Cc, H, W = x.shape
+    if out is None:
+        out = new_act(B, Cc, H, W, x.dtype, x.device)
+    stats = torch.empty((B, H * W, 2), dtype=torch.float32, device=x.device)
+    xp, xld = view_of(x)
+    yp, yld = view_of(out)
+    L = _lib.lib()
+    check(L.lpc_cbam_stats(dt_code(x.dtype), xp, xld, B, H * W, Cc, _fp(ca), _fp(stats), _stream()), "cbam_stats")
+    check(L.lpc_cbam_apply(dt_code(x.dtype), xp, xld, B, H, W, Cc, _fp(ca), _fp(stats), _fp(w7), k, yp, yld, _stream()), "cbam_apply")
+    return out
+
+
+# ---- v10Detect tail ---------------------------------------------------------------------------------------
+def _raw_args(raw, strides):
+    r0, r1, r2 = raw
+    B, Ct, H0, W0 = r0.shape
+    ptrs, lds = zip(*(view_of(r) for r in raw))
+    if len(set(lds)) != 1:
+        raise LpcError("the three head maps must share one pixel pitch")
+    assert tuple(r1.shape[2:]) == (H0 // 2, W0 // 2) and tuple(r2.shape[2:]) == (H0 // 4, W0 // 4)
+    st = (C.c_float * 3)(*[float(s) for s in strides])
+    return ptrs, lds[0], B, Ct, H0, W0, st
+
+
+def v10_decode(raw, strides, nc):
+    """Detect.inference: three NHWC head maps -> y [B, 4+nc, A] fp32."""
+    ptrs, ld, B, Ct, H0, W0, st = _raw_args(raw, strides)
+    assert Ct == 64 + nc
+    A = H0 * W0 + (H0 // 2) * (W0 // 2) + (H0 // 4) * (W0 // 4)
+    y = torch.empty((B, 4 + nc, A), dtype=torch.float32, device=raw[0].device)
+    check(_lib.lib().lpc_v10_decode(dt_code(raw[0].dtype), ptrs[0], ptrs[1], ptrs[2], ld, B, H0, W0, nc, st, _fp(y), _stream()), "v10_decode")
+    return y
+
+
+def v10_decode_topk(raw, strides, nc, max_det=300, img_hw=None, return_index=False):
+    """Fused decode + v10postprocess + xywh2xyxy (+clip): -> dets [B,K,6] fp32 (x1,y1,x2,y2,score,label)."""
+    ptrs, ld, B, Ct, H0, W0, st = _raw_args(raw, strides)
+    assert Ct == 64 + nc
+    A = H0 * W0 + (H0 // 2) * (W0 // 2) + (H0 // 4) * (W0 // 4)
+    dev = raw[0].device
+    L = _lib.lib()
+    ws_bytes = L.lpc_v10_topk_workspace_bytes(B, A, max_det)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    dets = torch.empty((B, max_det, 6), dtype=torch.float32, device=dev)
+    aidx = torch.empty((B, max_det), dtype=torch.int32, device=dev) if return_index else None
+    ih, iw = (img_hw if img_hw is not None else (0, 0))
+    check(L.lpc_v10_decode_topk(dt_code(raw[0].dtype), ptrs[0], ptrs[1], ptrs[2], ld, B, H0, W0, nc, st, max_det, ih, iw,
+                                _fp(ws), ws_bytes, _fp(dets), _fp(aidx), _stream()), "v10_decode_topk")
+    return (dets, aidx) if return_index else dets
+
+
+def v10_postprocess(preds, max_det, nc):
+    """ops.v10postprocess on preds [B,A,4+nc] fp32 (any strides) -> boxes [B,K,4], scores [B,K], labels [B,K] i64."""
+    if not preds.is_cuda:
+        raise LpcError("v10postprocess runs on CUDA tensors only")
+    if preds.dtype != torch.float32:
+        preds = preds.float()
+    B, A, Ct = preds.shape
+    assert Ct == 4 + nc
+    dev = preds.device
+    L = _lib.lib()
+    ws_bytes = L.lpc_v10_topk_workspace_bytes(B, A, max_det)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    boxes = torch.empty((B, max_det, 4), dtype=torch.float32, device=dev)
+    scores = torch.empty((B, max_det), dtype=torch.float32, device=dev)
+    labels = torch.empty((B, max_det), dtype=torch.int64, device=dev)
+    sb, sa, sc = preds.stride()
+    check(L.lpc_v10_postprocess(_fp(preds), sb, sa, sc, B, A, nc, max_det, _fp(ws), ws_bytes, _fp(boxes), _fp(scores),
+                                _fp(labels), _stream()), "v10_postprocess")
+    return boxes, scores, labels

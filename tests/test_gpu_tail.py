@@ -1,0 +1,128 @@
+"""GPU parity tests, tier T3: the fused tail (DFL + anchor decode + sigmoid + NMS-free top-k) fed IDENTICAL raw
+head maps as the oracle / the reference.  Integer results (anchor index, class id) must be bit-exact wherever
+the oracle's selected scores are strictly separated; tie groups are compared as sets; scores within 2 ulp;
+boxes within 1e-3 px."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+STRIDES = [8.0, 16.0, 32.0]
+
+
+@pytest.fixture(scope="module")
+def Fn(pkg):
+    return importlib.import_module("lpc-yolo_b200.functional")
+
+
+def _to_dev(raw, dtype, Fn):
+    out = []
+    for r in raw:
+        t = Fn.new_act(*r.shape, dtype, "cuda")
+        t.copy_(r.cuda())
+        out.append(t)
+    return out
+
+
+def _ulp_close(a, b, n=2):
+    return (a.view(torch.int32) - b.view(torch.int32)).abs().max().item() <= n
+
+
+def _check_against_oracle(oracle, dets, aidx, raw_cpu, K, nc, img_hw):
+    """dets/aidx from the GPU vs the oracle run on the same (already rounded) raw maps."""
+    y = oracle.decode(raw_cpu, STRIDES, nc)
+    odets, oaidx = oracle.postprocess(y, K, nc, img_hw=img_hw)
+    B = y.shape[0]
+    dets, aidx = dets.cpu(), aidx.cpu().long()
+    for b in range(B):
+        gs, os_ = dets[b, :, 4], odets[b, :, 4]
+        assert _ulp_close(gs.contiguous(), os_.contiguous()), "score multiset differs"
+        assert (gs[:-1] >= gs[1:]).all(), "scores must be sorted descending"
+        # strictly separated ranks: exact anchor index and class id
+        sep = torch.ones(K, dtype=torch.bool)
+        eq = os_[:-1] == os_[1:]
+        sep[:-1] &= ~eq
+        sep[1:] &= ~eq
+        sep[-1] = False
+        assert torch.equal(aidx[b, sep], oaidx[b, sep])
+        assert torch.equal(dets[b, sep, 5], odets[b, sep, 5])
+        assert (dets[b, sep, :4] - odets[b, sep, :4]).abs().max() < 1e-3
+        # every selected pair must carry the score it claims, and our tie order is ascending flat index
+        flat = aidx[b] * nc + dets[b, :, 5].long()
+        got_scores = y[b, 4:, :].t().reshape(-1)[flat]
+        assert _ulp_close(got_scores.contiguous(), gs.contiguous())
+        tie = gs[:-1] == gs[1:]
+        assert (flat[:-1][tie] < flat[1:][tie]).all()
+        assert flat.unique().numel() == K
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("name", ["yolov10n", "lpc"])
+def test_tail_on_reference_raw_maps(oracle, Fn, dtype, name):
+    """Golden raw maps produced by the unmodified reference (tests/golden, 160x160)."""
+    g = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    raw = [torch.from_numpy(g[f"raw_small_{l}"])[None] for l in range(3)]
+    if dtype == torch.bfloat16:
+        raw = [r.bfloat16().float() for r in raw]
+    dev = _to_dev(raw, dtype, Fn)
+    dets, aidx = Fn.v10_decode_topk(dev, STRIDES, 80, 300, (160, 160), return_index=True)
+    _check_against_oracle(oracle, dets, aidx, raw, 300, 80, (160, 160))
+    if dtype == torch.float32:
+        # against the reference's own outputs: y and the final [300,6]
+        y = Fn.v10_decode(dev, STRIDES, 80).cpu()
+        ref_y = torch.from_numpy(g["y_small"])
+        assert (y[0, 4:] - ref_y[4:]).abs().max() < 1e-6
+        assert (y[0, :4] - ref_y[:4]).abs().max() < 1e-3
+        rd = torch.from_numpy(g["dets_small"])
+        assert _ulp_close(dets[0, :, 4].cpu().contiguous(), rd[:, 4].contiguous())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,S,K", [(3, 640, 300), (2, 320, 300), (1, 160, 300), (2, 160, 100), (1, 1280, 300)])
+def test_tail_random_maps(oracle, Fn, dtype, B, S, K):
+    """Seeded synthetic head maps at the BASELINE sizes (A = 8400 @640, 33600 @1280), incl. heavy ties in bf16."""
+    g = torch.Generator().manual_seed(S + B)
+    raw = []
+    for l in range(3):
+        h = S // 8 >> l
+        r = torch.randn(B, 144, h, h, generator=g) * 2.0
+        r[:, 64:] -= 6.0
+        raw.append(r.to(dtype).float())
+    dev = _to_dev(raw, dtype, Fn)
+    dets, aidx = Fn.v10_decode_topk(dev, STRIDES, 80, K, (S, S), return_index=True)
+    _check_against_oracle(oracle, dets, aidx, raw, K, 80, (S, S))
+
+
+def test_tail_all_equal_scores(oracle, Fn):
+    """Degenerate input (SURVEY.md finding 5): every class logit identical -> pure tie-break by flat index."""
+    raw = [torch.zeros(1, 144, 20 >> l, 20 >> l) for l in range(3)]
+    dev = _to_dev(raw, torch.bfloat16, Fn)
+    dets, aidx = Fn.v10_decode_topk(dev, STRIDES, 80, 300, None, return_index=True)
+    assert (dets[0, :, 4] == 0.5).all()
+    # two-stage semantics: stage 1 keeps anchors 0..299 (ties by index), stage 2 keeps the first 300 pairs
+    flat = aidx[0].cpu().long() * 80 + dets[0, :, 5].cpu().long()
+    assert torch.equal(flat, torch.arange(300))
+
+
+def test_v10postprocess_api(oracle, Fn, pkg):
+    """utils.ops.v10postprocess drop-in on a decoded preds tensor (both contiguous and transposed views)."""
+    ops = importlib.import_module("lpc-yolo_b200.utils.ops")
+    g = torch.Generator().manual_seed(7)
+    y = torch.rand(2, 84, 2100, generator=g)
+    y[:, 4:] = torch.sigmoid(torch.randn(2, 80, 2100, generator=g) * 2 - 5)
+    ob, os_, ol, _ = oracle.v10postprocess(y.transpose(-1, -2), 300, 80)
+    for preds in (y.cuda().transpose(-1, -2), y.cuda().transpose(-1, -2).contiguous()):
+        b, s, l = ops.v10postprocess(preds, 300, 80)
+        assert torch.equal(s.cpu(), os_)
+        sep = torch.ones(2, 300, dtype=torch.bool)
+        eq = os_[:, :-1] == os_[:, 1:]
+        sep[:, :-1] &= ~eq
+        sep[:, 1:] &= ~eq
+        sep[:, -1] = False
+        assert torch.equal(l.cpu()[sep], ol[sep]) and torch.equal(b.cpu()[sep], ob[sep])
+        assert l.dtype == torch.int64

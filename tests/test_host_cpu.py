@@ -1,0 +1,116 @@
+"""CPU-side checks of the host mirror: parser known answers (SURVEY.md 4.1 tier T1), state_dict key parity
+with the oracle/reference inventory, packing algebra, and that the C-ABI library exports what the header declares."""
+import ctypes
+import hashlib
+import importlib
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT
+
+MODELS = ["yolov10n", "yolov10s", "yolov10m", "yolov10b", "yolov10l", "yolov10x", "lpc"]
+
+
+def _model(pkg, oracle, name):
+    return pkg.YOLOv10DetectionModel(oracle.MODEL_FILES[name])
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_parser_matches_reference_inventory(pkg, oracle, name):
+    g = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    m = _model(pkg, oracle, name)
+    sd = m.state_dict()
+    shapes = {k: tuple(v.shape) for k, v in sd.items()}
+    txt = "\n".join(f"{k}:{v}" for k, v in sorted(shapes.items()))
+    assert hashlib.sha1(txt.encode()).hexdigest() == str(g["keys_sha1"])      # same keys, same shapes as the reference
+    assert len(sd) == int(g["n_keys"])
+    assert sum(p.numel() for p in m.parameters()) == int(g["n_params"])
+    assert m.save == list(g["save"])
+    det = m.model[-1]
+    assert [float(s) for s in det.stride] == list(g["strides"])
+    assert [s[0].conv.in_channels for s in det.cv2] == list(g["head_ch"])
+    # the oracle's synthetic weights load strictly
+    layers, _, meta = oracle.load_layers(name)
+    m.load_state_dict(oracle.synth_state_dict(oracle.param_shapes(layers), 0, meta["strides"], 80), strict=True)
+
+
+def test_activation_quirk(pkg, oracle):
+    """SURVEY.md finding 1: block modules use Mish, YAML-level Conv and the head use SiLU (yolov10n: 41 / 46 / 9)."""
+    m = _model(pkg, oracle, "yolov10n")
+    conv_mod = importlib.import_module("lpc-yolo_b200.nn.modules.conv")
+    acts = [type(x.act).__name__ for x in m.modules() if isinstance(x, conv_mod.Conv)]
+    rep = [x for x in m.modules() if type(x).__name__ == "RepVGGDW"]
+    assert acts.count("Mish") == 46
+    assert acts.count("SiLU") + len(rep) == 41
+    assert acts.count("Identity") == 9 + 2 * len(rep) - 0 or acts.count("Identity") >= 9
+
+
+def test_lpc_yaml_quirks(pkg, oracle):
+    m = _model(pkg, oracle, "lpc")
+    det = m.model[-1]
+    assert det.f == [20, 23, 26] and [s[0].conv.in_channels for s in det.cv2] == [64, 192, 384]
+    dest, live = m._plan()
+    assert 27 not in live                       # dead layer is skipped
+    assert m.yaml["scale"] == ""                # scale falls back to the first key
+    assert dest[15] == (16, 0) and dest[10][0] == 16 and dest[22] == (23, 0) and dest[17][0] == 23
+
+
+def test_bn_fold_algebra(pkg):
+    pack = importlib.import_module("lpc-yolo_b200.pack")
+    torch.manual_seed(0)
+    conv = torch.nn.Conv2d(8, 16, 3, 1, 1, bias=False)
+    bn = torch.nn.BatchNorm2d(16, eps=1e-3)
+    bn.running_mean.uniform_(-1, 1); bn.running_var.uniform_(0.5, 2); bn.weight.data.uniform_(0.5, 1.5); bn.bias.data.uniform_(-1, 1)
+    bn.eval()
+    x = torch.randn(2, 8, 9, 9)
+    w, b = pack.fold_bn(conv.weight, None, bn)
+    ref = bn(conv(x))
+    got = torch.nn.functional.conv2d(x.double(), w, b, 1, 1).float()
+    assert (ref - got).abs().max() < 1e-5
+
+
+def test_qkv_permutation(pkg):
+    block = importlib.import_module("lpc-yolo_b200.nn.modules.block")
+    a = block.Attention(288, num_heads=4)
+    assert (a.key_dim, a.head_dim) == (36, 72)                       # yolov10m
+    perm = a._qkv_perm()
+    assert sorted(perm.tolist()) == list(range(288 + 2 * 36 * 4))
+    per = 2 * 36 + 72
+    assert perm[0] == 0 and perm[36] == per and perm[4 * 36] == 36 and perm[8 * 36] == 72 and perm[8 * 36 + 72] == per + 72
+
+
+def test_abi_exports_every_declared_symbol(pkg):
+    lib_mod = importlib.import_module("lpc-yolo_b200._lib")
+    header = open(os.path.join(ROOT, "include", "lpcyolo.h")).read()
+    declared = set(re.findall(r"\b(lpc_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(lib_mod.SIGNATURES), declared ^ set(lib_mod.SIGNATURES)
+    h = ctypes.CDLL(lib_mod.build())
+    for name in declared:
+        assert hasattr(h, name), name
+    assert lib_mod.lib().lpc_abi_version() == 1
+    assert lib_mod.lib().lpc_conv2d_tc_kpad(16, 3) == 192 and lib_mod.lib().lpc_conv2d_tc_kpad(64, 1) == 64
+
+
+def test_no_cpu_fallback(pkg, oracle):
+    """The product path must fail loudly without a CUDA tensor."""
+    m = _model(pkg, oracle, "yolov10n")
+    with pytest.raises(pkg.LpcError):
+        m(torch.rand(1, 3, 64, 64))
+    ops = importlib.import_module("lpc-yolo_b200.utils.ops")
+    with pytest.raises(pkg.LpcError):
+        ops.v10postprocess(torch.rand(1, 400, 84), 300, 80)
+
+
+def test_product_never_imports_oracle():
+    bad = []
+    for dp, _, fn in os.walk(os.path.join(ROOT, "lpc-yolo_b200")):
+        for f in fn:
+            if f.endswith(".py"):
+                s = open(os.path.join(dp, f)).read()
+                if re.search(r"^\s*(import|from)\s+(oracle|lpc_oracle)", s, re.M):
+                    bad.append(f)
+    assert not bad
