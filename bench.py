@@ -1,0 +1,268 @@
+#!/usr/bin/env python
+"""bench.py - images/sec of the LPC-YOLO / YOLOv10 inference hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--model lpc] [--batch 64] [--size 640]
+
+A "step" is one pass of the hot path (backbone + neck + one2one head + fused decode/top-k -> [B,300,6]) over one
+synthetic batch.  N=1 workload = BASELINE.json configs[1]: the LPC-YOLO YAML, 640x640, batch 64, bf16.
+  value     whole-job images/s, inputs resident in HBM (bf16 NHWC), CUDA-graph replay, CUDA-event timed, max over ranks
+  e2e       same metric through YOLO(...).predict(host tensor): pinned host fp32 [B,3,S,S] -> H2D -> pack -> network ->
+            fused tail -> D2H of [B,300,6], everything inside the timed region
+  roofline  dominant kernel = conv_tc_kernel (tcgen05 implicit GEMM): algorithmic FLOPs of the dense convs it ran in one
+            step / summed CUDA-event durations of those launches, against the measured bf16 peak (MEASURED_PEAKS.json)
+  cpu_baseline  the CPU oracle port (same torch-CPU ATen ops the reference bottoms out in) on a bounded sample
+N>1: one process per GPU (torchrun), batch sharded (B per GPU fixed => weak scaling), no collective on the compute path,
+one all_gather of the [B,300,6] detections per step.
+--impl reference: times the reference's CPU path (the oracle port - the reference is pure Python on torch and cannot
+travel to the GPU box) with all host threads; rank 0 only.
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# dense-conv FLOPs per image of the one2one path @640 (2*MAC), BASELINE.md section 2 (dead layer 27 excluded for LPC)
+GFLOP_IMG_640 = {"lpc": 10.54, "yolov10n": 6.70, "yolov10s": 21.59, "yolov10m": 59.10, "yolov10b": 91.95,
+                 "yolov10l": 120.34, "yolov10x": 160.39}
+FILES = {"lpc": "yolov10-SPD-Conv-Tiny-CBAM-LPC.yaml", **{f"yolov10{s}": f"yolov10{s}.yaml" for s in "nsmblx"}}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sust": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm": 6650.0, "tf_burst": 1590.0, "tf_sust": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.stop_flag = gpu_index, [], False
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop_flag = True
+        self.th.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names) if any(r[2 + j].lower().startswith("active") for r in self.rows if len(r) > 2 + j)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_reference_leg(model_key, size, batch, reps, warm=1):
+    """Time the oracle port on the host cores: returns (img/s, threads, description)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import lpc_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    om = O.build(model_key, calibrate=False)
+    x = O.synth_input(batch, size)
+    with torch.no_grad():
+        for _ in range(warm):
+            om.predict(x)
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            om.predict(x)
+            ts.append(time.perf_counter() - t0)
+    t = statistics.median(ts)
+    return batch / t, torch.get_num_threads(), f"{model_key} @{size} batch {batch}, fp32, median of {reps} predict() passes after {warm} warm-up", t
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    b = min(args.batch, 8)
+    ips, threads, desc, t = cpu_reference_leg(args.model, args.size, b, max(args.steps, 1), max(args.warmup, 1))
+    line = {"metric": "images/sec", "value": round(ips, 3), "unit": "img/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(t * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"{args.model} YAML predict, {args.size}x{args.size}, batch {b} per step (bounded CPU sample of the batch-{args.batch} workload)"},
+            "cpu_baseline": {"value": round(ips, 3), "unit": "img/s", "cores": threads, "kind": "port", "sample": desc},
+            "e2e": {"value": round(ips, 3), "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="lpc", choices=sorted(FILES))
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--size", type=int, default=640)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py measures the CUDA path; there is no CPU fallback"
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    pkg = importlib.import_module("lpc-yolo_b200")
+    Fn = importlib.import_module("lpc-yolo_b200.functional")
+    synth = importlib.import_module("lpc-yolo_b200.utils.synth")
+    L = pkg.lib()
+    B, S, K = args.batch, args.size, 300
+
+    yolo = pkg.YOLO(FILES[args.model])
+    synth.init_synthetic(yolo.model, seed=0)
+    model = yolo.model.to(dev).eval()
+    model.compute_dtype = torch.bfloat16
+    g = torch.Generator().manual_seed(1 + rank)
+    x_host = torch.rand(B, 3, S, S, generator=g).pin_memory()
+    x_dev = Fn.pack_input(x_host.to(dev), torch.bfloat16)             # bf16 NHWC, resident before timing
+    par = importlib.import_module("lpc-yolo_b200.parallel")
+
+    def step():
+        d = model.detect(x_dev, K, clip=True)
+        return par.gather_detections(d) if world > 1 else d     # the path's only exchange: [B,300,6] per rank
+
+    with torch.no_grad():
+        n0 = L.lpc_launch_count()
+        step()
+        torch.cuda.synchronize()
+        launches_per_step = L.lpc_launch_count() - n0
+        graph = None
+        if not args.no_graph and world == 1:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                step()
+            torch.cuda.current_stream().wait_stream(s)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = step()
+        run = graph.replay if graph is not None else step
+        for _ in range(max(args.warmup, 3)):
+            run()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as cs:
+            e0.record()
+            for _ in range(args.steps):
+                run()
+            e1.record()
+            torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+        clocks = cs.summary()
+
+        # ---- e2e: public API with host buffers (H2D + network + tail + D2H inside the timed region) ----
+        pred_kwargs = dict(conf=0.25, half=True)
+        for _ in range(3):
+            yolo.predict(x_host, **pred_kwargs)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e_steps = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            res = yolo.predict(x_host, **pred_kwargs)
+            host_dets = yolo.predictor.last_preds.cpu()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        te = torch.tensor([e2e_s], device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_ips = world * B * e_steps / te.item()
+
+        # ---- roofline of the dominant kernel, measured live: per-launch CUDA events around every tcgen05 conv ----
+        roof = None
+        if rank == 0:
+            Fn.PROFILE = []
+            step()
+            torch.cuda.synchronize()
+            prof, Fn.PROFILE = Fn.PROFILE, None
+            tc = [(a.elapsed_time(b) * 1e-3, fl) for (kind, a, b, fl, _, _t) in prof if kind == "conv2d_tc"]
+            tail = [(a.elapsed_time(b) * 1e-3, by) for (kind, a, b, _, by, _t) in prof if kind == "v10_decode_topk"]
+            allk = sum(a.elapsed_time(b) for (_, a, b, _, _, _t) in prof)
+            pk = peaks()
+            if tc:
+                t_tc, fl_tc = sum(x[0] for x in tc), sum(x[1] for x in tc)
+                ach = fl_tc / t_tc / 1e12
+                roof = {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, all dense-conv launches of one step)",
+                        "bound": "tensor", "achieved": round(ach, 2), "peak": pk["tf_burst"], "unit": "TFLOP/s",
+                        "frac": round(ach / pk["tf_burst"], 4), "traffic": None, "peak_source": pk["src"] + " (burst)",
+                        "launches": len(tc), "share_of_step": round(t_tc * 1e3 / allk, 3),
+                        "algorithmic_gflop_per_step": round(fl_tc / 1e9, 2)}
+            if tail:
+                t_t, by_t = sum(x[0] for x in tail), sum(x[1] for x in tail)
+                roof_tail = {"kernel": "amax_keys + select_decode (fused v10 tail)", "bound": "hbm", "achieved": round(by_t / t_t / 1e9, 1),
+                             "peak": pk["hbm"], "unit": "GB/s", "frac": round(by_t / t_t / 1e9 / pk["hbm"], 4), "traffic": None}
+            else:
+                roof_tail = None
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu and world == 1:
+            ips, threads, desc, _ = cpu_reference_leg(args.model, S, 4, 3)
+            cpu = {"value": round(ips, 3), "unit": "img/s", "cores": threads, "kind": "port", "sample": desc}
+        total_imgs = world * B * args.steps
+        line = {"metric": "images/sec", "value": round(total_imgs / (ms * 1e-3), 2), "unit": "img/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"{FILES[args.model]} predict hot path, {S}x{S}, batch {B} per GPU, bf16, random-init (synthetic) weights",
+                           "global_batch": world * B, "parallelism": f"dp{world} (batch sharded, no compute-path collective)",
+                           "cuda_graph": graph is not None,
+                           "l2": "no flush: per-step working set (input %.0f MB + activations) exceeds the 126 MB L2" % (x_dev.numel() * 2 / 1e6 * 4 / 3)},
+                "clocks": clocks,
+                "e2e": {"value": round(e2e_ips, 2), "unit": "img/s", "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": B * K * 6 * 4 + B * 8},
+                "gpu_launches": int(launches_per_step * args.steps),
+                "roofline": roof, "roofline_tail": roof_tail, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -152,6 +152,7 @@ class YOLOv10DetectionPredictor:
         [B,K,6] xyxy (the export-mode contract, head.py:521-523), clipped to the image (scale_boxes is the
         identity + clip when source and network sizes agree)."""
         B = preds.shape[0]
+        self.last_preds = preds          # batched [B,K,6] on the device (one D2H gives every detection)
         if self.args.classes is None:
             counts = (preds[..., 4] > self.args.conf).sum(1).tolist()        # scores are sorted: a prefix survives
             per_img = [preds[i, :n] for i, n in enumerate(counts)]

@@ -14,6 +14,43 @@ from ._lib import ACT_MISH, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SILU, BF16, F32
 _DT = {torch.bfloat16: BF16, torch.float32: F32}
 
 
+# Optional per-launch profiling (bench.py): when PROFILE is a list, every op appends
+# (kind, start_event, end_event, algorithmic_flops, algorithmic_bytes, shape tag).
+PROFILE = None
+
+
+class _prof:
+    def __init__(self, kind, flops=0.0, nbytes=0.0, tag=""):
+        self.rec = None
+        if PROFILE is not None:
+            self.rec = [kind, torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), flops, nbytes, tag]
+
+    def __enter__(self):
+        if self.rec is not None:
+            self.rec[1].record()
+        return self
+
+    def __exit__(self, *a):
+        if self.rec is not None:
+            self.rec[2].record()
+            PROFILE.append(tuple(self.rec))
+
+
+def _profiled(fn):
+    import functools
+
+    @functools.wraps(fn)
+    def wrap(*a, **k):
+        if PROFILE is None:
+            return fn(*a, **k)
+        t = a[0] if a and torch.is_tensor(a[0]) else None
+        tag = "x".join(map(str, t.shape)) if t is not None else ""
+        nb = 2.0 * t.numel() * t.element_size() if t is not None else 0.0
+        with _prof(fn.__name__, 0.0, nb, tag):
+            return fn(*a, **k)
+    return wrap
+
+
 def dt_code(dtype):
     try:
         return _DT[dtype]
@@ -74,6 +111,7 @@ def _fp(t):
 
 
 # ---------------------------------------------------------------------------------------------------------
+@_profiled
 def pack_input(x, dtype, cpad=4):
     """fp32 NCHW image batch -> NHWC activation with C padded to ``cpad`` (logical C stays x.shape[1])."""
     B, Cc, H, W = x.shape
@@ -98,16 +136,22 @@ def conv2d(x, pc, out=None, res=None, chan_scale=None):
     L = _lib.lib()
     use_tc = (pc.w_tc is not None and x.dtype == torch.bfloat16 and xp % 16 == 0 and yp % 16 == 0 and rp % 16 == 0
               and rld % 8 == 0 and L.lpc_conv2d_tc_supported(Cin, pc.cout, pc.k, pc.s, pc.p, xld, yld))
+    flops = 2.0 * B * Ho * Wo * pc.cout * Cin * pc.k * pc.k
+    nbytes = x.element_size() * (B * H * W * Cin + B * Ho * Wo * pc.cout * (2 if res is not None else 1) + pc.cout * Cin * pc.k * pc.k)
+    tag = f"{Cin}->{pc.cout} k{pc.k}s{pc.s} {H}x{W} B{B}"
     if use_tc:
-        check(L.lpc_conv2d_tc(xp, xld, B, H, W, Cin, _fp(pc.w_tc), _fp(pc.bias), pc.k, pc.s, pc.p, pc.cout, yp, yld,
-                              pc.act, _fp(chan_scale), rp or None, rld, _stream()), "conv2d_tc")
+        with _prof("conv2d_tc", flops, nbytes, tag):
+            check(L.lpc_conv2d_tc(xp, xld, B, H, W, Cin, _fp(pc.w_tc), _fp(pc.bias), pc.k, pc.s, pc.p, pc.cout, yp, yld,
+                                  pc.act, _fp(chan_scale), rp or None, rld, _stream()), "conv2d_tc")
     else:
-        check(L.lpc_conv2d_direct(dt_code(x.dtype), xp, xld, B, H, W, Cin, _fp(pc.w_direct), _fp(pc.bias), pc.k, pc.s,
-                                  pc.p, pc.cout, yp, yld, pc.act, _fp(chan_scale), rp or None, rld, _stream()),
-              "conv2d_direct")
+        with _prof("conv2d_direct", flops, nbytes, tag):
+            check(L.lpc_conv2d_direct(dt_code(x.dtype), xp, xld, B, H, W, Cin, _fp(pc.w_direct), _fp(pc.bias), pc.k, pc.s,
+                                      pc.p, pc.cout, yp, yld, pc.act, _fp(chan_scale), rp or None, rld, _stream()),
+                  "conv2d_direct")
     return out
 
 
+@_profiled
 def dwconv2d(x, pd, out=None, res=None):
     B, Cc, H, W = x.shape
     ke = pd.d * (pd.k - 1) + 1
@@ -124,6 +168,7 @@ def dwconv2d(x, pd, out=None, res=None):
     return out
 
 
+@_profiled
 def sppf_pool(x, out):
     """out (3C channels) <- [pool5(x), pool9(x), pool13(x)]."""
     B, Cc, H, W = x.shape
@@ -134,6 +179,7 @@ def sppf_pool(x, out):
     return out
 
 
+@_profiled
 def psa_attention(qkv, heads, kd, hd, out=None):
     B, Ct, H, W = qkv.shape
     assert Ct == heads * (2 * kd + hd)
@@ -145,6 +191,7 @@ def psa_attention(qkv, heads, kd, hd, out=None):
     return out
 
 
+@_profiled
 def upsample2x(x, out=None):
     B, Cc, H, W = x.shape
     if out is None:
@@ -156,6 +203,7 @@ def upsample2x(x, out=None):
     return out
 
 
+@_profiled
 def copy_channels(x, out):
     B, Cc, H, W = x.shape
     assert tuple(out.shape) == tuple(x.shape)
@@ -165,6 +213,7 @@ def copy_channels(x, out):
     return out
 
 
+@_profiled
 def space_to_depth(x, out=None):
     B, Cc, H, W = x.shape
     if out is None:
@@ -175,6 +224,7 @@ def space_to_depth(x, out=None):
     return out
 
 
+@_profiled
 def channel_deinterleave(x, out=None):
     B, Cc, H, W = x.shape
     if out is None:
@@ -185,6 +235,7 @@ def channel_deinterleave(x, out=None):
     return out
 
 
+@_profiled
 def global_avgpool(x):
     B, Cc, H, W = x.shape
     out = torch.empty((B, Cc), dtype=torch.float32, device=x.device)
@@ -193,6 +244,7 @@ def global_avgpool(x):
     return out
 
 
+@_profiled
 def channel_mlp(v, W1, b1, act1, W2=None, b2=None, act2=ACT_NONE):
     B, C0 = v.shape
     C1 = W1.shape[0]
@@ -202,6 +254,7 @@ def channel_mlp(v, W1, b1, act1, W2=None, b2=None, act2=ACT_NONE):
     return out
 
 
+@_profiled
 def cbam_spatial(x, ca, w7, k, out=None):
     """y = x*ca*sigmoid(conv_kxk([mean_c(x*ca), max_c(x*ca)]))."""
     B, Cc, H, W = x.shape
@@ -228,6 +281,7 @@ def _raw_args(raw, strides):
     return ptrs, lds[0], B, Ct, H0, W0, st
 
 
+@_profiled
 def v10_decode(raw, strides, nc):
     """Detect.inference: three NHWC head maps -> y [B, 4+nc, A] fp32."""
     ptrs, ld, B, Ct, H0, W0, st = _raw_args(raw, strides)
@@ -250,11 +304,15 @@ def v10_decode_topk(raw, strides, nc, max_det=300, img_hw=None, return_index=Fal
     dets = torch.empty((B, max_det, 6), dtype=torch.float32, device=dev)
     aidx = torch.empty((B, max_det), dtype=torch.int32, device=dev) if return_index else None
     ih, iw = (img_hw if img_hw is not None else (0, 0))
-    check(L.lpc_v10_decode_topk(dt_code(raw[0].dtype), ptrs[0], ptrs[1], ptrs[2], ld, B, H0, W0, nc, st, max_det, ih, iw,
-                                _fp(ws), ws_bytes, _fp(dets), _fp(aidx), _stream()), "v10_decode_topk")
+    # algorithmic bytes: raw maps read once + detections written
+    nbytes = B * A * (64 + nc) * raw[0].element_size() + B * max_det * 6 * 4
+    with _prof("v10_decode_topk", 0.0, nbytes):
+        check(L.lpc_v10_decode_topk(dt_code(raw[0].dtype), ptrs[0], ptrs[1], ptrs[2], ld, B, H0, W0, nc, st, max_det, ih, iw,
+                                    _fp(ws), ws_bytes, _fp(dets), _fp(aidx), _stream()), "v10_decode_topk")
     return (dets, aidx) if return_index else dets
 
 
+@_profiled
 def v10_postprocess(preds, max_det, nc):
     """ops.v10postprocess on preds [B,A,4+nc] fp32 (any strides) -> boxes [B,K,4], scores [B,K], labels [B,K] i64."""
     if not preds.is_cuda:

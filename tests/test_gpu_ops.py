@@ -34,7 +34,7 @@ def _randomize(mod, seed=0):
 
 
 def _sd(mod, dtype):
-    sd = {"m." + k: v.detach().clone().float() for k, v in mod.state_dict().items()}
+    sd = {"m." + k: v.detach().cpu().clone().float() for k, v in mod.state_dict().items()}
     if dtype == torch.bfloat16:
         # what the bf16 path sees: folded weights rounded to bf16.  Rounding the un-folded weights is not
         # identical, but BN scale is folded in fp64 first; we emulate by leaving weights fp32 here and
