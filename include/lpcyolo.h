@@ -78,8 +78,17 @@ int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int Cin,
                   const void* res, int res_ld, void* stream);
 /* K padding rule of the tcgen05 weight layout; returns Kpad (multiple of 64) or <0. */
 int lpc_conv2d_tc_kpad(int Cin, int k);
+/* Kernel selection override for tests / profiling: 0 = auto, 1 = always the per-tap TMA kernel, 2 = the halo-patch
+ * kernel for every 3x3 stride-1 conv whose buffers fit.  Returns the previous mode. */
+int lpc_conv2d_tc_set_mode(int mode);
 /* 1 if lpc_conv2d_tc accepts this shape, else 0. */
 int lpc_conv2d_tc_supported(int Cin, int Cout, int k, int stride, int pad, int x_ld, int y_ld);
+
+/* Stem: Conv(3, Cout, 3, stride, pad 1) on an NHWC input whose pixel pitch is exactly 4 (lpc_pack_input's Cpad=4):
+ * a register-tiled CUDA-core kernel (K=27 is too small for the tensor-core path).  w: [27][Cout] fp32 with row index
+ * (ky*3+kx)*3+cin; Cout % 8 == 0, Cout <= 96.  Replaces layer 0 of every v10 / LPC YAML (conv.py:36-54). */
+int lpc_stem_conv(int dtype, const void* x, int B, int H, int W, const float* w, const float* bias, int stride,
+                  int Cout, void* y, int y_ld, int act, void* stream);
 
 /* ---- depthwise convolution ---------------------------------------------------------------------
  * groups == C convs: CIB / RepVGGDW (block.py:700-756; the 3x3 branch is merged into the 7x7 on the
@@ -111,10 +120,14 @@ int lpc_channel_deinterleave(int dtype, const void* x, int x_ld, long long npix,
 int lpc_pack_input(int dtype, const float* x_nchw, int B, int C, int H, int W, void* y, int y_ld, int Cpad, void* stream);
 
 /* ---- CBAM / SPCA pooled gates (conv.py:278-320, block.py:5735-5747) */
-int lpc_global_avgpool(int dtype, const void* x, int x_ld, int B, int HW, int C, float* out, void* stream);
-/* out[b] = act2(W2 . act1(W1 . in[b] + b1) + b2); W2 may be NULL (single layer). W row-major [Cout][Cin]. */
-int lpc_channel_mlp(const float* in, int B, int C0, const float* W1, const float* b1, int C1, int act1,
-                    const float* W2, const float* b2, int C2, int act2, float* out, void* stream);
+/* partial[b][chunk][c] = sum of x over the chunk's pixels, chunk count = lpc_global_avgpool_chunks(B, HW)
+ * (a fixed-order two-stage reduction: deterministic, no atomics). */
+int lpc_global_avgpool_chunks(int B, int HW);
+int lpc_global_avgpool(int dtype, const void* x, int x_ld, int B, int HW, int C, float* partial, void* stream);
+/* v[b] = in_scale * sum_parts in[b][part][:];  out[b] = act2(W2 . act1(W1 . v[b] + b1) + b2); W2 may be NULL
+ * (single layer). W row-major [Cout][Cin]. */
+int lpc_channel_mlp(const float* in, int B, int parts, float in_scale, int C0, const float* W1, const float* b1, int C1,
+                    int act1, const float* W2, const float* b2, int C2, int act2, float* out, void* stream);
 /* stats[b,p,0] = mean_c(x*ca), stats[b,p,1] = max_c(x*ca) */
 int lpc_cbam_stats(int dtype, const void* x, int x_ld, int B, int HW, int C, const float* ca, float* stats, void* stream);
 /* y = x * ca * sigmoid(conv_kxk(stats, w)) ; w: [2][k][k] fp32 (cin-major as nn.Conv2d(2,1,k)) */

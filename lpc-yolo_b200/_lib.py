@@ -24,7 +24,9 @@ SIGNATURES = {
     "lpc_conv2d_direct": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _f32p, _i, _i, _i, _i, _p, _i, _i, _f32p, _p, _i, _p]),
     "lpc_conv2d_tc": (_i, [_p, _i, _i, _i, _i, _i, _p, _f32p, _i, _i, _i, _i, _p, _i, _i, _f32p, _p, _i, _p]),
     "lpc_conv2d_tc_kpad": (_i, [_i, _i]),
+    "lpc_conv2d_tc_set_mode": (_i, [_i]),
     "lpc_conv2d_tc_supported": (_i, [_i, _i, _i, _i, _i, _i, _i]),
+    "lpc_stem_conv": (_i, [_i, _p, _i, _i, _i, _f32p, _f32p, _i, _i, _p, _i, _i, _p]),
     "lpc_dwconv2d": (_i, [_i, _p, _i, _i, _i, _i, _i, _f32p, _f32p, _i, _i, _i, _i, _p, _i, _i, _p, _i, _p]),
     "lpc_sppf_pool": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _i, _p]),
     "lpc_psa_attention": (_i, [_i, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
@@ -34,7 +36,8 @@ SIGNATURES = {
     "lpc_channel_deinterleave": (_i, [_i, _p, _i, _ll, _i, _p, _i, _p]),
     "lpc_pack_input": (_i, [_i, _f32p, _i, _i, _i, _i, _p, _i, _i, _p]),
     "lpc_global_avgpool": (_i, [_i, _p, _i, _i, _i, _i, _f32p, _p]),
-    "lpc_channel_mlp": (_i, [_f32p, _i, _i, _f32p, _f32p, _i, _i, _f32p, _f32p, _i, _i, _f32p, _p]),
+    "lpc_global_avgpool_chunks": (_i, [_i, _i]),
+    "lpc_channel_mlp": (_i, [_f32p, _i, _i, C.c_float, _i, _f32p, _f32p, _i, _i, _f32p, _f32p, _i, _i, _f32p, _p]),
     "lpc_cbam_stats": (_i, [_i, _p, _i, _i, _i, _i, _f32p, _f32p, _p]),
     "lpc_cbam_apply": (_i, [_i, _p, _i, _i, _i, _i, _i, _f32p, _f32p, _f32p, _i, _p, _i, _p]),
     "lpc_v10_topk_workspace_bytes": (_sz, [_i, _i, _i]),

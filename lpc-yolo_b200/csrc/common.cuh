@@ -95,15 +95,38 @@ template <bool PRECISE> __device__ __forceinline__ float div_(float a, float b) 
 template <bool PRECISE> __device__ __forceinline__ float sigmoid_(float x) {
   return div_<PRECISE>(1.0f, 1.0f + exp_<PRECISE>(-x));
 }
-template <bool PRECISE> __device__ __forceinline__ float silu_(float x) {
-  return div_<PRECISE>(x, 1.0f + exp_<PRECISE>(-x));
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-// mish(x) = x*tanh(softplus(x)) = x*n/(n+2) with n = e^x (e^x + 2)   (one exp, one divide)
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <bool PRECISE> __device__ __forceinline__ float silu_(float x) {
+  if (PRECISE) return x / (1.0f + expf(-x));
+  // x*sigmoid(x) = 0.5x(1 + tanh(x/2)): ONE MUFU op (tanh.approx, ~2^-11 rel. error, below bf16 rounding)
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_approx(h), h);
+}
+// mish(x) = x*tanh(softplus(x)) = x*n/(n+2) = x - 2x/(n+2) with n = e^x (e^x + 2)   (one exp, one reciprocal)
 template <bool PRECISE> __device__ __forceinline__ float mish_(float x) {
-  if (x > 20.0f) return x;
-  float e = exp_<PRECISE>(x);
-  float n = e * (e + 2.0f);
-  return x * div_<PRECISE>(n, n + 2.0f);
+  if (PRECISE) {
+    if (x > 20.0f) return x;
+    const float e = expf(x);
+    const float n = e * (e + 2.0f);
+    return x * (n / (n + 2.0f));
+  }
+  const float e = ex2_approx(fminf(x, 20.0f) * 1.4426950408889634f);   // clamp: e^20 squared still fits fp32
+  const float n = fmaf(e, e, e + e);
+  return fmaf(-2.0f * x, rcp_approx(n + 2.0f), x);
 }
 template <bool PRECISE> __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {

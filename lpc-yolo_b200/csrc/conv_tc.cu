@@ -1,35 +1,39 @@
 // conv_tc.cu - dense convolution as an implicit GEMM on the 5th-gen tensor cores (sm_100a).
 //
-//   D[M = output pixels, N = Cout] = A[M, K = taps*Cin] * W[N, K]^T,  bf16 operands, fp32 accumulate.
+//   D[M = output pixels, N = Cout] = A[M, K = taps*Cin] * W[N, K]^T,  bf16 operands, fp32 accumulate in TMEM.
 //
-// * A is never materialised (no im2col buffer): for every filter tap the TMA engine loads a box
-//   [kc channels, TW, TH, 1 image] of the NHWC activation straight into 128B/64B/32B-swizzled shared
-//   memory; zero padding is the TMA out-of-bounds fill.  Stride-2 convs (and the space_to_depth + 1x1
-//   fold, k=2) read through four "parity" tensor maps whose W/H strides are doubled, so tap (ky,kx)
-//   is again a plain shifted box.  1x1 convs see the activation as a flat [M, Cin] matrix.
-// * W ([Cout][Kpad] bf16, K-major) is loaded by a 2-D TMA map, 64 K-elements x n_tile rows per stage.
-// * tcgen05.mma (cta_group::1, M=128, N=n_tile<=256, K=16) is issued by one elected thread; the
-//   accumulator lives in TMEM; tcgen05.commit releases smem stages and signals the epilogue.
-// * Epilogue warps read TMEM with tcgen05.ld (32 lanes x 16 columns), apply bias + activation
-//   (+ SPCA channel gate, + residual), convert to bf16 and store 32-byte runs into the NHWC output
-//   view (which may be a channel slice of a concat buffer).
-// * Warp roles: w0 = TMA producer, w1 = TMEM allocator + MMA issuer, w2..w5 = epilogue.  Up to two
-//   CTAs are resident per SM, so one tile's epilogue overlaps another tile's main loop.
+// Two persistent, warp-specialised kernels share the PTX helpers and the epilogue:
+//
+//  conv_tc_taps_kernel  (1x1 as a flat GEMM, 3x3 stride 2, the k=2/s=2 space_to_depth fold, small 3x3 maps)
+//     Per 64-wide K step the TMA engine loads, for the current filter tap, a box [kc channels, TW, TH, 1 image] of
+//     the NHWC activation into 128B/64B/32B-swizzled shared memory (zero padding = TMA out-of-bounds fill; stride-2
+//     convs read through four "parity" tensor maps with doubled W/H strides) plus the [n_tile x 64] weight block.
+//  conv_tc_halo_kernel  (3x3 stride 1 - 72 % of LPC-YOLO's FLOPs)
+//     Per M tile (8 x 16 output pixels) ONE halo patch (10 x 18 pixels, all Cin) is loaded, as Cin/8 un-swizzled
+//     "planes" [pixel][8 channels]; the nine taps are nine shifted UMMA descriptors into that patch (core-matrix
+//     row group = one 8-pixel tile row, SBO = patch row pitch), so the activation crosses L2->SM 1.4x instead of 9x.
+//     The weights stay resident in shared memory for the CTA's lifetime when they fit, else stream through a ring.
+//
+// Common structure (one CTA per SM, or two when TMEM/smem allow): warp 0 = TMA producer, warp 1 = TMEM allocator
+// + single-thread tcgen05.mma issuer, warps 2.. = epilogue.  The accumulator is double-buffered in TMEM
+// (tmem_full / tmem_empty mbarriers), so tile i's epilogue (tcgen05.ld -> bias + SiLU/Mish (+gate, +residual) ->
+// bf16 -> 16-byte stores into the NHWC output slice) overlaps tile i+1's main loop.  All mbarrier waits are
+// bounded: a protocol bug traps instead of hanging the GPU.
 #include <cuda.h>
 
-#include <mutex>
-#include <unordered_map>
-#include <string>
 #include <cstring>
+#include <mutex>
 
 #include "common.cuh"
 
 namespace {
 
-constexpr int TC_NT = 192;
 constexpr int MAX_STAGES = 8;
-constexpr int A_STAGE_BYTES = 128 * 64 * 2;  // 128 rows x 64 K-elements of bf16
+constexpr int A_STAGE_BYTES = 128 * 64 * 2;  // taps kernel: 128 rows x 64 K-elements of bf16
 constexpr int MAX_TAPS = 9;
+constexpr int HALO_TW = 8, HALO_TH = 16;
+constexpr int HALO_PW = HALO_TW + 2, HALO_PH = HALO_TH + 2;
+constexpr int HALO_PLANE_BYTES = ((HALO_PW * HALO_PH * 16 + 127) / 128) * 128;  // 2944: TMA wants 128-B aligned targets
 
 struct TmapPack {
   CUtensorMap a[4];
@@ -39,9 +43,12 @@ struct TmapPack {
 struct ConvTcParams {
   int Ho, Wo, B;
   int tiles_x, tiles_y, TW, TH;
-  int Cout, n_tile, tmem_cols;
-  int ksteps, kc, nsub, chunks_per_tap, real_slots, stages;
+  int m_tiles, n_tiles, n_tile, acc_cols, tmem_cols;
+  int Cout, Cin, ksteps, kc, nsub, chunks_per_tap, real_slots, stages;
   int pix_per_img;
+  float inv_tiles_per_img, inv_tiles_x, inv_tw;  // reciprocals for the small integer divisions of the tile scheduler
+  int a_bufs, b_resident, b_stages;  // halo kernel
+  int epi_split;                     // epilogue warps = 4 * epi_split
   signed char tap_map[MAX_TAPS], tap_dx[MAX_TAPS], tap_dy[MAX_TAPS];
   const float* bias;
   const float* chan_scale;
@@ -61,6 +68,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -72,13 +82,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU.
+// Bounded wait (try_wait itself suspends the thread for a hardware time slice, so 2^22 failed polls are seconds):
+// a protocol bug traps instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) {
-      printf("lpc conv_tc: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+    if (++spins > (1u << 22)) {
+      printf("lpc conv_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
       __trap();
     }
   }
@@ -129,42 +139,170 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major shared-memory matrix descriptor (sm_100 format: version 1 at bit 46).
-//   layout: 2 = 128B swizzle, 4 = 64B, 6 = 32B; sbo = bytes between 8-row groups; lbo unused (=1).
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
+//   layout: 0 = no swizzle (core matrices of 8 rows x 16 B; lbo = bytes between the two K core matrices of a K=16
+//   slice, sbo = bytes between 8-row groups), 2 = 128B swizzle, 4 = 64B, 6 = 32B (lbo unused, sbo = 8 * row bytes).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)layout << 61;
   return d;
 }
+__device__ __forceinline__ uint32_t make_idesc(int n_tile) {
+  // c = f32 (bit 4), a = b = bf16 (bits 7, 10), both K-major, N >> 3 at bit 17, M = 128 (>> 4) at bit 24
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_tile >> 3) << 17) | ((128u >> 4) << 24);
+}
 
-// ---- the kernel ----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_NT)
-conv_tc_kernel(const __grid_constant__ TmapPack maps, const __grid_constant__ ConvTcParams p) {
+// exact n / d for 0 <= n < 2^24 via one float multiply and a fix-up (integer division costs ~25 instructions)
+__device__ __forceinline__ int fast_div(int n, int d, float inv) {
+  int q = __float2int_rz(__int2float_rz(n) * inv);
+  const int r = n - q * d;
+  q += (r >= d) ? 1 : 0;
+  q -= (r < 0) ? 1 : 0;
+  return q;
+}
+
+// ---- bias through the tensor core ---------------------------------------------------------------------------
+// The accumulator is INITIALISED by one extra K=16 MMA: A = "ones" tile (every row = [1, 1, 0...]), B = per output
+// channel [bias_hi, bias_lo, 0...] (bf16 hi/lo split: 16 mantissa bits).  Both tiles are un-swizzled K-major core
+// matrices written once per CTA with ordinary stores, then published to the async proxy.
+constexpr int ONES_BYTES = 2 * 128 * 16;
+__device__ __forceinline__ void write_bias_tiles(uint32_t ones_addr, uint32_t bias_addr, const float* bias, int n0, int n_tile) {
+  // generic-proxy stores through 32-bit shared addresses
+  for (int i = threadIdx.x; i < 2 * 128 * 4; i += blockDim.x) {          // 2 planes x 128 rows x 4 words
+    const int plane = i >> 9, w = i & 3;
+    const uint32_t v = (plane == 0 && w == 0) ? 0x3F803F80u : 0u;          // bf16 (1.0, 1.0)
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(ones_addr + (uint32_t)i * 4u), "r"(v) : "memory");
+  }
+  for (int i = threadIdx.x; i < 2 * n_tile * 4; i += blockDim.x) {
+    const int plane = i / (n_tile * 4), rem = i - plane * n_tile * 4;
+    const int row = rem >> 2, w = rem & 3;
+    uint32_t v = 0u;
+    if (plane == 0 && w == 0 && bias) {
+      const float b = bias[n0 + row];
+      const bf16 hi = __float2bfloat16_rn(b);
+      const bf16 lo = __float2bfloat16_rn(b - __bfloat162float(hi));
+      v = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+    }
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(bias_addr + (uint32_t)i * 4u), "r"(v) : "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void issue_bias_mma(uint32_t acc, uint32_t ones_addr, uint32_t bias_addr, int n_tile, uint32_t idesc) {
+  umma_bf16(acc, smem_desc(ones_addr, 128u * 16u, 128u, 0u), smem_desc(bias_addr, (uint32_t)n_tile * 16u, 128u, 0u), idesc, 0u);
+}
+
+// ---- epilogue: one accumulator tile (128 rows x n_tile columns) -> NHWC bf16 --------------------------------
+template <int ACT>
+__device__ __forceinline__ void store16(const uint32_t* v, bf16* yrow, const bf16* rrow, const float* srow) {
+  float f[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float t = __uint_as_float(v[i]);
+    f[i] = ACT == LPC_ACT_MISH ? mish_<false>(t) : ACT == LPC_ACT_SILU ? silu_<false>(t) : ACT == LPC_ACT_NONE ? t : apply_act<false>(t, ACT);
+  }
+  if (srow) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] *= __ldg(srow + i);
+  }
+  if (rrow) {
+    float r8[8];
+    ld_vec<bf16>(rrow).unpack(r8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] += r8[i];
+    ld_vec<bf16>(rrow + 8).unpack(r8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[8 + i] += r8[i];
+  }
+  Vec<bf16> o;
+  o.pack(f);
+  st_vec<bf16>(yrow, o);
+  o.pack(f + 8);
+  st_vec<bf16>(yrow + 8, o);
+}
+
+template <int ACT>
+__device__ __forceinline__ void epilogue_cols(uint32_t trow, int c, int c_end, bool valid, bf16* yrow, const bf16* rrow, const float* srow) {
+  for (; c + 32 <= c_end; c += 32) {
+    uint32_t v0[16], v1[16];
+    tmem_ld16(trow + (uint32_t)c, v0);
+    tmem_ld16(trow + (uint32_t)c + 16, v1);
+    tmem_ld_wait();
+    if (valid) {
+      store16<ACT>(v0, yrow + c, rrow ? rrow + c : nullptr, srow ? srow + c : nullptr);
+      store16<ACT>(v1, yrow + c + 16, rrow ? rrow + c + 16 : nullptr, srow ? srow + c + 16 : nullptr);
+    }
+  }
+  for (; c < c_end; c += 16) {
+    uint32_t v0[16];
+    tmem_ld16(trow + (uint32_t)c, v0);
+    tmem_ld_wait();
+    if (valid) store16<ACT>(v0, yrow + c, rrow ? rrow + c : nullptr, srow ? srow + c : nullptr);
+  }
+}
+
+__device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, uint32_t tmem_acc, int warp, int lane, int img, int x0,
+                                              int y0, int n0) {
+  const int q = warp & 3;              // TMEM lane quarter this warp may read
+  const int part = (warp - 2) >> 2;    // column partition when 8 epilogue warps share a tile
+  const int r = q * 32 + lane;
+  const int ty = fast_div(r, p.TW, p.inv_tw), tx = r - ty * p.TW;
+  const int ox = x0 + tx, oy = y0 + ty;
+  const bool valid = (ty < p.TH) && ox < p.Wo && oy < p.Ho;
+  const long long pix = ((long long)img * p.Ho + oy) * p.Wo + ox;
+  bf16* yrow = p.y + pix * p.y_ld + n0;
+  const bf16* rrow = p.res ? p.res + pix * p.res_ld + n0 : nullptr;
+  const float* srow = p.chan_scale ? p.chan_scale + (pix / p.pix_per_img) * p.Cout + n0 : nullptr;
+  const int cols = p.n_tile / p.epi_split;
+  const int c0 = part * cols, c_end = c0 + cols;
+  const uint32_t trow = tmem_acc + ((uint32_t)(q * 32) << 16);
+  switch (p.act) {
+    case LPC_ACT_MISH: epilogue_cols<LPC_ACT_MISH>(trow, c0, c_end, valid, yrow, rrow, srow); break;
+    case LPC_ACT_SILU: epilogue_cols<LPC_ACT_SILU>(trow, c0, c_end, valid, yrow, rrow, srow); break;
+    case LPC_ACT_NONE: epilogue_cols<LPC_ACT_NONE>(trow, c0, c_end, valid, yrow, rrow, srow); break;
+    case LPC_ACT_SIGMOID: epilogue_cols<LPC_ACT_SIGMOID>(trow, c0, c_end, valid, yrow, rrow, srow); break;
+    default: epilogue_cols<LPC_ACT_RELU>(trow, c0, c_end, valid, yrow, rrow, srow); break;
+  }
+}
+
+struct TileCoord {
+  int img, x0, y0;
+};
+__device__ __forceinline__ TileCoord tile_coord(const ConvTcParams& p, int m_idx) {
+  const int per_img = p.tiles_x * p.tiles_y;
+  TileCoord t;
+  t.img = fast_div(m_idx, per_img, p.inv_tiles_per_img);
+  const int rem = m_idx - t.img * per_img;
+  const int tyi = fast_div(rem, p.tiles_x, p.inv_tiles_x);
+  t.x0 = (rem - tyi * p.tiles_x) * p.TW;
+  t.y0 = tyi * p.TH;
+  return t;
+}
+
+// ---- kernel 1: per-tap TMA boxes ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(320, 2)
+conv_tc_taps_kernel(const __grid_constant__ TmapPack maps, const __grid_constant__ ConvTcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  __shared__ __align__(8) unsigned long long bars[2 * MAX_STAGES + 1];
+  __shared__ __align__(8) unsigned long long bars[2 * MAX_STAGES + 4];
   __shared__ uint32_t tmem_base_slot;
 
-  // dynamic smem may not be 1024-aligned by default: align manually (host adds 1 KB of slack)
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t ones_addr = (smem_u32(smem_raw) + 1023u) & ~1023u;   // [ones | bias | pad] precede the stage ring
+  const uint32_t bias_addr = ones_addr + ONES_BYTES;
+  const uint32_t smem_base = (bias_addr + (uint32_t)p.n_tile * 32u + 1023u) & ~1023u;
   const int b_stage_bytes = p.n_tile * 128;
   const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(&bars[0]);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
-  const uint32_t accum_bar = bar0 + 8u * (2 * MAX_STAGES);
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * MAX_STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * MAX_STAGES + 2 + b); };
 
-  // tile coordinates
-  const int tiles_per_img = p.tiles_x * p.tiles_y;
-  const int img = blockIdx.x / tiles_per_img;
-  const int trem = blockIdx.x - img * tiles_per_img;
-  const int tyi = trem / p.tiles_x, txi = trem - tyi * p.tiles_x;
-  const int x0 = txi * p.TW, y0 = tyi * p.TH;
-  const int n0 = blockIdx.y * p.n_tile;
+  const int n_idx = blockIdx.x % p.n_tiles;
+  const int m_first = blockIdx.x / p.n_tiles, m_step = gridDim.x / p.n_tiles;
+  const int n0 = n_idx * p.n_tile;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&maps.a[0]);
@@ -173,111 +311,228 @@ conv_tc_kernel(const __grid_constant__ TmapPack maps, const __grid_constant__ Co
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 4 * p.epi_split);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), (uint32_t)p.tmem_cols);
+  write_bias_tiles(ones_addr, bias_addr, p.bias, n_idx * p.n_tile, p.n_tile);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
   if (warp == 0) {
-    // ===== TMA producer =====
     if (lane == 0) {
-      const int rows = p.TW * p.TH;
-      const uint32_t tx_bytes = (uint32_t)(rows * 128 + b_stage_bytes);
+      const uint32_t tx_bytes = (uint32_t)(p.TW * p.TH * 128 + b_stage_bytes);
       const int sub_bytes = 256 * p.kc;
-      for (int ks = 0; ks < p.ksteps; ++ks) {
-        const int s = ks % p.stages;
-        const uint32_t ph = (uint32_t)((ks / p.stages) & 1);
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        const uint32_t a_dst = smem_base + (uint32_t)(s * stage_bytes);
-        const uint32_t b_dst = a_dst + A_STAGE_BYTES;
-        mbar_expect_tx(full_bar(s), tx_bytes);
-        for (int j = 0; j < p.nsub; ++j) {
-          int q = ks * p.nsub + j;
-          if (q >= p.real_slots) q = p.real_slots - 1;  // padded K: weights are zero there, any finite A will do
-          const int tap = q / p.chunks_per_tap;
-          const int c0 = (q - tap * p.chunks_per_tap) * p.kc;
-          tma_load_4d(a_dst + (uint32_t)(j * sub_bytes), &maps.a[p.tap_map[tap]], full_bar(s), c0,
-                      x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], img);
+      int it = 0;
+      for (int m = m_first; m < p.m_tiles; m += m_step) {
+        const TileCoord t = tile_coord(p, m);
+        for (int ks = 0; ks < p.ksteps; ++ks, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (uint32_t)((it / p.stages) & 1);
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const uint32_t a_dst = smem_base + (uint32_t)(s * stage_bytes);
+          mbar_expect_tx(full_bar(s), tx_bytes);
+          for (int j = 0; j < p.nsub; ++j) {
+            int q = ks * p.nsub + j;
+            if (q >= p.real_slots) q = p.real_slots - 1;  // padded K: weights are zero there, any finite A will do
+            const int tap = q / p.chunks_per_tap;
+            const int c0 = (q - tap * p.chunks_per_tap) * p.kc;
+            tma_load_4d(a_dst + (uint32_t)(j * sub_bytes), &maps.a[p.tap_map[tap]], full_bar(s), c0, t.x0 + p.tap_dx[tap],
+                        t.y0 + p.tap_dy[tap], t.img);
+          }
+          tma_load_2d(a_dst + A_STAGE_BYTES, &maps.b, full_bar(s), ks * 64, n0);
         }
-        tma_load_2d(b_dst, &maps.b, full_bar(s), ks * 64, n0);
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc = make_idesc(p.n_tile);
       const uint32_t a_layout = p.kc == 64 ? 2u : (p.kc == 32 ? 4u : 6u);
-      const uint32_t a_sbo = (uint32_t)(16 * p.kc);  // 8 rows * (kc*2) bytes
+      const uint32_t a_sbo = (uint32_t)(16 * p.kc);
       const int sub_bytes = 256 * p.kc;
-      for (int ks = 0; ks < p.ksteps; ++ks) {
-        const int s = ks % p.stages;
-        const uint32_t ph = (uint32_t)((ks / p.stages) & 1);
-        mbar_wait(full_bar(s), ph);
+      int it = 0, tcount = 0;
+      for (int m = m_first; m < p.m_tiles; m += m_step, ++tcount) {
+        const int buf = tcount & 1;
+        mbar_wait(tempty_bar(buf), (uint32_t)(((tcount >> 1) & 1) ^ 1));
         tc_fence_after();
-        const uint32_t a_base = smem_base + (uint32_t)(s * stage_bytes);
-        const uint32_t b_base = a_base + A_STAGE_BYTES;
+        const uint32_t acc = tmem_base + (uint32_t)(buf * p.acc_cols);
+        issue_bias_mma(acc, ones_addr, bias_addr, p.n_tile, idesc);      // accumulator := bias
+        for (int ks = 0; ks < p.ksteps; ++ks, ++it) {
+          const int s = it % p.stages;
+          mbar_wait(full_bar(s), (uint32_t)((it / p.stages) & 1));
+          tc_fence_after();
+          const uint32_t a_base = smem_base + (uint32_t)(s * stage_bytes);
+          const uint32_t b_base = a_base + A_STAGE_BYTES;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int e = k * 16;
-          const int j = e / p.kc;
-          const uint32_t a_addr = a_base + (uint32_t)(j * sub_bytes + (e - j * p.kc) * 2);
-          const uint64_t adesc = smem_desc(a_addr, a_sbo, a_layout);
-          const uint64_t bdesc = smem_desc(b_base + (uint32_t)(k * 32), 1024u, 2u);
-          umma_bf16(tmem_base, adesc, bdesc, idesc, (ks > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            const int e = k * 16;
+            const int j = e / p.kc;
+            const uint32_t a_addr = a_base + (uint32_t)(j * sub_bytes + (e - j * p.kc) * 2);
+            umma_bf16(acc, smem_desc(a_addr, 16u, a_sbo, a_layout), smem_desc(b_base + (uint32_t)(k * 32), 16u, 1024u, 2u), idesc, 1u);
+          }
+          umma_commit(empty_bar(s));
         }
-        umma_commit(empty_bar(s));  // frees this smem stage once the MMAs above have read it
+        umma_commit(tfull_bar(buf));
       }
-      umma_commit(accum_bar);  // accumulator complete
     }
   } else {
-    // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
-    const int q = warp & 3;
-    const int r = q * 32 + lane;  // accumulator row == pixel slot inside the tile
-    const int ty = r / p.TW, tx = r - ty * p.TW;
-    const int ox = x0 + tx, oy = y0 + ty;
-    const bool valid = (r < p.TW * p.TH) && ox < p.Wo && oy < p.Ho;
-    const long long pix = ((long long)img * p.Ho + oy) * p.Wo + ox;
-    bf16* yrow = p.y + pix * p.y_ld + n0;
-    const bf16* rrow = p.res ? p.res + pix * p.res_ld + n0 : nullptr;
-    const float* srow = p.chan_scale ? p.chan_scale + (pix / p.pix_per_img) * p.Cout + n0 : nullptr;
-    const float* brow = p.bias ? p.bias + n0 : nullptr;
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int c = 0; c < p.n_tile; c += 16) {
-      uint32_t v[16];
-      tmem_ld16(trow + (uint32_t)c, v);
-      tmem_ld_wait();
-      if (valid) {
-        float f[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float t = __uint_as_float(v[i]) + (brow ? __ldg(brow + c + i) : 0.f);
-          f[i] = apply_act<false>(t, p.act);
-        }
-        if (srow) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] *= __ldg(srow + c + i);
-        }
-        if (rrow) {
-          float r8[8];
-          ld_vec<bf16>(rrow + c).unpack(r8);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] += r8[i];
-          ld_vec<bf16>(rrow + c + 8).unpack(r8);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) f[8 + i] += r8[i];
-        }
-        Vec<bf16> o;
-        o.pack(f);
-        st_vec<bf16>(yrow + c, o);
-        o.pack(f + 8);
-        st_vec<bf16>(yrow + c + 8, o);
+    int tcount = 0;
+    for (int m = m_first; m < p.m_tiles; m += m_step, ++tcount) {
+      const TileCoord t = tile_coord(p, m);
+      const int buf = tcount & 1;
+      mbar_wait(tfull_bar(buf), (uint32_t)((tcount >> 1) & 1));
+      tc_fence_after();
+      epilogue_tile(p, tmem_base + (uint32_t)(buf * p.acc_cols), warp, lane, t.img, t.x0, t.y0, n0);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(buf));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ---- kernel 2: 3x3 stride-1 conv from one halo patch per tile ---------------------------------------------
+__global__ void __launch_bounds__(320, 2)
+conv_tc_halo_kernel(const __grid_constant__ TmapPack maps, const __grid_constant__ ConvTcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long bars[4 * MAX_STAGES + 4];
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t ones_addr = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bias_addr = ones_addr + ONES_BYTES;
+  const uint32_t smem_base = (bias_addr + (uint32_t)p.n_tile * 32u + 1023u) & ~1023u;
+  const int b_block = p.n_tile * 128;
+  const int b_blocks = p.b_resident ? p.ksteps : p.b_stages;
+  const int planes = p.Cin / 8;
+  const int halo_bytes = planes * HALO_PLANE_BYTES;
+  const uint32_t a_region = smem_base + (uint32_t)(b_blocks * b_block);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(&bars[0]);
+  auto bfull_bar = [&](int s) { return bar0 + 8u * s; };
+  auto bempty_bar = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
+  auto afull_bar = [&](int s) { return bar0 + 8u * (2 * MAX_STAGES + s); };
+  auto aempty_bar = [&](int s) { return bar0 + 8u * (3 * MAX_STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (4 * MAX_STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (4 * MAX_STAGES + 2 + b); };
+
+  const int n_idx = blockIdx.x % p.n_tiles;
+  const int m_first = blockIdx.x / p.n_tiles, m_step = gridDim.x / p.n_tiles;
+  const int n0 = n_idx * p.n_tile;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&maps.a[0]);
+    prefetch_tmap(&maps.b);
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      mbar_init(bfull_bar(s), 1);
+      mbar_init(bempty_bar(s), 1);
+    }
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      mbar_init(afull_bar(s), 1);
+      mbar_init(aempty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 4 * p.epi_split);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), (uint32_t)p.tmem_cols);
+  write_bias_tiles(ones_addr, bias_addr, p.bias, n_idx * p.n_tile, p.n_tile);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      if (p.b_resident) {
+        mbar_expect_tx(bfull_bar(0), (uint32_t)(p.ksteps * b_block));
+        for (int ks = 0; ks < p.ksteps; ++ks) tma_load_2d(smem_base + (uint32_t)(ks * b_block), &maps.b, bfull_bar(0), ks * 64, n0);
       }
+      const uint32_t a_tx = (uint32_t)(planes * HALO_PW * HALO_PH * 16);
+      int tcount = 0, bit = 0;
+      for (int m = m_first; m < p.m_tiles; m += m_step, ++tcount) {
+        const TileCoord t = tile_coord(p, m);
+        const int ab = tcount % p.a_bufs;
+        mbar_wait(aempty_bar(ab), (uint32_t)(((tcount / p.a_bufs) & 1) ^ 1));
+        mbar_expect_tx(afull_bar(ab), a_tx);
+        const uint32_t a_dst = a_region + (uint32_t)(ab * halo_bytes);
+        for (int pl = 0; pl < planes; ++pl)
+          tma_load_4d(a_dst + (uint32_t)(pl * HALO_PLANE_BYTES), &maps.a[0], afull_bar(ab), pl * 8, t.x0 - 1, t.y0 - 1, t.img);
+        if (!p.b_resident) {
+          for (int ks = 0; ks < p.ksteps; ++ks, ++bit) {
+            const int s = bit % p.b_stages;
+            mbar_wait(bempty_bar(s), (uint32_t)(((bit / p.b_stages) & 1) ^ 1));
+            mbar_expect_tx(bfull_bar(s), (uint32_t)b_block);
+            tma_load_2d(smem_base + (uint32_t)(s * b_block), &maps.b, bfull_bar(s), ks * 64, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(p.n_tile);
+      const int kreal = 9 * p.Cin;
+      if (p.b_resident) mbar_wait(bfull_bar(0), 0);
+      int tcount = 0, bit = 0;
+      for (int m = m_first; m < p.m_tiles; m += m_step, ++tcount) {
+        const int buf = tcount & 1;
+        const int ab = tcount % p.a_bufs;
+        mbar_wait(tempty_bar(buf), (uint32_t)(((tcount >> 1) & 1) ^ 1));
+        mbar_wait(afull_bar(ab), (uint32_t)((tcount / p.a_bufs) & 1));
+        tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)(buf * p.acc_cols);
+        const uint32_t a_buf = a_region + (uint32_t)(ab * halo_bytes);
+        issue_bias_mma(acc, ones_addr, bias_addr, p.n_tile, idesc);      // accumulator := bias
+        int tap = 0, c = 0;  // K cursor: k = tap*Cin + c
+        for (int ks = 0; ks < p.ksteps; ++ks) {
+          uint32_t b_base;
+          if (p.b_resident) {
+            b_base = smem_base + (uint32_t)(ks * b_block);
+          } else {
+            const int s = bit % p.b_stages;
+            mbar_wait(bfull_bar(s), (uint32_t)((bit / p.b_stages) & 1));
+            tc_fence_after();
+            b_base = smem_base + (uint32_t)(s * b_block);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const bool real = (ks * 64 + k * 16) < kreal;
+            const int tp = real ? tap : 0, cc = real ? c : 0;  // padded K: zero weights, any finite A
+            const int ty = tp / 3, tx = tp - ty * 3;
+            const uint32_t a_addr = a_buf + (uint32_t)((cc >> 3) * HALO_PLANE_BYTES + (ty * HALO_PW + tx) * 16);
+            umma_bf16(acc, smem_desc(a_addr, (uint32_t)HALO_PLANE_BYTES, (uint32_t)(HALO_PW * 16), 0u),
+                      smem_desc(b_base + (uint32_t)(k * 32), 16u, 1024u, 2u), idesc, 1u);
+            c += 16;
+            if (c >= p.Cin) { c = 0; ++tap; }
+          }
+          if (!p.b_resident) {
+            umma_commit(bempty_bar(bit % p.b_stages));
+            ++bit;
+          }
+        }
+        umma_commit(aempty_bar(ab));
+        umma_commit(tfull_bar(buf));
+      }
+    }
+  } else {
+    int tcount = 0;
+    for (int m = m_first; m < p.m_tiles; m += m_step, ++tcount) {
+      const TileCoord t = tile_coord(p, m);
+      const int buf = tcount & 1;
+      mbar_wait(tfull_bar(buf), (uint32_t)((tcount >> 1) & 1));
+      tc_fence_after();
+      epilogue_tile(p, tmem_base + (uint32_t)(buf * p.acc_cols), warp, lane, t.img, t.x0, t.y0, n0);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(buf));
     }
   }
   tc_fence_before();
@@ -303,11 +558,22 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
 int pick_kc(int Cin) { return Cin % 64 == 0 ? 64 : (Cin % 32 == 0 ? 32 : 16); }
 
-int pick_ntile(int Cout) {
-  for (int nt = (Cout + 255) / 256; nt <= Cout / 16; ++nt)
-    if (Cout % nt == 0 && (Cout / nt) % 16 == 0 && Cout / nt <= 256) return Cout / nt;
+int pick_ntile(int Cout, int max_tile) {
+  for (int nt = (Cout + max_tile - 1) / max_tile; nt <= Cout / 16; ++nt)
+    if (Cout % nt == 0 && (Cout / nt) % 16 == 0 && Cout / nt <= max_tile) return Cout / nt;
   return 0;
 }
 
@@ -320,29 +586,38 @@ void pick_tile(int Ho, int Wo, int* TW, int* TH) {
     if (th < 1) continue;
     const double tiles = (double)((Ho + th - 1) / th) * ((Wo + tw - 1) / tw);
     const double eff = (double)Ho * Wo / (tiles * 128.0);
-    if (eff > best + 1e-9 || (eff > best - 1e-9 && tw > bw)) { best = eff; bw = tw; bh = th; }
+    // prefer squarer patches among equally efficient ones (less halo re-read from L2): minimise (tw+2)*(th+2)
+    const double halo = (double)(tw + 2) * (th + 2);
+    const double bhalo = (double)(bw + 2) * (bh + 2);
+    if (eff > best + 1e-9 || (eff > best - 1e-9 && halo < bhalo)) { best = eff; bw = tw; bh = th; }
   }
   *TW = bw;
   *TH = bh;
 }
 
-int encode_act_map(CUtensorMap* m, const bf16* base, long long ld, int C, long long Wd, long long Hd, long long Bd,
-                   long long sW, long long sH, long long sB, int kc, int TW, int TH) {
+int encode_act_map(CUtensorMap* m, const bf16* base, int C, long long Wd, long long Hd, long long Bd, long long sW,
+                   long long sH, long long sB, int box_c, int TW, int TH, CUtensorMapSwizzle sw) {
   EncodeTiledFn enc = get_encode();
   if (!enc) LPC_FAIL(LPC_E_CUDA, "conv2d_tc: cuTensorMapEncodeTiled not available");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wd, (cuuint64_t)Hd, (cuuint64_t)Bd};
   cuuint64_t strides[3] = {(cuuint64_t)sW * 2, (cuuint64_t)sH * 2, (cuuint64_t)sB * 2};
-  cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)TW, (cuuint32_t)TH, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  const CUtensorMapSwizzle sw = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-  (void)ld;
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(base), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
-    LPC_FAIL(LPC_E_CUDA, "conv2d_tc: activation tensor map encode failed (CUresult %d; C=%d W=%lld H=%lld B=%lld kc=%d box %dx%d)",
-             (int)r, C, Wd, Hd, Bd, kc, TW, TH);
+    LPC_FAIL(LPC_E_CUDA, "conv2d_tc: activation tensor map encode failed (CUresult %d; C=%d W=%lld H=%lld B=%lld box %dx%dx%d)",
+             (int)r, C, Wd, Hd, Bd, box_c, TW, TH);
   return LPC_OK;
 }
+
+CUtensorMapSwizzle swizzle_of(int kc) {
+  return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+constexpr size_t SMEM_LIMIT = 200 * 1024;   // dynamic smem budget per CTA (of 227 KB)
+#define BIAS_REGION(n_tile) ((size_t)ONES_BYTES + (size_t)(n_tile) * 32 + 1024)
+int g_force_mode = 0;                       // 0 auto, 1 taps, 2 halo (tests exercise both paths)
 
 }  // namespace
 
@@ -360,8 +635,14 @@ extern "C" int lpc_conv2d_tc_supported(int Cin, int Cout, int k, int stride, int
   if (k == 2 && (stride != 2 || pad != 0)) return 0;
   if (k == 3 && pad != 1) return 0;
   if (x_ld % 8 || y_ld % 8) return 0;
-  if (pick_ntile(Cout) == 0) return 0;
+  if (pick_ntile(Cout, 256) == 0) return 0;
   return 1;
+}
+
+extern "C" int lpc_conv2d_tc_set_mode(int mode) {
+  const int old = g_force_mode;
+  if (mode >= 0 && mode <= 2) g_force_mode = mode;
+  return old;
 }
 
 extern "C" int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int Cin, const void* w, const float* bias,
@@ -376,22 +657,18 @@ extern "C" int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int C
   LPC_REQUIRE(stride == 1 || (H % 2 == 0 && W % 2 == 0), "conv2d_tc: stride-2 needs even H, W");
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   const bf16* xb = (const bf16*)x;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) LPC_FAIL(LPC_E_CUDA, "conv2d_tc: cuTensorMapEncodeTiled not available");
 
   ConvTcParams p;
   memset(&p, 0, sizeof(p));
   TmapPack maps;
   memset(&maps, 0, sizeof(maps));
-  p.kc = pick_kc(Cin);
-  p.nsub = 64 / p.kc;
-  p.chunks_per_tap = Cin / p.kc;
   const int ntaps = k * k;
-  p.real_slots = ntaps * p.chunks_per_tap;
   const int kpad = lpc_conv2d_tc_kpad(Cin, k);
-  p.ksteps = kpad / 64;
+  p.Cin = Cin;
   p.Cout = Cout;
-  p.n_tile = pick_ntile(Cout);
-  p.tmem_cols = 32;
-  while (p.tmem_cols < p.n_tile) p.tmem_cols <<= 1;
+  p.ksteps = kpad / 64;
   p.pix_per_img = Ho * Wo;
   p.bias = bias;
   p.chan_scale = chan_scale;
@@ -401,41 +678,98 @@ extern "C" int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int C
   p.y_ld = y_ld;
   p.act = act;
 
-  if (k == 1) {
-    // flat GEMM view: one "image" of M x 1 pixels
-    const long long M = (long long)B * H * W;
-    LPC_REQUIRE(M < (1ll << 31), "conv2d_tc: too many pixels");
-    p.B = 1; p.Ho = 1; p.Wo = (int)M; p.TW = 128; p.TH = 1;
-    p.tiles_x = (int)((M + 127) / 128); p.tiles_y = 1;
-    p.tap_map[0] = 0; p.tap_dx[0] = 0; p.tap_dy[0] = 0;
-    if (int e = encode_act_map(&maps.a[0], xb, x_ld, Cin, M, 1, 1, x_ld, (long long)M * x_ld, (long long)M * x_ld, p.kc, 128, 1)) return e;
-  } else {
-    p.B = B; p.Ho = Ho; p.Wo = Wo;
-    pick_tile(Ho, Wo, &p.TW, &p.TH);
-    p.tiles_x = (Wo + p.TW - 1) / p.TW;
-    p.tiles_y = (Ho + p.TH - 1) / p.TH;
-    if (stride == 1) {
-      for (int t = 0; t < ntaps; ++t) { p.tap_map[t] = 0; p.tap_dx[t] = (signed char)(t % k - pad); p.tap_dy[t] = (signed char)(t / k - pad); }
-      if (int e = encode_act_map(&maps.a[0], xb, x_ld, Cin, W, H, B, x_ld, (long long)W * x_ld, (long long)H * W * x_ld, p.kc, p.TW, p.TH)) return e;
-    } else {
-      // parity maps: map (py,px) views pixels (2*hy+py, 2*hx+px)
-      for (int py = 0; py < 2; ++py)
-        for (int px = 0; px < 2; ++px)
-          if (int e = encode_act_map(&maps.a[py * 2 + px], xb + ((long long)py * W + px) * x_ld, x_ld, Cin, (W - px + 1) / 2,
-                                     (H - py + 1) / 2, B, 2ll * x_ld, 2ll * W * x_ld, (long long)H * W * x_ld, p.kc, p.TW, p.TH))
-            return e;
-      for (int t = 0; t < ntaps; ++t) {
-        const int oy = t / k - pad, ox = t % k - pad;          // input offset relative to 2*o
-        const int py = ((oy % 2) + 2) % 2, px = ((ox % 2) + 2) % 2;
-        p.tap_map[t] = (signed char)(py * 2 + px);
-        p.tap_dy[t] = (signed char)((oy - py) / 2);
-        p.tap_dx[t] = (signed char)((ox - px) / 2);
-      }
+  // ---- choose the kernel -------------------------------------------------------------------------------
+  bool halo = false;
+  if (k == 3 && stride == 1 && g_force_mode != 1) {
+    const long long tiles = (long long)((Wo + HALO_TW - 1) / HALO_TW) * ((Ho + HALO_TH - 1) / HALO_TH);
+    const double eff = (double)Ho * Wo / (double)(tiles * 128);
+    const size_t halo_bytes = (size_t)(Cin / 8) * HALO_PLANE_BYTES;
+    // weights resident if they fit next to two halo buffers, else a 3-block ring with full-width N tiles
+    int nt = pick_ntile(Cout, 256);
+    size_t need = (size_t)p.ksteps * nt * 128 + 2 * halo_bytes;
+    int resident = 1;
+    if (need > SMEM_LIMIT) {
+      resident = 0;
+      need = (size_t)3 * nt * 128 + 2 * halo_bytes;
+    }
+    if ((eff >= 0.7 || g_force_mode == 2) && need <= SMEM_LIMIT) {
+      halo = true;
+      p.n_tile = nt;
+      p.b_resident = resident;
+      p.b_stages = resident ? 0 : 3;
+      // deep activation prefetch: small-C layers are HBM-bound and need tens of KB in flight per SM
+      const size_t b_bytes = need - 2 * halo_bytes;
+      const size_t budget = (nt <= 128 && b_bytes + 3 * halo_bytes <= 100 * 1024) ? 100 * 1024 : SMEM_LIMIT;  // 2 CTAs/SM when small
+      int ab = (int)((budget - b_bytes) / halo_bytes);
+      p.a_bufs = ab > MAX_STAGES ? MAX_STAGES : (ab < 2 ? 2 : ab);
     }
   }
+  if (!halo) p.n_tile = pick_ntile(Cout, 256);
+  p.n_tiles = Cout / p.n_tile;
+  p.acc_cols = 32;
+  while (p.acc_cols < p.n_tile) p.acc_cols <<= 1;
+  p.tmem_cols = 2 * p.acc_cols;
+  p.epi_split = (p.n_tile % 32 == 0) ? 2 : 1;
+
+  size_t smem = 0;
+  if (halo) {
+    p.B = B; p.Ho = Ho; p.Wo = Wo; p.TW = HALO_TW; p.TH = HALO_TH;
+    p.tiles_x = (Wo + HALO_TW - 1) / HALO_TW;
+    p.tiles_y = (Ho + HALO_TH - 1) / HALO_TH;
+    if (int e = encode_act_map(&maps.a[0], xb, Cin, W, H, B, x_ld, (long long)W * x_ld, (long long)H * W * x_ld, 8, HALO_PW, HALO_PH,
+                               CU_TENSOR_MAP_SWIZZLE_NONE))
+      return e;
+    smem = (size_t)(p.b_resident ? p.ksteps : p.b_stages) * p.n_tile * 128 + (size_t)p.a_bufs * (Cin / 8) * HALO_PLANE_BYTES + 1024 + BIAS_REGION(p.n_tile);
+  } else {
+    p.kc = pick_kc(Cin);
+    p.nsub = 64 / p.kc;
+    p.chunks_per_tap = Cin / p.kc;
+    p.real_slots = ntaps * p.chunks_per_tap;
+    const CUtensorMapSwizzle sw = swizzle_of(p.kc);
+    if (k == 1) {
+      const long long M = (long long)B * H * W;
+      LPC_REQUIRE(M < (1ll << 31), "conv2d_tc: too many pixels");
+      p.B = 1; p.Ho = 1; p.Wo = (int)M; p.TW = 128; p.TH = 1;
+      p.tiles_x = (int)((M + 127) / 128); p.tiles_y = 1;
+      if (int e = encode_act_map(&maps.a[0], xb, Cin, M, 1, 1, x_ld, (long long)M * x_ld, (long long)M * x_ld, p.kc, 128, 1, sw)) return e;
+    } else {
+      p.B = B; p.Ho = Ho; p.Wo = Wo;
+      pick_tile(Ho, Wo, &p.TW, &p.TH);
+      p.tiles_x = (Wo + p.TW - 1) / p.TW;
+      p.tiles_y = (Ho + p.TH - 1) / p.TH;
+      if (stride == 1) {
+        for (int t = 0; t < ntaps; ++t) { p.tap_map[t] = 0; p.tap_dx[t] = (signed char)(t % k - pad); p.tap_dy[t] = (signed char)(t / k - pad); }
+        if (int e = encode_act_map(&maps.a[0], xb, Cin, W, H, B, x_ld, (long long)W * x_ld, (long long)H * W * x_ld, p.kc, p.TW, p.TH, sw)) return e;
+      } else {
+        for (int py = 0; py < 2; ++py)
+          for (int px = 0; px < 2; ++px)
+            if (int e = encode_act_map(&maps.a[py * 2 + px], xb + ((long long)py * W + px) * x_ld, Cin, (W - px + 1) / 2, (H - py + 1) / 2, B,
+                                       2ll * x_ld, 2ll * W * x_ld, (long long)H * W * x_ld, p.kc, p.TW, p.TH, sw))
+              return e;
+        for (int t = 0; t < ntaps; ++t) {
+          const int oy = t / k - pad, ox = t % k - pad;
+          const int py = ((oy % 2) + 2) % 2, px = ((ox % 2) + 2) % 2;
+          p.tap_map[t] = (signed char)(py * 2 + px);
+          p.tap_dy[t] = (signed char)((oy - py) / 2);
+          p.tap_dx[t] = (signed char)((ox - px) / 2);
+        }
+      }
+    }
+    const int stage_bytes = A_STAGE_BYTES + p.n_tile * 128;
+    // two CTAs per SM when the double-buffered accumulators leave TMEM room, else one CTA with a deeper ring
+    const size_t budget = (p.tmem_cols <= 256) ? 100 * 1024 : SMEM_LIMIT;
+    int stages = (int)(budget / stage_bytes);
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages < 2) stages = 2;
+    p.stages = stages;
+    smem = (size_t)stages * stage_bytes + 1024 + BIAS_REGION(p.n_tile);
+  }
+  p.m_tiles = p.tiles_x * p.tiles_y * p.B;
+  LPC_REQUIRE(p.m_tiles < (1 << 24), "conv2d_tc: too many tiles");
+  p.inv_tiles_per_img = 1.0f / (float)(p.tiles_x * p.tiles_y);
+  p.inv_tiles_x = 1.0f / (float)p.tiles_x;
+  p.inv_tw = 1.0f / (float)p.TW;
   {
-    EncodeTiledFn enc = get_encode();
-    if (!enc) LPC_FAIL(LPC_E_CUDA, "conv2d_tc: cuTensorMapEncodeTiled not available");
     cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)Cout};
     cuuint64_t strides[1] = {(cuuint64_t)kpad * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)p.n_tile};
@@ -445,21 +779,23 @@ extern "C" int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int C
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) LPC_FAIL(LPC_E_CUDA, "conv2d_tc: weight tensor map encode failed (CUresult %d)", (int)r);
   }
-  const int stage_bytes = A_STAGE_BYTES + p.n_tile * 128;
-  int stages = (100 * 1024) / stage_bytes;
-  if (stages > 4) stages = 4;
-  if (stages > p.ksteps) stages = p.ksteps;
-  if (stages < 2) stages = p.ksteps < 2 ? 1 : 2;
-  p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 1024;
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) LPC_FAIL(LPC_E_CUDA, "conv2d_tc: smem attribute: %s", cudaGetErrorString(e));
-    smem_set = 200 * 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e1 = cudaFuncSetAttribute(conv_tc_taps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT + 16 * 1024);
+    cudaError_t e2 = cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT + 16 * 1024);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) LPC_FAIL(LPC_E_CUDA, "conv2d_tc: smem attribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    attr_set = true;
   }
-  dim3 grid((unsigned)(p.tiles_x * p.tiles_y * p.B), (unsigned)(Cout / p.n_tile));
-  conv_tc_kernel<<<grid, TC_NT, smem, (cudaStream_t)stream>>>(maps, p);
+  const int ctas_per_sm = (p.tmem_cols <= 256 && smem <= 110 * 1024) ? 2 : 1;
+  int per_n = (num_sms() * ctas_per_sm) / p.n_tiles;
+  if (per_n < 1) per_n = 1;
+  if (per_n > p.m_tiles) per_n = p.m_tiles;
+  const unsigned grid = (unsigned)(per_n * p.n_tiles);
+  const unsigned threads = 64 + 128 * p.epi_split;
+  if (halo)
+    conv_tc_halo_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(maps, p);
+  else
+    conv_tc_taps_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(maps, p);
   LPC_CHECK_LAUNCH("conv2d_tc");
   return LPC_OK;
 }

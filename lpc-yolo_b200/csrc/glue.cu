@@ -87,37 +87,46 @@ __global__ void pack_input_kernel(const float* __restrict__ x, int B, int C, int
   }
 }
 
-// out[b, c] = mean over HW.  grid (C/32 rounded, B): block 256 = 8 pixel lanes x 32 channels.
+// partial[b, chunk, c] = sum over the chunk's pixels (fixed order: deterministic, no atomics).  grid (chunks, B);
+// 256 threads = 8 pixel lanes x 32 channel lanes looping over channel blocks.
 template <typename T>
-__global__ void global_avgpool_kernel(const T* __restrict__ x, int x_ld, int HW, int C, float* __restrict__ out) {
+__global__ void global_avgpool_kernel(const T* __restrict__ x, int x_ld, int HW, int C, int chunk_pix, float* __restrict__ out) {
   __shared__ float part[8][33];
-  const int b = blockIdx.y;
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int lane_p = threadIdx.x >> 5;
-  float s = 0.f;
-  if (c < C) {
-    const T* base = x + (long long)b * HW * x_ld + c;
-    for (int p = lane_p; p < HW; p += 8) s += to_f(base[(long long)p * x_ld]);
-  }
-  part[lane_p][threadIdx.x & 31] = s;
-  __syncthreads();
-  if (threadIdx.x < 32 && c < C) {
-    float t = 0.f;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int p0 = chunk * chunk_pix, p1 = min(HW, p0 + chunk_pix);
+  const int lane_c = threadIdx.x & 31, lane_p = threadIdx.x >> 5;
+  for (int cb = 0; cb < C; cb += 32) {
+    const int c = cb + lane_c;
+    float s = 0.f;
+    if (c < C) {
+      const T* base = x + (long long)b * HW * x_ld + c;
+      for (int p = p0 + lane_p; p < p1; p += 8) s += to_f(base[(long long)p * x_ld]);
+    }
+    part[lane_p][lane_c] = s;
+    __syncthreads();
+    if (threadIdx.x < 32 && c < C) {
+      float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x];
-    out[(long long)b * C + c] = t / (float)HW;
+      for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x];
+      out[((long long)b * gridDim.x + chunk) * C + c] = t;
+    }
+    __syncthreads();
   }
 }
 
 // tiny per-image MLP on pooled vectors; one block per image.
-__global__ void channel_mlp_kernel(const float* __restrict__ in, int C0, const float* __restrict__ W1,
+__global__ void channel_mlp_kernel(const float* __restrict__ in, int parts, float in_scale, int C0, const float* __restrict__ W1,
                                    const float* __restrict__ b1, int C1, int act1, const float* __restrict__ W2,
                                    const float* __restrict__ b2, int C2, int act2, float* __restrict__ out) {
   extern __shared__ float sm[];
   float* v0 = sm;
   float* v1 = sm + C0;
   const int b = blockIdx.x;
-  for (int i = threadIdx.x; i < C0; i += blockDim.x) v0[i] = in[(long long)b * C0 + i];
+  for (int i = threadIdx.x; i < C0; i += blockDim.x) {
+    float t = 0.f;
+    for (int q = 0; q < parts; ++q) t += in[((long long)b * parts + q) * C0 + i];
+    v0[i] = t * in_scale;
+  }
   __syncthreads();
   for (int o = threadIdx.x; o < C1; o += blockDim.x) {
     float s = b1 ? b1[o] : 0.f;
@@ -136,62 +145,83 @@ __global__ void channel_mlp_kernel(const float* __restrict__ in, int C0, const f
   }
 }
 
-// one warp per pixel: mean_c and max_c of x*ca
+// LPP lanes (a power of two <= 32) share one pixel, each owning 16-byte channel vectors: mean_c and max_c of x*ca
 template <typename T>
-__global__ void cbam_stats_kernel(const T* __restrict__ x, int x_ld, int B, int HW, int C, const float* __restrict__ ca,
+__global__ void cbam_stats_kernel(const T* __restrict__ x, int x_ld, int B, int HW, int C, int lpp, const float* __restrict__ ca,
                                   float* __restrict__ stats) {
-  const long long gp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (gp >= (long long)B * HW) return;
-  const int b = (int)(gp / HW);
-  const T* px = x + gp * x_ld;
-  const float* cab = ca + (long long)b * C;
+  constexpr int V = Vec<T>::N;
+  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long gp = gt / lpp;
+  const int sub = (int)(gt - gp * lpp);
+  const bool live = gp < (long long)B * HW;
   float s = 0.f, m = -INFINITY;
-  for (int c = lane; c < C; c += 32) {
-    float v = to_f(px[c]) * cab[c];
-    s += v;
-    m = fmaxf(m, v);
-  }
+  if (live) {
+    const int b = (int)(gp / HW);
+    const T* px = x + gp * x_ld;
+    const float* cab = ca + (long long)b * C;
+    for (int c = sub * V; c < C; c += lpp * V) {
+      float f[V];
+      ldg_vec<T>(px + c).unpack(f);
 #pragma unroll
-  for (int o = 16; o; o >>= 1) {
+      for (int v = 0; v < V; ++v) {
+        const float t = f[v] * __ldg(cab + c + v);
+        s += t;
+        m = fmaxf(m, t);
+      }
+    }
+  }
+  for (int o = lpp >> 1; o; o >>= 1) {
     s += __shfl_xor_sync(0xffffffffu, s, o);
     m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   }
-  if (lane == 0) {
+  if (live && sub == 0) {
     stats[gp * 2] = s / (float)C;
     stats[gp * 2 + 1] = m;
   }
 }
 
-// one warp per pixel: gate = sigmoid(conv_kxk(stats)); y = x*ca*gate
+// same mapping: gate = sigmoid(conv_kxk(stats)) computed cooperatively by the pixel's lanes; y = x*ca*gate
 template <typename T>
-__global__ void cbam_apply_kernel(const T* __restrict__ x, int x_ld, int B, int H, int W, int C, const float* __restrict__ ca,
+__global__ void cbam_apply_kernel(const T* __restrict__ x, int x_ld, int B, int H, int W, int C, int lpp, const float* __restrict__ ca,
                                   const float* __restrict__ stats, const float* __restrict__ w, int k,
                                   T* __restrict__ y, int y_ld) {
-  const long long gp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+  constexpr int V = Vec<T>::N;
+  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long gp = gt / lpp;
+  const int sub = (int)(gt - gp * lpp);
   const long long HW = (long long)H * W;
-  if (gp >= (long long)B * HW) return;
-  const int b = (int)(gp / HW);
-  const int r = (int)(gp - (long long)b * HW);
-  const int oy = r / W, ox = r - oy * W;
-  const int pad = k / 2;
+  const bool live = gp < (long long)B * HW;
   float s = 0.f;
-  for (int t = lane; t < k * k; t += 32) {
-    const int ky = t / k, kx = t - ky * k;
-    const int iy = oy - pad + ky, ix = ox - pad + kx;
-    if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
-    const float* st = stats + ((long long)b * HW + (long long)iy * W + ix) * 2;
-    s = fmaf(st[0], w[t], s);
-    s = fmaf(st[1], w[k * k + t], s);
+  int b = 0;
+  if (live) {
+    b = (int)(gp / HW);
+    const int r = (int)(gp - (long long)b * HW);
+    const int oy = r / W, ox = r - oy * W;
+    const int pad = k / 2;
+    for (int t = sub; t < k * k; t += lpp) {
+      const int ky = t / k, kx = t - ky * k;
+      const int iy = oy - pad + ky, ix = ox - pad + kx;
+      if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+      const float2 st = __ldg(reinterpret_cast<const float2*>(stats) + (long long)b * HW + (long long)iy * W + ix);
+      s = fmaf(st.x, __ldg(w + t), s);
+      s = fmaf(st.y, __ldg(w + k * k + t), s);
+    }
   }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  for (int o = lpp >> 1; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (!live) return;
   const float gate = sigmoid_<true>(s);
   const T* px = x + gp * x_ld;
   T* py = y + gp * y_ld;
   const float* cab = ca + (long long)b * C;
-  for (int c = lane; c < C; c += 32) py[c] = from_f<T>(to_f(px[c]) * cab[c] * gate);
+  for (int c = sub * V; c < C; c += lpp * V) {
+    float f[V];
+    ldg_vec<T>(px + c).unpack(f);
+#pragma unroll
+    for (int v = 0; v < V; ++v) f[v] *= __ldg(cab + c + v) * gate;
+    Vec<T> o;
+    o.pack(f);
+    st_vec<T>(py + c, o);
+  }
 }
 
 template <typename T> int vec_of() { return Vec<T>::N; }
@@ -257,36 +287,57 @@ extern "C" int lpc_pack_input(int dtype, const float* x, int B, int C, int H, in
              (pack_input_kernel<bf16><<<g, 256, 0, s>>>(x, B, C, H, W, (bf16*)y, y_ld, Cpad)), "pack_input")
 }
 
-extern "C" int lpc_global_avgpool(int dtype, const void* x, int x_ld, int B, int HW, int C, float* out, void* stream) {
-  LPC_REQUIRE(x && out && B > 0 && HW > 0 && C > 0 && x_ld >= C, "global_avgpool: bad argument");
-  cudaStream_t s = (cudaStream_t)stream;
-  dim3 g(cdiv(C, 32), B);
-  DISPATCH_T(dtype, (global_avgpool_kernel<float><<<g, 256, 0, s>>>((const float*)x, x_ld, HW, C, out)),
-             (global_avgpool_kernel<bf16><<<g, 256, 0, s>>>((const bf16*)x, x_ld, HW, C, out)), "global_avgpool")
+extern "C" int lpc_global_avgpool_chunks(int B, int HW) {
+  int chunks = (592 + B - 1) / B;             // ~4 CTAs per SM in total
+  const int max_chunks = (HW + 63) / 64;      // at least 64 pixels per chunk
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks > 64) chunks = 64;
+  return chunks < 1 ? 1 : chunks;
 }
 
-extern "C" int lpc_channel_mlp(const float* in, int B, int C0, const float* W1, const float* b1, int C1, int act1,
-                               const float* W2, const float* b2, int C2, int act2, float* out, void* stream) {
-  LPC_REQUIRE(in && W1 && out && B > 0 && C0 > 0 && C1 > 0, "channel_mlp: bad argument");
+extern "C" int lpc_global_avgpool(int dtype, const void* x, int x_ld, int B, int HW, int C, float* partial, void* stream) {
+  LPC_REQUIRE(x && partial && B > 0 && HW > 0 && C > 0 && x_ld >= C, "global_avgpool: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int chunks = lpc_global_avgpool_chunks(B, HW);
+  const int chunk_pix = (HW + chunks - 1) / chunks;
+  dim3 g(chunks, B);
+  DISPATCH_T(dtype, (global_avgpool_kernel<float><<<g, 256, 0, s>>>((const float*)x, x_ld, HW, C, chunk_pix, partial)),
+             (global_avgpool_kernel<bf16><<<g, 256, 0, s>>>((const bf16*)x, x_ld, HW, C, chunk_pix, partial)), "global_avgpool")
+}
+
+extern "C" int lpc_channel_mlp(const float* in, int B, int parts, float in_scale, int C0, const float* W1, const float* b1, int C1,
+                               int act1, const float* W2, const float* b2, int C2, int act2, float* out, void* stream) {
+  LPC_REQUIRE(in && W1 && out && B > 0 && C0 > 0 && C1 > 0 && parts > 0, "channel_mlp: bad argument");
   LPC_REQUIRE((size_t)(C0 + C1) * 4 <= 48 * 1024, "channel_mlp: vectors too large");
-  channel_mlp_kernel<<<B, 256, (size_t)(C0 + C1) * 4, (cudaStream_t)stream>>>(in, C0, W1, b1, C1, act1, W2, b2, C2, act2, out);
+  channel_mlp_kernel<<<B, 256, (size_t)(C0 + C1) * 4, (cudaStream_t)stream>>>(in, parts, in_scale, C0, W1, b1, C1, act1, W2, b2, C2, act2, out);
   LPC_CHECK_LAUNCH("channel_mlp");
   return LPC_OK;
 }
 
+static int lanes_per_pixel(int dtype, int C) {
+  const int V = dtype == LPC_F32 ? 4 : 8;
+  int l = 1;
+  while (l * 2 <= 32 && l * 2 * V <= C) l *= 2;
+  return l;
+}
+
 extern "C" int lpc_cbam_stats(int dtype, const void* x, int x_ld, int B, int HW, int C, const float* ca, float* stats, void* stream) {
   LPC_REQUIRE(x && ca && stats && x_ld >= C, "cbam_stats: bad argument");
+  if (int e = check_vec("cbam_stats", dtype, C, x_ld, x_ld, x, x)) return e;
   cudaStream_t s = (cudaStream_t)stream;
-  const int g = cdiv((long long)B * HW * 32, 256);
-  DISPATCH_T(dtype, (cbam_stats_kernel<float><<<g, 256, 0, s>>>((const float*)x, x_ld, B, HW, C, ca, stats)),
-             (cbam_stats_kernel<bf16><<<g, 256, 0, s>>>((const bf16*)x, x_ld, B, HW, C, ca, stats)), "cbam_stats")
+  const int lpp = lanes_per_pixel(dtype, C);
+  const int g = cdiv((long long)B * HW * lpp, 256);
+  DISPATCH_T(dtype, (cbam_stats_kernel<float><<<g, 256, 0, s>>>((const float*)x, x_ld, B, HW, C, lpp, ca, stats)),
+             (cbam_stats_kernel<bf16><<<g, 256, 0, s>>>((const bf16*)x, x_ld, B, HW, C, lpp, ca, stats)), "cbam_stats")
 }
 
 extern "C" int lpc_cbam_apply(int dtype, const void* x, int x_ld, int B, int H, int W, int C, const float* ca,
                               const float* stats, const float* w, int k, void* y, int y_ld, void* stream) {
   LPC_REQUIRE(x && ca && stats && w && y && (k == 3 || k == 7), "cbam_apply: bad argument");
+  if (int e = check_vec("cbam_apply", dtype, C, x_ld, y_ld, x, y)) return e;
   cudaStream_t s = (cudaStream_t)stream;
-  const int g = cdiv((long long)B * H * W * 32, 256);
-  DISPATCH_T(dtype, (cbam_apply_kernel<float><<<g, 256, 0, s>>>((const float*)x, x_ld, B, H, W, C, ca, stats, w, k, (float*)y, y_ld)),
-             (cbam_apply_kernel<bf16><<<g, 256, 0, s>>>((const bf16*)x, x_ld, B, H, W, C, ca, stats, w, k, (bf16*)y, y_ld)), "cbam_apply")
+  const int lpp = lanes_per_pixel(dtype, C);
+  const int g = cdiv((long long)B * H * W * lpp, 256);
+  DISPATCH_T(dtype, (cbam_apply_kernel<float><<<g, 256, 0, s>>>((const float*)x, x_ld, B, H, W, C, lpp, ca, stats, w, k, (float*)y, y_ld)),
+             (cbam_apply_kernel<bf16><<<g, 256, 0, s>>>((const bf16*)x, x_ld, B, H, W, C, lpp, ca, stats, w, k, (bf16*)y, y_ld)), "cbam_apply")
 }

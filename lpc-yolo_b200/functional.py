@@ -137,6 +137,12 @@ def conv2d(x, pc, out=None, res=None, chan_scale=None):
     use_tc = (pc.w_tc is not None and x.dtype == torch.bfloat16 and xp % 16 == 0 and yp % 16 == 0 and rp % 16 == 0
               and rld % 8 == 0 and L.lpc_conv2d_tc_supported(Cin, pc.cout, pc.k, pc.s, pc.p, xld, yld))
     flops = 2.0 * B * Ho * Wo * pc.cout * Cin * pc.k * pc.k
+    if pc.w_stem is not None and xld == 4 and chan_scale is None and res is None and yld % 8 == 0 and xp % 16 == 0 and yp % 16 == 0:
+        nb = x.element_size() * (B * H * W * 4 + B * Ho * Wo * pc.cout)
+        with _prof("stem_conv", flops, nb, f"3->{pc.cout} k3s{pc.s} {H}x{W} B{B}"):
+            check(L.lpc_stem_conv(dt_code(x.dtype), xp, B, H, W, _fp(pc.w_stem), _fp(pc.bias), pc.s, pc.cout, yp, yld, pc.act,
+                                  _stream()), "stem_conv")
+        return out
     nbytes = x.element_size() * (B * H * W * Cin + B * Ho * Wo * pc.cout * (2 if res is not None else 1) + pc.cout * Cin * pc.k * pc.k)
     tag = f"{Cin}->{pc.cout} k{pc.k}s{pc.s} {H}x{W} B{B}"
     if use_tc:
@@ -237,21 +243,34 @@ def channel_deinterleave(x, out=None):
 
 @_profiled
 def global_avgpool(x):
+    """-> (partial sums [B, chunks, C] fp32, scale = 1/HW); channel_mlp finishes the reduction."""
     B, Cc, H, W = x.shape
-    out = torch.empty((B, Cc), dtype=torch.float32, device=x.device)
+    L = _lib.lib()
+    chunks = L.lpc_global_avgpool_chunks(B, H * W)
+    out = torch.empty((B, chunks, Cc), dtype=torch.float32, device=x.device)
     xp, xld = view_of(x)
-    check(_lib.lib().lpc_global_avgpool(dt_code(x.dtype), xp, xld, B, H * W, Cc, _fp(out), _stream()), "global_avgpool")
-    return out
+    check(L.lpc_global_avgpool(dt_code(x.dtype), xp, xld, B, H * W, Cc, _fp(out), _stream()), "global_avgpool")
+    return out, 1.0 / (H * W)
 
 
 @_profiled
-def channel_mlp(v, W1, b1, act1, W2=None, b2=None, act2=ACT_NONE):
-    B, C0 = v.shape
+def channel_mlp(v, W1, b1, act1, W2=None, b2=None, act2=ACT_NONE, scale=1.0):
+    """v: [B, C0] or partial sums [B, parts, C0] (summed and scaled by ``scale`` on load)."""
+    if v.dim() == 2:
+        v = v.unsqueeze(1)
+    B, parts, C0 = v.shape
     C1 = W1.shape[0]
     C2 = W2.shape[0] if W2 is not None else 0
     out = torch.empty((B, C2 if W2 is not None else C1), dtype=torch.float32, device=v.device)
-    check(_lib.lib().lpc_channel_mlp(_fp(v), B, C0, _fp(W1), _fp(b1), C1, act1, _fp(W2), _fp(b2), C2, act2, _fp(out), _stream()), "channel_mlp")
+    check(_lib.lib().lpc_channel_mlp(_fp(v), B, parts, float(scale), C0, _fp(W1), _fp(b1), C1, act1, _fp(W2), _fp(b2), C2, act2,
+                                     _fp(out), _stream()), "channel_mlp")
     return out
+
+
+def pooled_gate(x, W1, b1, act1, W2=None, b2=None, act2=ACT_NONE):
+    """act2(W2 act1(W1 avgpool(x) + b1) + b2): CBAM's channel attention / SPCA's gate."""
+    part, scale = global_avgpool(x)
+    return channel_mlp(part, W1, b1, act1, W2, b2, act2, scale)
 
 
 @_profiled

@@ -81,12 +81,19 @@ class C2f(LpcModule):
         self.cv2 = Conv((2 + n) * self.c, c2, 1)
         self.m = nn.ModuleList(Bottleneck(self.c, self.c, shortcut, g, k=((3, 3), (3, 3)), e=1.0) for _ in range(n))
 
-    def forward(self, x, out=None):
+    def forward(self, x, out=None, s2d=False):
+        """``s2d=True``: x is the tensor BEFORE a space_to_depth layer; cv1 then runs as a 2x2 stride-2 conv
+        (the s2d + 1x1 fold), so the 4x-channel tensor is never written."""
         x = self._in(x)
         B, _, H, W = x.shape
+        if s2d:
+            H, W = H // 2, W // 2
         c, n = self.c, len(self.m)
         ybuf = F.new_act(B, (2 + n) * c, H, W, x.dtype, x.device)
-        self.cv1(x, out=ybuf[:, : 2 * c])
+        if s2d:
+            self.cv1.forward_s2d(x, out=ybuf[:, : 2 * c])
+        else:
+            self.cv1(x, out=ybuf[:, : 2 * c])
         for i, m in enumerate(self.m):
             m(ybuf[:, (1 + i) * c:(2 + i) * c], out=ybuf[:, (2 + i) * c:(3 + i) * c])
         return self.cv2(ybuf, out=out)
@@ -293,7 +300,7 @@ class SPCA(LpcModule):
         feats = F.new_act(B, 3 * c, H, W, x.dtype, x.device)
         for j, pd in enumerate(dws):
             F.dwconv2d(x, pd, out=feats[:, j * c:(j + 1) * c])
-        gate = F.channel_mlp(F.global_avgpool(x), w1, None, ACT_RELU, w2, None, ACT_SIGMOID)
+        gate = F.pooled_gate(x, w1, None, ACT_RELU, w2, None, ACT_SIGMOID)
         return F.conv2d(feats, pw, out=out, res=x, chan_scale=gate)
 
 

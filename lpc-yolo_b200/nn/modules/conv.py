@@ -45,6 +45,26 @@ class Conv(LpcModule):
 
     forward_fuse = forward  # BN is always folded; kept for API parity (conv.py:52-54)
 
+    def _build_s2d(self, dtype, device):
+        """This 1x1 conv applied to space_to_depth(x) (block.py:4069-4070) == a 2x2 stride-2 conv on x:
+        s2d channel q*C + c holds pixel (2y + (q&1), 2x + (q>>1)), so w2[co, c, ky, kx] = w1[co, (ky + 2*kx)*C + c]."""
+        w, b = pack.fold_bn(self.conv.weight, self.conv.bias, getattr(self, "bn", None))
+        cout, c4 = w.shape[0], w.shape[1]
+        c = c4 // 4
+        w2 = w.view(cout, 2, 2, c).permute(0, 3, 2, 1).contiguous()      # [co, kx, ky, c] -> [co, c, ky, kx]
+        return pack.PackedConv(w2, b, 2, 2, 0, act_code(self.act), dtype, device)
+
+    def forward_s2d(self, x, out=None):
+        """conv1x1(space_to_depth(x)) without materialising the space_to_depth tensor."""
+        assert self.conv.kernel_size == (1, 1) and self.conv.groups == 1 and self.conv.in_channels == 4 * x.shape[1]
+        x = self._in(x)
+        key = ("s2d", x.dtype, x.device)
+        pk = self._pcache.get(key)
+        if pk is None:
+            with torch.no_grad():
+                pk = self._pcache[key] = self._build_s2d(x.dtype, x.device)
+        return F.conv2d(x, pk, out)
+
     def out_shape(self, s):
         B, _, H, W = s
         k, st, p, d = self.conv.kernel_size[0], self.conv.stride[0], self.conv.padding[0], self.conv.dilation[0]
@@ -67,7 +87,7 @@ class ChannelAttention(LpcModule):
 
     def gate(self, x):
         w, b = self._packed(x, self._build)
-        return F.channel_mlp(F.global_avgpool(x), w, b, ACT_SIGMOID)
+        return F.pooled_gate(x, w, b, ACT_SIGMOID)
 
     def forward(self, x):
         x = self._in(x)

@@ -120,6 +120,7 @@ class BaseModel(LpcModule):
     """tasks.py:48-258 for inference."""
 
     compute_dtype = torch.bfloat16
+    fold_s2d = True      # space_to_depth + C2f.cv1 -> one 2x2 stride-2 conv (exact same arithmetic)
 
     def forward(self, x, *args, **kwargs):
         return self.predict(x, *args, **kwargs)
@@ -152,14 +153,21 @@ class BaseModel(LpcModule):
                         dest[src] = (m.i, off)
                     off += c
         live = {i for i, c in consumers.items() if c} | {len(L) - 1}
-        self._plan_cache = (dest, live)
+        # space_to_depth whose only consumer is a C2f: fold it into that block's first 1x1 conv
+        fold = {}
+        for m in L:
+            if isinstance(m, space_to_depth) and self.fold_s2d:
+                cons = consumers[m.i]
+                if len(cons) == 1 and type(L[cons[0]]) is C2f and L[cons[0]].f == -1 and m.i not in self.save:
+                    fold[m.i] = cons[0]
+        self._plan_cache = (dest, live, fold)
         return self._plan_cache
 
     def _predict_once(self, x, tail=None):
         """tasks.py:83-111.  ``tail``: optional callable applied instead of the detect head's forward."""
         if not x.is_cuda:
             raise F.LpcError("lpc-yolo_b200 runs on CUDA tensors only (no CPU fallback)")
-        dest, live = self._plan()
+        dest, live, fold = self._plan()
         if x.dtype not in (torch.bfloat16, torch.float32) or not F.is_nhwc_view(x) or x.dtype != self.compute_dtype:
             x = F.pack_input(x.float().contiguous(), self.compute_dtype) if x.shape[1] <= 4 else F.as_act(x, self.compute_dtype)
         y, catbuf = [], {}
@@ -167,6 +175,13 @@ class BaseModel(LpcModule):
         for m in L:
             if m.i not in live:
                 y.append(None)
+                continue
+            if m.i in fold:            # skipped: the consumer reads our INPUT and applies the s2d fold
+                y.append(None)
+                continue
+            if m.i - 1 in fold and fold[m.i - 1] == m.i:
+                x = m(x, s2d=True)
+                y.append(x if m.i in self.save else None)
                 continue
             if m.f != -1:
                 x = y[m.f] if isinstance(m.f, int) else [x if j == -1 else y[j] for j in m.f]

@@ -38,6 +38,9 @@ class PackedConv:
         self.bias = b.float().to(device).contiguous()
         self.w_direct = w32.permute(2, 3, 1, 0).reshape(k * k, self.cin, self.cout).to(device=device, dtype=dtype).contiguous()
         self.w_tc = None
+        self.w_stem = None
+        if self.cin == 3 and k == 3 and p == 1 and s in (1, 2) and self.cout % 8 == 0 and self.cout <= 96:
+            self.w_stem = w32.permute(2, 3, 1, 0).reshape(27, self.cout).to(device).contiguous()
         if dtype == torch.bfloat16 and self.cin % 16 == 0 and self.cout % 16 == 0 and k in (1, 2, 3):
             kpad = _lib.lib().lpc_conv2d_tc_kpad(self.cin, k)
             if kpad > 0:

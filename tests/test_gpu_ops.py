@@ -139,6 +139,34 @@ def test_conv_tc_is_used_and_slices(M, Fn, oracle, pkg):
     assert (big_out[:, :64] == 7).all() and (big_out[:, 128:] == 7).all()      # neighbours untouched
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("case", [(16, 32, 32, 32, 2), (64, 64, 40, 40, 2), (128, 128, 20, 20, 2), (80, 80, 24, 24, 2),
+                                  (16, 32, 160, 160, 8), (32, 64, 72, 88, 6), (128, 256, 40, 40, 4), (256, 64, 16, 24, 3)])
+def test_conv3x3_both_tc_kernels(M, oracle, pkg, mode, case):
+    """3x3 stride-1 convs through BOTH tensor-core kernels (1 = per-tap TMA boxes, 2 = halo patch with resident or
+    streamed weights), incl. shapes with many more tiles than persistent CTAs and partial edge tiles."""
+    c1, c2, H, W, B = case
+    lib = pkg.lib()
+    mod = _randomize(M.Conv(c1, c2, 3, 1), seed=c1 * 7 + c2)
+    x = _x((B, c1, H, W), torch.bfloat16)
+    ref = oracle._Ctx(_sd(mod, torch.bfloat16)).conv(x, "m", 3, 1, act="silu")
+    old = lib.lpc_conv2d_tc_set_mode(mode)
+    try:
+        got = _run(mod, x, torch.bfloat16)
+        torch.cuda.synchronize()
+    finally:
+        lib.lpc_conv2d_tc_set_mode(old)
+    _cmp(got, ref, torch.bfloat16, f"conv3x3 mode {mode} {case}")
+
+
+def test_conv1x1_many_tiles(M, oracle):
+    """Persistent 1x1 kernel: 3200 M tiles over ~300 CTAs, two N tiles, residual epilogue."""
+    mod = _randomize(M.Conv(64, 512, 1, 1), seed=5)
+    x = _x((4, 64, 160, 160), torch.bfloat16)
+    ref = oracle._Ctx(_sd(mod, torch.bfloat16)).conv(x, "m", 1, 1, act="silu")
+    _cmp(_run(mod, x, torch.bfloat16), ref, torch.bfloat16, "conv1x1 many tiles")
+
+
 # ---- depthwise ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("k,s,d", [(3, 1, 1), (3, 2, 1), (5, 1, 1), (7, 1, 1), (3, 1, 2), (3, 1, 3)])
