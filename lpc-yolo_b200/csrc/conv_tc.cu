@@ -9,9 +9,12 @@
 //     the NHWC activation into 128B/64B/32B-swizzled shared memory (zero padding = TMA out-of-bounds fill; stride-2
 //     convs read through four "parity" tensor maps with doubled W/H strides) plus the [n_tile x 64] weight block.
 //  conv_tc_halo_kernel  (3x3 stride 1 - 72 % of LPC-YOLO's FLOPs)
-//     Per M tile (8 x 16 output pixels) ONE halo patch (10 x 18 pixels, all Cin) is loaded, as Cin/8 un-swizzled
-//     "planes" [pixel][8 channels]; the nine taps are nine shifted UMMA descriptors into that patch (core-matrix
-//     row group = one 8-pixel tile row, SBO = patch row pitch), so the activation crosses L2->SM 1.4x instead of 9x.
+//     Per M tile (8 x 16 output pixels) ONE halo patch (10 x 18 pixels, all Cin) is loaded, pixel-major with
+//     min(Cin,64) channels per row in the 32B/64B/128B-swizzled K-major layout; the nine taps are nine shifted UMMA
+//     descriptors into that patch (8-row group = one 8-pixel tile row, SBO = patch row pitch of 16 pixels so that
+//     every group starts on a swizzle-atom boundary), so the activation crosses L2->SM 1.4x instead of 9x.
+//     (An un-swizzled "planar" patch also works but the tensor core reads un-swizzled operands ~8x slower:
+//     measured 230 cycles per 128x32x16 MMA, profiles/r01_d_halo_trace.txt.)
 //     The weights stay resident in shared memory for the CTA's lifetime when they fit, else stream through a ring.
 //
 // Common structure (one CTA per SM, or two when TMEM/smem allow): warp 0 = TMA producer, warp 1 = TMEM allocator
@@ -21,6 +24,7 @@
 // bounded: a protocol bug traps instead of hanging the GPU.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -31,9 +35,11 @@ namespace {
 constexpr int MAX_STAGES = 8;
 constexpr int A_STAGE_BYTES = 128 * 64 * 2;  // taps kernel: 128 rows x 64 K-elements of bf16
 constexpr int MAX_TAPS = 9;
+constexpr int MAX_HALO_SLICES = 9 * 512 / 16;   // halo kernel handles Cin <= 512
 constexpr int HALO_TW = 8, HALO_TH = 16;
 constexpr int HALO_PW = HALO_TW + 2, HALO_PH = HALO_TH + 2;
-constexpr int HALO_PLANE_BYTES = ((HALO_PW * HALO_PH * 16 + 127) / 128) * 128;  // 2944: TMA wants 128-B aligned targets
+constexpr int HALO_SPW = 16;             // patch row pitch in pixels: a multiple of 8 so every 8-pixel row group starts on a swizzle-atom boundary
+constexpr int HALO_LOADERS = 128;        // four cp.async loader warps; thread t owns patch pixels t and t+128
 
 struct TmapPack {
   CUtensorMap a[4];
@@ -48,7 +54,13 @@ struct ConvTcParams {
   int pix_per_img;
   float inv_tiles_per_img, inv_tiles_x, inv_tw;  // reciprocals for the small integer divisions of the tile scheduler
   int a_bufs, b_resident, b_stages;  // halo kernel
+  const bf16* x;                     // halo kernel: activation base, pixel pitch, input geometry
+  long long x_ld;
+  int H, W;
+  int pitch, slabs, slab_bytes, use_base_offset;   // halo patch: bytes per pixel row (32/64/128), 64-channel slabs
   int epi_split;                     // epilogue warps = 4 * epi_split
+  int dbg;                           // LPC_TC_DBG bits (profiling only): 1 skip MMAs, 2 skip A loads, 4 skip stores, 8 trace
+  unsigned long long* trace;         // [4 roles][64 tiles][4 stamps] of clock64, CTA 0 only
   signed char tap_map[MAX_TAPS], tap_dx[MAX_TAPS], tap_dy[MAX_TAPS];
   const float* bias;
   const float* chan_scale;
@@ -62,6 +74,18 @@ struct ConvTcParams {
 // ---- PTX wrappers ------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One elected lane of a fully converged warp.  Unlike `lane == 0`, the compiler knows that exactly one thread runs the
+// guarded region, so operands of UTCHMMA / UTMALDG / UTCBAR move to uniform registers with plain R2UR instead of an
+// ELECT + BRA.U.ANY "waterfall" loop per instruction (measured: 270 -> ~30 cycles per issued MMA).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -138,6 +162,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {   // wait until at most n groups are pending
+  switch (n) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+    case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+    case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+  }
+}
+
 // K-major shared-memory matrix descriptor (sm_100 format: version 1 at bit 46).
 //   layout: 0 = no swizzle (core matrices of 8 rows x 16 B; lbo = bytes between the two K core matrices of a K=16
 //   slice, sbo = bytes between 8-row groups), 2 = 128B swizzle, 4 = 64B, 6 = 32B (lbo unused, sbo = 8 * row bytes).
@@ -149,6 +190,22 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)layout << 61;
   return d;
+}
+// The same descriptor as two 32-bit halves, so the issue loop only adds a 16-byte-unit offset to the low word.
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | (uint64_t)lo; }
+__device__ __forceinline__ void umma_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.eq.u32 p, 1, 1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc)
+      : "memory");
 }
 __device__ __forceinline__ uint32_t make_idesc(int n_tile) {
   // c = f32 (bit 4), a = b = bf16 (bits 7, 10), both K-major, N >> 3 at bit 17, M = 128 (>> 4) at bit 24
@@ -168,19 +225,21 @@ __device__ __forceinline__ int fast_div(int n, int d, float inv) {
 // The accumulator is INITIALISED by one extra K=16 MMA: A = "ones" tile (every row = [1, 1, 0...]), B = per output
 // channel [bias_hi, bias_lo, 0...] (bf16 hi/lo split: 16 mantissa bits).  Both tiles are un-swizzled K-major core
 // matrices written once per CTA with ordinary stores, then published to the async proxy.
-constexpr int ONES_BYTES = 2 * 128 * 16;
+constexpr int ONES_BYTES = 128 * 32;
 __device__ __forceinline__ void write_bias_tiles(uint32_t ones_addr, uint32_t bias_addr, const float* bias, int n0, int n_tile) {
-  // generic-proxy stores through 32-bit shared addresses
-  for (int i = threadIdx.x; i < 2 * 128 * 4; i += blockDim.x) {          // 2 planes x 128 rows x 4 words
-    const int plane = i >> 9, w = i & 3;
-    const uint32_t v = (plane == 0 && w == 0) ? 0x3F803F80u : 0u;          // bf16 (1.0, 1.0)
+  // Both tiles are [rows][16 bf16 = 32 B] in the 32B-swizzled K-major layout (16-byte chunk h of row r sits at
+  // h ^ ((r >> 2) & 1)); generic-proxy stores through 32-bit shared addresses, published to the async proxy below.
+  for (int i = threadIdx.x; i < 128 * 8; i += blockDim.x) {
+    const int row = i >> 3, w = i & 7;
+    const int lc = (w >> 2) ^ ((row >> 2) & 1);                            // logical chunk held by this physical word
+    const uint32_t v = (lc == 0 && (w & 3) == 0) ? 0x3F803F80u : 0u;       // bf16 (1.0, 1.0) in K = 0, 1
     asm volatile("st.shared.b32 [%0], %1;" ::"r"(ones_addr + (uint32_t)i * 4u), "r"(v) : "memory");
   }
-  for (int i = threadIdx.x; i < 2 * n_tile * 4; i += blockDim.x) {
-    const int plane = i / (n_tile * 4), rem = i - plane * n_tile * 4;
-    const int row = rem >> 2, w = rem & 3;
+  for (int i = threadIdx.x; i < n_tile * 8; i += blockDim.x) {
+    const int row = i >> 3, w = i & 7;
+    const int lc = (w >> 2) ^ ((row >> 2) & 1);
     uint32_t v = 0u;
-    if (plane == 0 && w == 0 && bias) {
+    if (lc == 0 && (w & 3) == 0 && bias) {
       const float b = bias[n0 + row];
       const bf16 hi = __float2bfloat16_rn(b);
       const bf16 lo = __float2bfloat16_rn(b - __bfloat162float(hi));
@@ -191,7 +250,8 @@ __device__ __forceinline__ void write_bias_tiles(uint32_t ones_addr, uint32_t bi
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 __device__ __forceinline__ void issue_bias_mma(uint32_t acc, uint32_t ones_addr, uint32_t bias_addr, int n_tile, uint32_t idesc) {
-  umma_bf16(acc, smem_desc(ones_addr, 128u * 16u, 128u, 0u), smem_desc(bias_addr, (uint32_t)n_tile * 16u, 128u, 0u), idesc, 0u);
+  (void)n_tile;
+  umma_bf16(acc, smem_desc(ones_addr, 16u, 256u, 6u), smem_desc(bias_addr, 16u, 256u, 6u), idesc, 0u);
 }
 
 // ---- epilogue: one accumulator tile (128 rows x n_tile columns) -> NHWC bf16 --------------------------------
@@ -225,16 +285,6 @@ __device__ __forceinline__ void store16(const uint32_t* v, bf16* yrow, const bf1
 
 template <int ACT>
 __device__ __forceinline__ void epilogue_cols(uint32_t trow, int c, int c_end, bool valid, bf16* yrow, const bf16* rrow, const float* srow) {
-  for (; c + 32 <= c_end; c += 32) {
-    uint32_t v0[16], v1[16];
-    tmem_ld16(trow + (uint32_t)c, v0);
-    tmem_ld16(trow + (uint32_t)c + 16, v1);
-    tmem_ld_wait();
-    if (valid) {
-      store16<ACT>(v0, yrow + c, rrow ? rrow + c : nullptr, srow ? srow + c : nullptr);
-      store16<ACT>(v1, yrow + c + 16, rrow ? rrow + c + 16 : nullptr, srow ? srow + c + 16 : nullptr);
-    }
-  }
   for (; c < c_end; c += 16) {
     uint32_t v0[16];
     tmem_ld16(trow + (uint32_t)c, v0);
@@ -243,27 +293,42 @@ __device__ __forceinline__ void epilogue_cols(uint32_t trow, int c, int c_end, b
   }
 }
 
-__device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, uint32_t tmem_acc, int warp, int lane, int img, int x0,
-                                              int y0, int n0) {
+// Per-thread epilogue state that does not depend on the tile: computed once, so the per-tile cost is a handful of
+// integer ops (the whole SM is instruction-issue bound on the small-channel layers, profiles/r01_e_*).
+struct EpiCtx {
+  int ty, tx, c0, c_end;
+  uint32_t lane_off;     // TMEM lane-quarter offset
+  bool row_ok;
+};
+__device__ __forceinline__ EpiCtx make_epi_ctx(const ConvTcParams& p, int warp, int lane) {
+  EpiCtx e;
   const int q = warp & 3;              // TMEM lane quarter this warp may read
   const int part = (warp - 2) >> 2;    // column partition when 8 epilogue warps share a tile
   const int r = q * 32 + lane;
-  const int ty = fast_div(r, p.TW, p.inv_tw), tx = r - ty * p.TW;
-  const int ox = x0 + tx, oy = y0 + ty;
-  const bool valid = (ty < p.TH) && ox < p.Wo && oy < p.Ho;
+  e.ty = fast_div(r, p.TW, p.inv_tw);
+  e.tx = r - e.ty * p.TW;
+  const int cols = p.n_tile / p.epi_split;
+  e.c0 = part * cols;
+  e.c_end = e.c0 + cols;
+  e.lane_off = (uint32_t)(q * 32) << 16;
+  e.row_ok = e.ty < p.TH && !(p.dbg & 4);
+  return e;
+}
+__device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, const EpiCtx& e, uint32_t tmem_acc, int img, int x0, int y0, int n0) {
+  const int ox = x0 + e.tx, oy = y0 + e.ty;
+  const bool valid = e.row_ok && ox < p.Wo && oy < p.Ho;
   const long long pix = ((long long)img * p.Ho + oy) * p.Wo + ox;
   bf16* yrow = p.y + pix * p.y_ld + n0;
   const bf16* rrow = p.res ? p.res + pix * p.res_ld + n0 : nullptr;
-  const float* srow = p.chan_scale ? p.chan_scale + (pix / p.pix_per_img) * p.Cout + n0 : nullptr;
-  const int cols = p.n_tile / p.epi_split;
-  const int c0 = part * cols, c_end = c0 + cols;
-  const uint32_t trow = tmem_acc + ((uint32_t)(q * 32) << 16);
+  const float* srow = nullptr;
+  if (p.chan_scale) srow = p.chan_scale + (pix / p.pix_per_img) * p.Cout + n0;
+  const uint32_t trow = tmem_acc + e.lane_off;
   switch (p.act) {
-    case LPC_ACT_MISH: epilogue_cols<LPC_ACT_MISH>(trow, c0, c_end, valid, yrow, rrow, srow); break;
-    case LPC_ACT_SILU: epilogue_cols<LPC_ACT_SILU>(trow, c0, c_end, valid, yrow, rrow, srow); break;
-    case LPC_ACT_NONE: epilogue_cols<LPC_ACT_NONE>(trow, c0, c_end, valid, yrow, rrow, srow); break;
-    case LPC_ACT_SIGMOID: epilogue_cols<LPC_ACT_SIGMOID>(trow, c0, c_end, valid, yrow, rrow, srow); break;
-    default: epilogue_cols<LPC_ACT_RELU>(trow, c0, c_end, valid, yrow, rrow, srow); break;
+    case LPC_ACT_MISH: epilogue_cols<LPC_ACT_MISH>(trow, e.c0, e.c_end, valid, yrow, rrow, srow); break;
+    case LPC_ACT_SILU: epilogue_cols<LPC_ACT_SILU>(trow, e.c0, e.c_end, valid, yrow, rrow, srow); break;
+    case LPC_ACT_NONE: epilogue_cols<LPC_ACT_NONE>(trow, e.c0, e.c_end, valid, yrow, rrow, srow); break;
+    case LPC_ACT_SIGMOID: epilogue_cols<LPC_ACT_SIGMOID>(trow, e.c0, e.c_end, valid, yrow, rrow, srow); break;
+    default: epilogue_cols<LPC_ACT_RELU>(trow, e.c0, e.c_end, valid, yrow, rrow, srow); break;
   }
 }
 
@@ -325,7 +390,7 @@ conv_tc_taps_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
   const uint32_t tmem_base = tmem_base_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const uint32_t tx_bytes = (uint32_t)(p.TW * p.TH * 128 + b_stage_bytes);
       const int sub_bytes = 256 * p.kc;
       int it = 0;
@@ -350,11 +415,18 @@ conv_tc_taps_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const uint32_t idesc = make_idesc(p.n_tile);
       const uint32_t a_layout = p.kc == 64 ? 2u : (p.kc == 32 ? 4u : 6u);
-      const uint32_t a_sbo = (uint32_t)(16 * p.kc);
+      const uint32_t a_hi = desc_hi((uint32_t)(16 * p.kc), a_layout), b_hi = desc_hi(1024u, 2u);
       const int sub_bytes = 256 * p.kc;
+      uint32_t a_off[4];                       // 16-byte units from the stage base, per K=16 slice
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int e = k * 16, j = e / p.kc;
+        a_off[k] = (uint32_t)((j * sub_bytes + (e - j * p.kc) * 2) >> 4);
+      }
+      const int last_real = (p.real_slots * p.kc - (p.ksteps - 1) * 64) / 16;   // real K=16 slices of the last step
       int it = 0, tcount = 0;
       for (int m = m_first; m < p.m_tiles; m += m_step, ++tcount) {
         const int buf = tcount & 1;
@@ -366,28 +438,26 @@ conv_tc_taps_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
           const int s = it % p.stages;
           mbar_wait(full_bar(s), (uint32_t)((it / p.stages) & 1));
           tc_fence_after();
-          const uint32_t a_base = smem_base + (uint32_t)(s * stage_bytes);
-          const uint32_t b_base = a_base + A_STAGE_BYTES;
+          const uint32_t a_lo = desc_lo(smem_base + (uint32_t)(s * stage_bytes), 16u);
+          const uint32_t b_lo = desc_lo(smem_base + (uint32_t)(s * stage_bytes) + A_STAGE_BYTES, 16u);
+          const int nk = (ks == p.ksteps - 1) ? last_real : 4;           // zero-padded K slices are skipped
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int e = k * 16;
-            const int j = e / p.kc;
-            const uint32_t a_addr = a_base + (uint32_t)(j * sub_bytes + (e - j * p.kc) * 2);
-            umma_bf16(acc, smem_desc(a_addr, 16u, a_sbo, a_layout), smem_desc(b_base + (uint32_t)(k * 32), 16u, 1024u, 2u), idesc, 1u);
-          }
+          for (int k = 0; k < 4; ++k)
+            if (k < nk) umma_acc(acc, desc64(a_lo + a_off[k], a_hi), desc64(b_lo + 2u * k, b_hi), idesc);
           umma_commit(empty_bar(s));
         }
         umma_commit(tfull_bar(buf));
       }
     }
   } else {
+    const EpiCtx ectx = make_epi_ctx(p, warp, lane);
     int tcount = 0;
     for (int m = m_first; m < p.m_tiles; m += m_step, ++tcount) {
       const TileCoord t = tile_coord(p, m);
       const int buf = tcount & 1;
       mbar_wait(tfull_bar(buf), (uint32_t)((tcount >> 1) & 1));
       tc_fence_after();
-      epilogue_tile(p, tmem_base + (uint32_t)(buf * p.acc_cols), warp, lane, t.img, t.x0, t.y0, n0);
+      epilogue_tile(p, ectx, tmem_base + (uint32_t)(buf * p.acc_cols), t.img, t.x0, t.y0, n0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(buf));
@@ -398,8 +468,15 @@ conv_tc_taps_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+#define TRACE(role, tile, k) do { if ((p.dbg & 8) && blockIdx.x == 0 && (tile) < 64) p.trace[((role) * 64 + (tile)) * 4 + (k)] = clock64(); } while (0)
+
 // ---- kernel 2: 3x3 stride-1 conv from one halo patch per tile ---------------------------------------------
-__global__ void __launch_bounds__(320, 2)
+// Warps: 0 = weight TMA, 1 = MMA issuer, 2..(1+4*epi_split) = epilogue, last two = activation loaders.  The halo
+// patch is gathered with 16-byte cp.async (coalesced in global memory, scattered into the planar layout, zero-filled
+// outside the image): TMA would need one request per 16-byte element here, and its per-request rate (~5 cycles)
+// made it the bottleneck of every small-Cin layer (profiles/r01_c_*).
+template <int CIN, int BRES>   // CIN > 0: patch geometry and the MMA issue sequence are compile-time; BRES: 1 weights resident, 0 streamed, -1 runtime
+__global__ void __launch_bounds__(448, 2)
 conv_tc_halo_kernel(const __grid_constant__ TmapPack maps, const __grid_constant__ ConvTcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long bars[4 * MAX_STAGES + 4];
@@ -408,10 +485,12 @@ conv_tc_halo_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
   const uint32_t ones_addr = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bias_addr = ones_addr + ONES_BYTES;
   const uint32_t smem_base = (bias_addr + (uint32_t)p.n_tile * 32u + 1023u) & ~1023u;
+  const bool b_res = BRES < 0 ? (p.b_resident != 0) : (BRES != 0);
   const int b_block = p.n_tile * 128;
-  const int b_blocks = p.b_resident ? p.ksteps : p.b_stages;
-  const int planes = p.Cin / 8;
-  const int halo_bytes = planes * HALO_PLANE_BYTES;
+  const int b_blocks = b_res ? p.ksteps : p.b_stages;
+  const int halo_bytes = p.slabs * p.slab_bytes;
+  const int chunks_px = p.Cin / 8;              // 16-byte channel groups per pixel
+  const int chunks_row = p.pitch / 16;          // ... per swizzled row (one 64-channel slab)
   const uint32_t a_region = smem_base + (uint32_t)(b_blocks * b_block);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(&bars[0]);
@@ -434,7 +513,7 @@ conv_tc_halo_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
       mbar_init(bempty_bar(s), 1);
     }
     for (int s = 0; s < MAX_STAGES; ++s) {
-      mbar_init(afull_bar(s), 1);
+      mbar_init(afull_bar(s), HALO_LOADERS);
       mbar_init(aempty_bar(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -451,22 +530,14 @@ conv_tc_halo_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
   const uint32_t tmem_base = tmem_base_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      if (p.b_resident) {
+    if (elect_one_sync()) {
+      if (b_res) {
         mbar_expect_tx(bfull_bar(0), (uint32_t)(p.ksteps * b_block));
         for (int ks = 0; ks < p.ksteps; ++ks) tma_load_2d(smem_base + (uint32_t)(ks * b_block), &maps.b, bfull_bar(0), ks * 64, n0);
       }
-      const uint32_t a_tx = (uint32_t)(planes * HALO_PW * HALO_PH * 16);
-      int tcount = 0, bit = 0;
-      for (int m = m_first; m < p.m_tiles; m += m_step, ++tcount) {
-        const TileCoord t = tile_coord(p, m);
-        const int ab = tcount % p.a_bufs;
-        mbar_wait(aempty_bar(ab), (uint32_t)(((tcount / p.a_bufs) & 1) ^ 1));
-        mbar_expect_tx(afull_bar(ab), a_tx);
-        const uint32_t a_dst = a_region + (uint32_t)(ab * halo_bytes);
-        for (int pl = 0; pl < planes; ++pl)
-          tma_load_4d(a_dst + (uint32_t)(pl * HALO_PLANE_BYTES), &maps.a[0], afull_bar(ab), pl * 8, t.x0 - 1, t.y0 - 1, t.img);
-        if (!p.b_resident) {
+      if (!b_res) {
+        int bit = 0;
+        for (int m = m_first; m < p.m_tiles; m += m_step) {
           for (int ks = 0; ks < p.ksteps; ++ks, ++bit) {
             const int s = bit % p.b_stages;
             mbar_wait(bempty_bar(s), (uint32_t)(((bit / p.b_stages) & 1) ^ 1));
@@ -476,63 +547,175 @@ conv_tc_halo_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
         }
       }
     }
+  } else if (warp >= 2 + 4 * p.epi_split) {
+    // ===== activation loaders =====
+    // Thread t owns patch pixels t and t+128 (of 180): per tile it resolves each pixel's address / in-image test once
+    // and then streams that pixel's Cin/8 16-byte channel groups (contiguous in global memory, one plane apart in
+    // shared memory).  .ca keeps the touched sectors in L1 for the neighbouring groups of the same pixel.
+    const int lt = threadIdx.x - (2 + 4 * p.epi_split) * 32;
+    const int look = p.a_bufs >= 6 ? 3 : (p.a_bufs >= 4 ? 2 : 1);   // tiles in flight per CTA before the oldest is awaited
+    int ppy[2], ppx[2];
+    uint32_t row_off[2], phase[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int pix = lt + q * HALO_LOADERS;
+      ppy[q] = pix / HALO_PW;
+      ppx[q] = pix - ppy[q] * HALO_PW;
+      row_off[q] = (uint32_t)((ppy[q] * HALO_SPW + ppx[q]) * p.pitch);        // buffers are 1024-B aligned
+      phase[q] = (row_off[q] >> 7) & (uint32_t)(chunks_row - 1);              // Swizzle<b,4,3> on the address
+    }
+    const bool second = lt + HALO_LOADERS < HALO_PW * HALO_PH;
+    const int img_elems = p.H * p.W * (int)p.x_ld;                             // < 2^31 (checked on the host)
+    int tcount = 0;
+    for (int m = m_first; m < p.m_tiles; m += m_step, ++tcount) {
+      const TileCoord t = tile_coord(p, m);
+      const int ab = tcount % p.a_bufs;
+      if (lt == 0) TRACE(0, tcount, 0);
+      mbar_wait(aempty_bar(ab), (uint32_t)(((tcount / p.a_bufs) & 1) ^ 1));
+      if (lt == 0) TRACE(0, tcount, 1);
+      const uint32_t a_dst = a_region + (uint32_t)(ab * halo_bytes);
+      const bf16* img_base = p.x + (long long)t.img * img_elems;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (q == 0 || second) {
+          const int iy = t.y0 - 1 + ppy[q], ix = t.x0 - 1 + ppx[q];
+          const bool in = (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
+          const bf16* src = in ? img_base + (iy * p.W + ix) * (int)p.x_ld : p.x;
+          const uint32_t nb = in ? 16u : 0u;
+          if (!(p.dbg & 2)) {
+            uint32_t dst_row = a_dst + row_off[q];
+            if (CIN > 0) {
+              constexpr int CROW = (CIN < 64 ? CIN : 64) / 8, NSLAB = (CIN + 63) / 64;
+              constexpr int SLABB = HALO_PH * HALO_SPW * (CIN < 64 ? CIN : 64) * 2;
+#pragma unroll
+              for (int sl = 0; sl < NSLAB; ++sl)
+#pragma unroll
+                for (int cw = 0; cw < CROW; ++cw)
+                  cp_async16(dst_row + (uint32_t)(sl * SLABB) + (((uint32_t)cw ^ phase[q]) << 4), src + (in ? (sl * CROW + cw) * 8 : 0), nb);
+            } else {
+              for (int c0 = 0; c0 < chunks_px; c0 += chunks_row, dst_row += (uint32_t)p.slab_bytes)   // one 64-channel slab per pass
+#pragma unroll 4
+                for (int cw = 0; cw < chunks_row; ++cw)
+                  cp_async16(dst_row + (((uint32_t)cw ^ phase[q]) << 4), src + (in ? (c0 + cw) * 8 : 0), nb);
+            }
+          }
+        }
+      }
+      cp_async_commit();
+      if (lt == 0) TRACE(0, tcount, 2);
+      if (tcount >= look) {                      // the tile issued `look` iterations ago has landed
+        cp_async_wait_dyn(look);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(afull_bar((tcount - look) % p.a_bufs));
+      }
+      if (lt == 0) TRACE(0, tcount, 3);
+    }
+    cp_async_wait_dyn(0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int i = (tcount > look ? tcount - look : 0); i < tcount; ++i) mbar_arrive(afull_bar(i % p.a_bufs));
   } else if (warp == 1) {
-    if (lane == 0) {
+    // Descriptors are derived arithmetically from kernel parameters and loop counters only (no table look-ups), so the
+    // compiler keeps them in the uniform datapath: per MMA a couple of UIADDs + UTCHMMA.  Slice (tap, slab, g) views the
+    // patch shifted by (ty, tx) pixels: start = buffer + slab*slab_bytes + (ty*16 + tx)*pitch + g*32 bytes, SBO = one
+    // patch row (16 pixels).  base_offset stays 0: the swizzle XOR is a function of the absolute shared-memory address
+    // (measured: the PTX-ISA base_offset formula gives wrong results here, base_offset = 0 is bit-exact).
+    if (elect_one_sync()) {
       const uint32_t idesc = make_idesc(p.n_tile);
-      const int kreal = 9 * p.Cin;
-      if (p.b_resident) mbar_wait(bfull_bar(0), 0);
+      const uint32_t a_layout = p.pitch == 128 ? 2u : (p.pitch == 64 ? 4u : 6u);
+      const uint32_t a_hi = desc_hi((uint32_t)(HALO_SPW * p.pitch), a_layout), b_hi = desc_hi(1024u, 2u);
+      const uint32_t pitch16 = (uint32_t)p.pitch >> 4, slab16 = (uint32_t)p.slab_bytes >> 4, bblk16 = (uint32_t)b_block >> 4;
+      const int groups = (p.Cin < 64 ? p.Cin : 64) / 16;     // K=16 slices per slab row
+      const uint32_t b_lo0 = desc_lo(smem_base, 16u);
+      if (b_res) mbar_wait(bfull_bar(0), 0);
       int tcount = 0, bit = 0;
       for (int m = m_first; m < p.m_tiles; m += m_step, ++tcount) {
         const int buf = tcount & 1;
         const int ab = tcount % p.a_bufs;
+        TRACE(1, tcount, 0);
         mbar_wait(tempty_bar(buf), (uint32_t)(((tcount >> 1) & 1) ^ 1));
+        TRACE(1, tcount, 1);
         mbar_wait(afull_bar(ab), (uint32_t)((tcount / p.a_bufs) & 1));
+        TRACE(1, tcount, 2);
         tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)(buf * p.acc_cols);
-        const uint32_t a_buf = a_region + (uint32_t)(ab * halo_bytes);
+        const uint32_t a_lo0 = desc_lo(a_region + (uint32_t)(ab * halo_bytes), 16u);
         issue_bias_mma(acc, ones_addr, bias_addr, p.n_tile, idesc);      // accumulator := bias
-        int tap = 0, c = 0;  // K cursor: k = tap*Cin + c
-        for (int ks = 0; ks < p.ksteps; ++ks) {
-          uint32_t b_base;
-          if (p.b_resident) {
-            b_base = smem_base + (uint32_t)(ks * b_block);
-          } else {
-            const int s = bit % p.b_stages;
-            mbar_wait(bfull_bar(s), (uint32_t)((bit / p.b_stages) & 1));
-            tc_fence_after();
-            b_base = smem_base + (uint32_t)(s * b_block);
-          }
+        int kin = 0, ks = 0;
+        uint32_t b_lo = b_lo0;
+        if (CIN > 0) {
+          constexpr int C_ROW = CIN < 64 ? CIN : 64, PITCH16 = C_ROW * 2 / 16, GROUPS = C_ROW / 16, SLABS = (CIN + 63) / 64;
+          constexpr int SLAB16 = HALO_PH * HALO_SPW * C_ROW * 2 / 16;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const bool real = (ks * 64 + k * 16) < kreal;
-            const int tp = real ? tap : 0, cc = real ? c : 0;  // padded K: zero weights, any finite A
-            const int ty = tp / 3, tx = tp - ty * 3;
-            const uint32_t a_addr = a_buf + (uint32_t)((cc >> 3) * HALO_PLANE_BYTES + (ty * HALO_PW + tx) * 16);
-            umma_bf16(acc, smem_desc(a_addr, (uint32_t)HALO_PLANE_BYTES, (uint32_t)(HALO_PW * 16), 0u),
-                      smem_desc(b_base + (uint32_t)(k * 32), 16u, 1024u, 2u), idesc, 1u);
-            c += 16;
-            if (c >= p.Cin) { c = 0; ++tap; }
+          for (int j = 0; j < 9 * SLABS * GROUPS; ++j) {
+            const int tap = j / (SLABS * GROUPS), sl = (j / GROUPS) % SLABS, g = j % GROUPS;     // all compile-time
+            const int kin_c = j & 3, ks_c = j >> 2;
+            if (kin_c == 0) {
+              if (b_res) {
+                b_lo = b_lo0 + (uint32_t)ks_c * bblk16;
+              } else {
+                const int st = bit % p.b_stages;
+                mbar_wait(bfull_bar(st), (uint32_t)((bit / p.b_stages) & 1));
+                tc_fence_after();
+                b_lo = b_lo0 + (uint32_t)st * bblk16;
+              }
+            }
+            if (!(p.dbg & 1))
+              umma_acc(acc, desc64(a_lo0 + (uint32_t)(((tap / 3) * HALO_SPW + tap % 3) * PITCH16 + sl * SLAB16 + 2 * g), a_hi),
+                       desc64(b_lo + 2u * (uint32_t)kin_c, b_hi), idesc);
+            if (kin_c == 3 && !b_res) { umma_commit(bempty_bar(bit % p.b_stages)); ++bit; }
           }
-          if (!p.b_resident) {
-            umma_commit(bempty_bar(bit % p.b_stages));
-            ++bit;
+          kin = (9 * SLABS * GROUPS) & 3;
+          ks = (9 * SLABS * GROUPS) >> 2;
+        } else {
+        for (int ty = 0; ty < 3; ++ty) {
+          for (int tx = 0; tx < 3; ++tx) {
+            const uint32_t tap_lo = a_lo0 + (uint32_t)(ty * HALO_SPW + tx) * pitch16;
+            for (int sl = 0; sl < p.slabs; ++sl) {
+              for (int g = 0; g < groups; ++g) {
+                if (kin == 0) {
+                  if (b_res) {
+                    b_lo = b_lo0 + (uint32_t)ks * bblk16;
+                  } else {
+                    const int st = bit % p.b_stages;
+                    mbar_wait(bfull_bar(st), (uint32_t)((bit / p.b_stages) & 1));
+                    tc_fence_after();
+                    b_lo = b_lo0 + (uint32_t)st * bblk16;
+                  }
+                }
+                if (!(p.dbg & 1)) umma_acc(acc, desc64(tap_lo + (uint32_t)sl * slab16 + 2u * (uint32_t)g, a_hi), desc64(b_lo + 2u * (uint32_t)kin, b_hi), idesc);
+                if (++kin == 4) {
+                  kin = 0;
+                  ++ks;
+                  if (!b_res) { umma_commit(bempty_bar(bit % p.b_stages)); ++bit; }
+                }
+              }
+            }
           }
         }
+        }
+        (void)ks;
+        if (kin != 0 && !b_res) { umma_commit(bempty_bar(bit % p.b_stages)); ++bit; }   // partial last K step
         umma_commit(aempty_bar(ab));
         umma_commit(tfull_bar(buf));
+        TRACE(1, tcount, 3);
       }
     }
-  } else {
+  } else if (warp < 2 + 4 * p.epi_split) {
+    const EpiCtx ectx = make_epi_ctx(p, warp, lane);
     int tcount = 0;
     for (int m = m_first; m < p.m_tiles; m += m_step, ++tcount) {
       const TileCoord t = tile_coord(p, m);
       const int buf = tcount & 1;
+      if (threadIdx.x == 64) TRACE(2, tcount, 0);
       mbar_wait(tfull_bar(buf), (uint32_t)((tcount >> 1) & 1));
+      if (threadIdx.x == 64) TRACE(2, tcount, 1);
       tc_fence_after();
-      epilogue_tile(p, tmem_base + (uint32_t)(buf * p.acc_cols), warp, lane, t.img, t.x0, t.y0, n0);
+      epilogue_tile(p, ectx, tmem_base + (uint32_t)(buf * p.acc_cols), t.img, t.x0, t.y0, n0);
+      if (threadIdx.x == 64) TRACE(2, tcount, 2);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(buf));
+      if (threadIdx.x == 64) TRACE(2, tcount, 3);
     }
   }
   tc_fence_before();
@@ -677,17 +860,25 @@ extern "C" int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int C
   p.y = (bf16*)y;
   p.y_ld = y_ld;
   p.act = act;
+  { const char* e = getenv("LPC_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
 
   // ---- choose the kernel -------------------------------------------------------------------------------
   bool halo = false;
-  if (k == 3 && stride == 1 && g_force_mode != 1) {
+  if (k == 3 && stride == 1 && g_force_mode != 1 && (Cin == 16 || Cin == 32 || Cin % 64 == 0) && Cin <= 256) {
     const long long tiles = (long long)((Wo + HALO_TW - 1) / HALO_TW) * ((Ho + HALO_TH - 1) / HALO_TH);
     const double eff = (double)Ho * Wo / (double)(tiles * 128);
-    const size_t halo_bytes = (size_t)(Cin / 8) * HALO_PLANE_BYTES;
-    // weights resident if they fit next to two halo buffers, else a 3-block ring with full-width N tiles
+    const int pitch = (Cin >= 64 ? 64 : Cin) * 2;
+    const size_t halo_bytes = (size_t)((Cin + 63) / 64) * HALO_PH * HALO_SPW * pitch;
+    // weights resident if they fit next to two halo buffers (halving the N tile once if that makes them fit: the
+    // activation patch is then loaded twice, still far cheaper than re-streaming the weights for every tile),
+    // else a 3-block ring with full-width N tiles
     int nt = pick_ntile(Cout, 256);
     size_t need = (size_t)p.ksteps * nt * 128 + 2 * halo_bytes;
     int resident = 1;
+    if (need > SMEM_LIMIT && nt % 32 == 0 && (size_t)p.ksteps * (nt / 2) * 128 + 2 * halo_bytes <= SMEM_LIMIT) {
+      nt /= 2;
+      need = (size_t)p.ksteps * nt * 128 + 2 * halo_bytes;
+    }
     if (need > SMEM_LIMIT) {
       resident = 0;
       need = (size_t)3 * nt * 128 + 2 * halo_bytes;
@@ -709,6 +900,7 @@ extern "C" int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int C
   p.acc_cols = 32;
   while (p.acc_cols < p.n_tile) p.acc_cols <<= 1;
   p.tmem_cols = 2 * p.acc_cols;
+  if ((p.dbg & 16) && p.acc_cols <= 32) p.tmem_cols = 256;   // experiment: spread dependent MMAs over 4 accumulators
   p.epi_split = (p.n_tile % 32 == 0) ? 2 : 1;
 
   size_t smem = 0;
@@ -716,10 +908,12 @@ extern "C" int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int C
     p.B = B; p.Ho = Ho; p.Wo = Wo; p.TW = HALO_TW; p.TH = HALO_TH;
     p.tiles_x = (Wo + HALO_TW - 1) / HALO_TW;
     p.tiles_y = (Ho + HALO_TH - 1) / HALO_TH;
-    if (int e = encode_act_map(&maps.a[0], xb, Cin, W, H, B, x_ld, (long long)W * x_ld, (long long)H * W * x_ld, 8, HALO_PW, HALO_PH,
-                               CU_TENSOR_MAP_SWIZZLE_NONE))
-      return e;
-    smem = (size_t)(p.b_resident ? p.ksteps : p.b_stages) * p.n_tile * 128 + (size_t)p.a_bufs * (Cin / 8) * HALO_PLANE_BYTES + 1024 + BIAS_REGION(p.n_tile);
+    p.x = xb; p.x_ld = x_ld; p.H = H; p.W = W;
+    p.pitch = (Cin >= 64 ? 64 : Cin) * 2;
+    p.slabs = (Cin + 63) / 64;
+    p.slab_bytes = HALO_PH * HALO_SPW * p.pitch;
+    { const char* e = getenv("LPC_TC_BO"); p.use_base_offset = e ? atoi(e) : 1; }
+    smem = (size_t)(p.b_resident ? p.ksteps : p.b_stages) * p.n_tile * 128 + (size_t)p.a_bufs * p.slabs * p.slab_bytes + 1024 + BIAS_REGION(p.n_tile);
   } else {
     p.kc = pick_kc(Cin);
     p.nsub = 64 / p.kc;
@@ -782,7 +976,11 @@ extern "C" int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int C
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e1 = cudaFuncSetAttribute(conv_tc_taps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT + 16 * 1024);
-    cudaError_t e2 = cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT + 16 * 1024);
+    cudaError_t e2 = cudaSuccess;
+    const int lim = (int)SMEM_LIMIT + 16 * 1024;
+#define HALO_ATTR(C_, R_) if (cudaFuncSetAttribute(conv_tc_halo_kernel<C_, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess) e2 = cudaErrorUnknown;
+    HALO_ATTR(0, -1) HALO_ATTR(16, 1) HALO_ATTR(32, 1) HALO_ATTR(64, 1) HALO_ATTR(128, 1) HALO_ATTR(128, 0)
+#undef HALO_ATTR
     if (e1 != cudaSuccess || e2 != cudaSuccess) LPC_FAIL(LPC_E_CUDA, "conv2d_tc: smem attribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
     attr_set = true;
   }
@@ -792,10 +990,43 @@ extern "C" int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int C
   if (per_n > p.m_tiles) per_n = p.m_tiles;
   const unsigned grid = (unsigned)(per_n * p.n_tiles);
   const unsigned threads = 64 + 128 * p.epi_split;
-  if (halo)
-    conv_tc_halo_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(maps, p);
+  static unsigned long long* trace_buf = nullptr;
+  if (p.dbg & 8) {
+    if (!trace_buf) cudaMalloc(&trace_buf, 4 * 64 * 4 * 8);
+    cudaMemset(trace_buf, 0, 4 * 64 * 4 * 8);
+    p.trace = trace_buf;
+  }
+  if (halo) {
+    LPC_REQUIRE((long long)H * W * x_ld < (1ll << 31), "conv2d_tc: image too large for 32-bit offsets");
+    const unsigned th = threads + HALO_LOADERS;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (Cin) {
+      case 16: if (p.b_resident) { conv_tc_halo_kernel<16, 1><<<grid, th, smem, st>>>(maps, p); break; }
+      case 32: if (p.b_resident && Cin == 32) { conv_tc_halo_kernel<32, 1><<<grid, th, smem, st>>>(maps, p); break; }
+      case 64: if (p.b_resident && Cin == 64) { conv_tc_halo_kernel<64, 1><<<grid, th, smem, st>>>(maps, p); break; }
+      case 128: if (Cin == 128) { if (p.b_resident) conv_tc_halo_kernel<128, 1><<<grid, th, smem, st>>>(maps, p); else conv_tc_halo_kernel<128, 0><<<grid, th, smem, st>>>(maps, p); break; }
+      default: conv_tc_halo_kernel<0, -1><<<grid, th, smem, st>>>(maps, p); break;
+    }
+  }
   else
     conv_tc_taps_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(maps, p);
   LPC_CHECK_LAUNCH("conv2d_tc");
+  if ((p.dbg & 8) && halo) {
+    static int dumps = 0;
+    cudaDeviceSynchronize();
+    if (dumps++ == 5) {
+      unsigned long long h[4 * 64 * 4];
+      cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
+      const unsigned long long t0 = h[0];
+      for (int t = 0; t < 40; ++t) {
+        printf("tile %2d MMAx: fence %6lld bias %6lld loop %6lld c1 %6lld\n", t, (long long)(h[(3 * 64 + t) * 4 + 0] - t0), (long long)(h[(3 * 64 + t) * 4 + 1] - t0), (long long)(h[(3 * 64 + t) * 4 + 2] - t0), (long long)(h[(3 * 64 + t) * 4 + 3] - t0));
+        printf("tile %2d  LD: w0 %6lld w1 %6lld iss %6lld sig %6lld | MMA: s %6lld te %6lld af %6lld done %6lld | EPI: s %6lld tf %6lld ep %6lld ar %6lld\n", t,
+               (long long)(h[(0 * 64 + t) * 4 + 0] - t0), (long long)(h[(0 * 64 + t) * 4 + 1] - t0), (long long)(h[(0 * 64 + t) * 4 + 2] - t0), (long long)(h[(0 * 64 + t) * 4 + 3] - t0),
+               (long long)(h[(1 * 64 + t) * 4 + 0] - t0), (long long)(h[(1 * 64 + t) * 4 + 1] - t0), (long long)(h[(1 * 64 + t) * 4 + 2] - t0), (long long)(h[(1 * 64 + t) * 4 + 3] - t0),
+               (long long)(h[(2 * 64 + t) * 4 + 0] - t0), (long long)(h[(2 * 64 + t) * 4 + 1] - t0), (long long)(h[(2 * 64 + t) * 4 + 2] - t0), (long long)(h[(2 * 64 + t) * 4 + 3] - t0));
+      }
+      fflush(stdout);
+    }
+  }
   return LPC_OK;
 }

@@ -147,6 +147,63 @@ class YOLOv10DetectionPredictor:
         """predictor.py:135-142: backbone + neck + one2one head + fused decode/top-k -> [B,K,6]."""
         return self.model.detect(im, self.args.max_det, clip=True)
 
+    # ---- host-source fast path: chunked H2D copies overlapped with CUDA-graph replays ---------------------------
+    class _Graphed:
+        """Two CUDA graphs of ``model.detect`` on two static input buffers (double buffering)."""
+
+        def __init__(self, model, shape, max_det):
+            dev = next(model.parameters()).device
+            self.inp = [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(2)]
+            for t in self.inp:
+                t.fill_(0.5)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    model.detect(self.inp[0], max_det, clip=True)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            self.graphs, self.outs = [], []
+            for i in range(2):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    out = model.detect(self.inp[i], max_det, clip=True)
+                self.graphs.append(g)
+                self.outs.append(out)
+
+    def inference_from_host(self, im_host):
+        """[B,3,H,W] fp32 host tensor -> [B,K,6] on the device.  The batch is cut into up to four chunks; chunk i+1's
+        host-to-device copy (copy stream) overlaps chunk i's graph replay (compute stream)."""
+        B = im_host.shape[0]
+        n = 4 if B % 4 == 0 and B >= 16 else (2 if B % 2 == 0 and B >= 4 else 1)
+        cb = B // n
+        key = (cb, tuple(im_host.shape[1:]), self.args.max_det, self.model.compute_dtype)
+        cache = self.__dict__.setdefault("_graphed", {})
+        if key not in cache:
+            cache[key] = self._Graphed(self.model, (cb, *im_host.shape[1:]), self.args.max_det)
+        gd = cache[key]
+        if not im_host.is_pinned():
+            im_host = im_host.pin_memory()
+        cur = torch.cuda.current_stream(self.device)
+        cs = self.__dict__.setdefault("_copy_stream", torch.cuda.Stream(device=self.device))
+        cs.wait_stream(cur)
+        preds = torch.empty((B, self.args.max_det, 6), dtype=torch.float32, device=self.device)
+        done = []
+        for i in range(n):
+            b = i & 1
+            ev = torch.cuda.Event()
+            with torch.cuda.stream(cs):
+                if i >= 2:
+                    cs.wait_event(done[i - 2])           # the replay that read this buffer has finished
+                gd.inp[b].copy_(im_host[i * cb:(i + 1) * cb], non_blocking=True)
+                ev.record(cs)
+            cur.wait_event(ev)
+            gd.graphs[b].replay()
+            preds[i * cb:(i + 1) * cb].copy_(gd.outs[b])
+            d = torch.cuda.Event()
+            d.record(cur)
+            done.append(d)
+        return preds
+
     def postprocess(self, preds, img, orig_imgs):
         """models/yolov10/predict.py:22-38: confidence / class filter, wrap in Results.  preds are already
         [B,K,6] xyxy (the export-mode contract, head.py:521-523), clipped to the image (scale_boxes is the
@@ -171,10 +228,16 @@ class YOLOv10DetectionPredictor:
         self.batch = source
         self.run_callbacks("on_predict_batch_start")
         with torch.no_grad():
-            with profilers[0]:
-                im = self.preprocess(source)
-            with profilers[1]:
-                preds = self.inference(im)
+            if torch.is_tensor(source) and not source.is_cuda and source.dtype == torch.float32 and source.dim() == 4:
+                with profilers[0]:
+                    im = check_tensor_source(source)
+                with profilers[1]:
+                    preds = self.inference_from_host(im)
+            else:
+                with profilers[0]:
+                    im = self.preprocess(source)
+                with profilers[1]:
+                    preds = self.inference(im)
             with profilers[2]:
                 self.results = self.postprocess(preds, im, im)
         self.run_callbacks("on_predict_postprocess_end")
