@@ -57,7 +57,7 @@ struct ConvTcParams {
   const bf16* x;                     // halo kernel: activation base, pixel pitch, input geometry
   long long x_ld;
   int H, W;
-  int pitch, slabs, slab_bytes, use_base_offset;   // halo patch: bytes per pixel row (32/64/128), 64-channel slabs
+  int pitch, slabs, slab_bytes;      // halo patch: bytes per pixel row (32/64/128), 64-channel slabs
   int epi_split;                     // epilogue warps = 4 * epi_split
   int dbg;                           // LPC_TC_DBG bits (profiling only): 1 skip MMAs, 2 skip A loads, 4 skip stores, 8 trace
   unsigned long long* trace;         // [4 roles][64 tiles][4 stamps] of clock64, CTA 0 only
@@ -912,7 +912,6 @@ extern "C" int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int C
     p.pitch = (Cin >= 64 ? 64 : Cin) * 2;
     p.slabs = (Cin + 63) / 64;
     p.slab_bytes = HALO_PH * HALO_SPW * p.pitch;
-    { const char* e = getenv("LPC_TC_BO"); p.use_base_offset = e ? atoi(e) : 1; }
     smem = (size_t)(p.b_resident ? p.ksteps : p.b_stages) * p.n_tile * 128 + (size_t)p.a_bufs * p.slabs * p.slab_bytes + 1024 + BIAS_REGION(p.n_tile);
   } else {
     p.kc = pick_kc(Cin);
