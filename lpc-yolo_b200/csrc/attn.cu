@@ -124,6 +124,205 @@ psa_attention_kernel(const T* __restrict__ qkv, int ld, int N, int heads, int kd
   }
 }
 
+// ---- bf16 tensor-core variant ------------------------------------------------------------------------------
+// Flash-attention style: CTA = 64 queries of one (image, head), 4 warps x 16 query rows; keys/values stream through a
+// double-buffered cp.async ring in 64-key tiles; S = Q K^T and O += P V are mma.sync m16n8k16 (bf16 in, fp32
+// accumulate); the softmax runs on the accumulator fragments (quad shuffles), P is re-packed to bf16 in registers as
+// the A operand of the second MMA (never touches shared memory).  This block is <= 0.4 % of the network's FLOPs, but
+// at fp32-FMA speed it was 7-9 % of the step (profiles/r01_f_*): the point of the tensor path is latency, not peak.
+__host__ __device__ constexpr int pitch_of(int dim) { return ((dim / 8) & 1) ? dim : dim + 8; }   // odd number of 16-byte units per row -> conflict-free ldmatrix
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+template <int BYTES> __device__ __forceinline__ void cp_async_zfill(uint32_t dst, const void* src, bool valid) {
+  const uint32_t n = valid ? BYTES : 0;
+  if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+
+constexpr int MQ = 64, MK = 64, MMA_NT = 128;
+
+template <int KD, int HD>
+__global__ void __launch_bounds__(MMA_NT)
+psa_attention_mma_kernel(const bf16* __restrict__ qkv, int ld, int N, int heads, bf16* __restrict__ out, int out_ld) {
+  constexpr int KDP = (KD + 15) / 16 * 16, KP = pitch_of(KDP), VP = pitch_of(HD);
+  constexpr int CH = (KD % 8 == 0) ? 16 : 8;            // global->shared copy granularity in bytes
+  constexpr int KCH = KD * 2 / CH, VCH = HD * 2 / 16;   // chunks per row
+  constexpr int KSTEPS = KDP / 16, NT_S = MK / 8, NT_O = HD / 8;
+  __shared__ __align__(16) bf16 Qs[MQ * KP];
+  __shared__ __align__(16) bf16 Ks[2][MK * KP];
+  __shared__ __align__(16) bf16 Vs[2][MK * VP];
+
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * MQ;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q_off = h * KD, k_off = heads * KD + h * KD, v_off = 2 * heads * KD + h * HD;
+  const bf16* base = qkv + (long long)b * N * ld;
+
+  // zero the K-padding columns (KD..KDP) of Q and both K stages once; the copies below never touch them
+  if (KDP > KD) {
+    for (int e = tid; e < MQ * (KDP - KD); e += MMA_NT) {
+      const int r = e / (KDP - KD), c = KD + e % (KDP - KD);
+      Qs[r * KP + c] = __float2bfloat16(0.f);
+      Ks[0][r * KP + c] = __float2bfloat16(0.f);
+      Ks[1][r * KP + c] = __float2bfloat16(0.f);
+    }
+  }
+  auto load_kv = [&](int stage, int j0) {
+    for (int e = tid; e < MK * KCH; e += MMA_NT) {
+      const int r = e / KCH, c = e - r * KCH;
+      const bool ok = j0 + r < N;
+      cp_async_zfill<CH>((uint32_t)__cvta_generic_to_shared(&Ks[stage][r * KP]) + c * CH,
+                         reinterpret_cast<const char*>(base + (long long)(ok ? j0 + r : 0) * ld + k_off) + c * CH, ok);
+    }
+    for (int e = tid; e < MK * VCH; e += MMA_NT) {
+      const int r = e / VCH, c = e - r * VCH;
+      const bool ok = j0 + r < N;
+      cp_async_zfill<16>((uint32_t)__cvta_generic_to_shared(&Vs[stage][r * VP]) + c * 16,
+                         reinterpret_cast<const char*>(base + (long long)(ok ? j0 + r : 0) * ld + v_off) + c * 16, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  for (int e = tid; e < MQ * KCH; e += MMA_NT) {
+    const int r = e / KCH, c = e - r * KCH;
+    const bool ok = q0 + r < N;
+    cp_async_zfill<CH>((uint32_t)__cvta_generic_to_shared(&Qs[r * KP]) + c * CH,
+                       reinterpret_cast<const char*>(base + (long long)(ok ? q0 + r : 0) * ld + q_off) + c * CH, ok);
+  }
+  load_kv(0, 0);
+
+  const float sl2 = rsqrtf((float)KD) * 1.4426950408889634f;   // softmax scale folded into the exp2 argument
+  float o[NT_O][4];
+#pragma unroll
+  for (int i = 0; i < NT_O; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  uint32_t qf[KSTEPS][4];
+
+  const int ntiles = (N + MK - 1) / MK;
+  for (int t = 0; t < ntiles; ++t) {
+    const int st = t & 1;
+    if (t + 1 < ntiles) {
+      load_kv(st ^ 1, (t + 1) * MK);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    if (t == 0) {
+#pragma unroll
+      for (int ks = 0; ks < KSTEPS; ++ks) {
+        const int row = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, col = ks * 16 + (lane >> 4) * 8;
+        ldsm_x4((uint32_t)__cvta_generic_to_shared(&Qs[row * KP + col]), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+      }
+    }
+    // ---- S = Q K^T : 16 x 64 per warp ----
+    float s[NT_S][4];
+#pragma unroll
+    for (int nt = 0; nt < NT_S; ++nt) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      const uint32_t krow = (uint32_t)__cvta_generic_to_shared(&Ks[st][(nt * 8 + (lane & 7)) * KP]);
+#pragma unroll
+      for (int ks = 0; ks + 1 < KSTEPS; ks += 2) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(krow + (uint32_t)(ks * 16 + (lane >> 3) * 8) * 2u, b0, b1, b2, b3);
+        mma_bf16(s[nt], qf[ks], b0, b1);
+        mma_bf16(s[nt], qf[ks + 1], b2, b3);
+      }
+      if (KSTEPS & 1) {
+        uint32_t b0, b1;
+        ldsm_x2(krow + (uint32_t)((KSTEPS - 1) * 16 + ((lane >> 3) & 1) * 8) * 2u, b0, b1);
+        mma_bf16(s[nt], qf[KSTEPS - 1], b0, b1);
+      }
+    }
+    // ---- online softmax on the fragments (rows g = lane/4 and g + 8; a quad shares a row) ----
+    const int jbase = t * MK + 2 * (lane & 3);
+    if (t == ntiles - 1) {
+#pragma unroll
+      for (int nt = 0; nt < NT_S; ++nt) {
+        if (jbase + nt * 8 >= N) s[nt][0] = s[nt][2] = -INFINITY;
+        if (jbase + nt * 8 + 1 >= N) s[nt][1] = s[nt][3] = -INFINITY;
+      }
+    }
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < NT_S; ++nt) {
+      mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+    }
+    float corr[2], msc[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      const float m_new = fmaxf(m_run[r], mx[r]);                  // finite: every tile holds at least one valid key
+      corr[r] = ex2_approx((m_run[r] - m_new) * sl2);              // first tile: exp2(-inf) = 0
+      m_run[r] = m_new;
+      msc[r] = m_new * sl2;
+    }
+    float rs[2] = {0.f, 0.f};
+    uint32_t pf[NT_S / 2][4];
+#pragma unroll
+    for (int nt = 0; nt < NT_S; ++nt) {
+      const float p0 = ex2_approx(fmaf(s[nt][0], sl2, -msc[0])), p1 = ex2_approx(fmaf(s[nt][1], sl2, -msc[0]));
+      const float p2 = ex2_approx(fmaf(s[nt][2], sl2, -msc[1])), p3 = ex2_approx(fmaf(s[nt][3], sl2, -msc[1]));
+      rs[0] += p0 + p1;
+      rs[1] += p2 + p3;
+      pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+      pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) l_run[r] = l_run[r] * corr[r] + rs[r];   // per-thread partial sums; reduced over the quad at the end
+#pragma unroll
+    for (int i = 0; i < NT_O; ++i) {
+      o[i][0] *= corr[0]; o[i][1] *= corr[0];
+      o[i][2] *= corr[1]; o[i][3] *= corr[1];
+    }
+    // ---- O += P V ----
+#pragma unroll
+    for (int dt = 0; dt < NT_O; ++dt) {
+#pragma unroll
+      for (int kk = 0; kk < MK / 32; ++kk) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_t((uint32_t)__cvta_generic_to_shared(&Vs[st][(kk * 32 + lane) * VP + dt * 8]), b0, b1, b2, b3);
+        mma_bf16(o[dt], pf[2 * kk], b0, b1);
+        mma_bf16(o[dt], pf[2 * kk + 1], b2, b3);
+      }
+    }
+    __syncthreads();   // this stage is refilled by the next iteration's prefetch
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+  }
+  const int g = lane >> 2;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int q = q0 + warp * 16 + g + r * 8;
+    if (q >= N) continue;
+    const float inv = 1.0f / l_run[r];
+    bf16* orow = out + ((long long)b * N + q) * out_ld + h * HD + 2 * (lane & 3);
+#pragma unroll
+    for (int dt = 0; dt < NT_O; ++dt)
+      *reinterpret_cast<uint32_t*>(orow + dt * 8) = pack_bf16x2(o[dt][r * 2] * inv, o[dt][r * 2 + 1] * inv);
+  }
+}
+
 constexpr size_t ATT_SMEM = sizeof(float) * (MAX_KD * (BQ + 4) + MAX_KD * (BKEY + 4) + BKEY * MAX_HD + BQ * (BKEY + 1));
 
 }  // namespace
@@ -139,6 +338,12 @@ extern "C" int lpc_psa_attention(int dtype, const void* qkv, int qkv_ld, int B, 
   if (dtype == LPC_F32) {
     if (!attr_done[0]) { cudaFuncSetAttribute(psa_attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM); attr_done[0] = true; }
     psa_attention_kernel<float><<<grid, ATT_NT, ATT_SMEM, s>>>((const float*)qkv, qkv_ld, N, heads, kd, hd, (float*)out, out_ld);
+  } else if (dtype == LPC_BF16 && ((kd == 32 && hd == 64) || (kd == 36 && hd == 72)) && qkv_ld % 8 == 0 && out_ld % 2 == 0 &&
+             aligned16(qkv) && (reinterpret_cast<uintptr_t>(out) & 3) == 0) {
+    // tensor-core path (the two head geometries of the YOLOv10 / LPC family)
+    dim3 g2(cdiv(N, MQ), heads, B);
+    if (kd == 32) psa_attention_mma_kernel<32, 64><<<g2, MMA_NT, 0, s>>>((const bf16*)qkv, qkv_ld, N, heads, (bf16*)out, out_ld);
+    else psa_attention_mma_kernel<36, 72><<<g2, MMA_NT, 0, s>>>((const bf16*)qkv, qkv_ld, N, heads, (bf16*)out, out_ld);
   } else if (dtype == LPC_BF16) {
     if (!attr_done[1]) { cudaFuncSetAttribute(psa_attention_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM); attr_done[1] = true; }
     psa_attention_kernel<bf16><<<grid, ATT_NT, ATT_SMEM, s>>>((const bf16*)qkv, qkv_ld, N, heads, kd, hd, (bf16*)out, out_ld);

@@ -29,6 +29,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace {
 
@@ -71,156 +72,6 @@ struct ConvTcParams {
   int act;
 };
 
-// ---- PTX wrappers ------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// One elected lane of a fully converged warp.  Unlike `lane == 0`, the compiler knows that exactly one thread runs the
-// guarded region, so operands of UTCHMMA / UTMALDG / UTCBAR move to uniform registers with plain R2UR instead of an
-// ELECT + BRA.U.ANY "waterfall" loop per instruction (measured: 270 -> ~30 cycles per issued MMA).
-__device__ __forceinline__ bool elect_one_sync() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait (try_wait itself suspends the thread for a hardware time slice, so 2^22 failed polls are seconds):
-// a protocol bug traps instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) {
-      printf("lpc conv_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_dyn(int n) {   // wait until at most n groups are pending
-  switch (n) {
-    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
-    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-    case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-    case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
-    case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
-    case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
-    default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
-  }
-}
-
-// K-major shared-memory matrix descriptor (sm_100 format: version 1 at bit 46).
-//   layout: 0 = no swizzle (core matrices of 8 rows x 16 B; lbo = bytes between the two K core matrices of a K=16
-//   slice, sbo = bytes between 8-row groups), 2 = 128B swizzle, 4 = 64B, 6 = 32B (lbo unused, sbo = 8 * row bytes).
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)layout << 61;
-  return d;
-}
-// The same descriptor as two 32-bit halves, so the issue loop only adds a 16-byte-unit offset to the low word.
-__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout) {
-  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
-}
-__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
-  return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
-}
-__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | (uint64_t)lo; }
-__device__ __forceinline__ void umma_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.eq.u32 p, 1, 1;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc)
-      : "memory");
-}
-__device__ __forceinline__ uint32_t make_idesc(int n_tile) {
-  // c = f32 (bit 4), a = b = bf16 (bits 7, 10), both K-major, N >> 3 at bit 17, M = 128 (>> 4) at bit 24
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_tile >> 3) << 17) | ((128u >> 4) << 24);
-}
-
-// exact n / d for 0 <= n < 2^24 via one float multiply and a fix-up (integer division costs ~25 instructions)
-__device__ __forceinline__ int fast_div(int n, int d, float inv) {
-  int q = __float2int_rz(__int2float_rz(n) * inv);
-  const int r = n - q * d;
-  q += (r >= d) ? 1 : 0;
-  q -= (r < 0) ? 1 : 0;
-  return q;
-}
-
 // ---- bias through the tensor core ---------------------------------------------------------------------------
 // The accumulator is INITIALISED by one extra K=16 MMA: A = "ones" tile (every row = [1, 1, 0...]), B = per output
 // channel [bias_hi, bias_lo, 0...] (bf16 hi/lo split: 16 mantissa bits).  Both tiles are un-swizzled K-major core
@@ -256,7 +107,7 @@ __device__ __forceinline__ void issue_bias_mma(uint32_t acc, uint32_t ones_addr,
 
 // ---- epilogue: one accumulator tile (128 rows x n_tile columns) -> NHWC bf16 --------------------------------
 template <int ACT>
-__device__ __forceinline__ void store16(const uint32_t* v, bf16* yrow, const bf16* rrow, const float* srow) {
+__device__ __forceinline__ void store16(const uint32_t* v, bf16* yrow, const bf16* rrow, const float* srow, bool no_store = false) {
   float f[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
@@ -276,20 +127,24 @@ __device__ __forceinline__ void store16(const uint32_t* v, bf16* yrow, const bf1
 #pragma unroll
     for (int i = 0; i < 8; ++i) f[8 + i] += r8[i];
   }
-  Vec<bf16> o;
+  Vec<bf16> o, o2;
   o.pack(f);
+  o2.pack(f + 8);
+  if (no_store) {   // LPC_TC_DBG & 32 (profiling): keep the math alive, drop the global stores
+    if ((o.raw.x ^ o2.raw.y) == 0x7fc17fc1u) st_vec<bf16>(yrow, o);
+    return;
+  }
   st_vec<bf16>(yrow, o);
-  o.pack(f + 8);
-  st_vec<bf16>(yrow + 8, o);
+  st_vec<bf16>(yrow + 8, o2);
 }
 
 template <int ACT>
-__device__ __forceinline__ void epilogue_cols(uint32_t trow, int c, int c_end, bool valid, bf16* yrow, const bf16* rrow, const float* srow) {
+__device__ __forceinline__ void epilogue_cols(uint32_t trow, int c, int c_end, bool valid, bf16* yrow, const bf16* rrow, const float* srow, bool no_store) {
   for (; c < c_end; c += 16) {
     uint32_t v0[16];
     tmem_ld16(trow + (uint32_t)c, v0);
     tmem_ld_wait();
-    if (valid) store16<ACT>(v0, yrow + c, rrow ? rrow + c : nullptr, srow ? srow + c : nullptr);
+    if (valid) store16<ACT>(v0, yrow + c, rrow ? rrow + c : nullptr, srow ? srow + c : nullptr, no_store);
   }
 }
 
@@ -323,12 +178,13 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, const EpiCt
   const float* srow = nullptr;
   if (p.chan_scale) srow = p.chan_scale + (pix / p.pix_per_img) * p.Cout + n0;
   const uint32_t trow = tmem_acc + e.lane_off;
+  const bool ns = (p.dbg & 32) != 0;
   switch (p.act) {
-    case LPC_ACT_MISH: epilogue_cols<LPC_ACT_MISH>(trow, e.c0, e.c_end, valid, yrow, rrow, srow); break;
-    case LPC_ACT_SILU: epilogue_cols<LPC_ACT_SILU>(trow, e.c0, e.c_end, valid, yrow, rrow, srow); break;
-    case LPC_ACT_NONE: epilogue_cols<LPC_ACT_NONE>(trow, e.c0, e.c_end, valid, yrow, rrow, srow); break;
-    case LPC_ACT_SIGMOID: epilogue_cols<LPC_ACT_SIGMOID>(trow, e.c0, e.c_end, valid, yrow, rrow, srow); break;
-    default: epilogue_cols<LPC_ACT_RELU>(trow, e.c0, e.c_end, valid, yrow, rrow, srow); break;
+    case LPC_ACT_MISH: epilogue_cols<LPC_ACT_MISH>(trow, e.c0, e.c_end, valid, yrow, rrow, srow, ns); break;
+    case LPC_ACT_SILU: epilogue_cols<LPC_ACT_SILU>(trow, e.c0, e.c_end, valid, yrow, rrow, srow, ns); break;
+    case LPC_ACT_NONE: epilogue_cols<LPC_ACT_NONE>(trow, e.c0, e.c_end, valid, yrow, rrow, srow, ns); break;
+    case LPC_ACT_SIGMOID: epilogue_cols<LPC_ACT_SIGMOID>(trow, e.c0, e.c_end, valid, yrow, rrow, srow, ns); break;
+    default: epilogue_cols<LPC_ACT_RELU>(trow, e.c0, e.c_end, valid, yrow, rrow, srow, ns); break;
   }
 }
 
