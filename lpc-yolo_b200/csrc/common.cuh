@@ -124,9 +124,11 @@ template <bool PRECISE> __device__ __forceinline__ float mish_(float x) {
     const float n = e * (e + 2.0f);
     return x * (n / (n + 2.0f));
   }
-  const float e = ex2_approx(fminf(x, 20.0f) * 1.4426950408889634f);   // clamp: e^20 squared still fits fp32
-  const float n = fmaf(e, e, e + e);
-  return fmaf(-2.0f * x, rcp_approx(n + 2.0f), x);
+  // 7 instructions, 2 of them MUFU (the epilogue of the small-channel convs is MUFU / issue bound, profiles/r01_g_*).
+  // No clamp needed: e = +inf gives d = +inf, rcp = 0 and the result is x; x -> -inf gives e = 0, d = 2, result -0.
+  const float e = ex2_approx(x * 1.4426950408889634f);
+  const float d = fmaf(e, e + 2.0f, 2.0f);            // n + 2
+  return x * fmaf(-2.0f, rcp_approx(d), 1.0f);        // x (1 - 2/(n+2)) = x n/(n+2)
 }
 template <bool PRECISE> __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {

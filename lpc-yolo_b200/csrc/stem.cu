@@ -116,6 +116,9 @@ stem_conv_kernel(const T* __restrict__ x, int B, int H, int W, const float* __re
 
 }  // namespace
 
+int lpc_stem_conv_tc(const void* x, int B, int H, int W, const float* w, const float* bias, int Cout, void* y, int y_ld,
+                     int act, cudaStream_t stream);   // stem_tc.cu
+
 extern "C" int lpc_stem_conv(int dtype, const void* x, int B, int H, int W, const float* w, const float* bias, int stride,
                              int Cout, void* y, int y_ld, int act, void* stream) {
   LPC_REQUIRE(x && w && y, "stem_conv: null pointer");
@@ -126,6 +129,10 @@ extern "C" int lpc_stem_conv(int dtype, const void* x, int B, int H, int W, cons
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
   dim3 grid(cdiv(Wo, ST_TW), cdiv(Ho, ST_TH), B);
   cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == LPC_BF16 && stride == 2) {   // tensor-core path; falls through for shapes it does not take
+    const int r = lpc_stem_conv_tc(x, B, H, W, w, bias, Cout, y, y_ld, act, s);
+    if (r != LPC_E_UNSUPPORTED) return r;
+  }
 #define STEM(T_, S_) stem_conv_kernel<T_, S_><<<grid, ST_NT, 0, s>>>((const T_*)x, B, H, W, w, bias, Cout, Ho, Wo, (T_*)y, y_ld, act)
   if (dtype == LPC_BF16) { if (stride == 2) STEM(bf16, 2); else STEM(bf16, 1); }
   else if (dtype == LPC_F32) { if (stride == 2) STEM(float, 2); else STEM(float, 1); }

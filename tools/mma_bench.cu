@@ -95,6 +95,55 @@ __global__ void __launch_bounds__(192, 2) mma_bench_kernel(Cfg c, unsigned long 
   (void)lane;
 }
 
+// ---- cost of the per-tile bookkeeping ops of the issuing thread ---------------------------------------------
+__global__ void __launch_bounds__(64, 1) op_cost_kernel(unsigned long long* out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) unsigned long long bars[4];
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t base = (smem_u32(smem) + 1023u) & ~1023u;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);            // completes on every commit
+    mbar_init(smem_u32(&bars[1]), 1u << 20);     // never completes: absorbs arrivals
+    mbar_init(smem_u32(&bars[2]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (warp == 1 && elect_one_sync()) {
+    const uint32_t idesc = make_idesc(16);
+    const uint64_t ad = desc64(desc_lo(base, 16u), desc_hi(1024u, 2u)), bd = desc64(desc_lo(base + 32768, 16u), desc_hi(1024u, 2u));
+    const uint32_t b0 = smem_u32(&bars[0]), b1 = smem_u32(&bars[1]), b2 = smem_u32(&bars[2]);
+    const int R = 200;
+    long long t[8];
+    // complete phase 0 of bars[2] so that waiting on parity 0 is an "already complete" wait
+    mbar_arrive(b2);
+    t[0] = clock64();
+    for (int i = 0; i < R; ++i) mbar_wait(b2, 0);                       // ready wait
+    t[1] = clock64();
+    for (int i = 0; i < R; ++i) tc_fence_after();
+    t[2] = clock64();
+    for (int i = 0; i < R; ++i) umma_commit(b1);                         // commit with nothing pending
+    t[3] = clock64();
+    for (int i = 0; i < R; ++i) { umma_bf16(tmem, ad, bd, idesc, 0u); umma_commit(b1); }   // 1 MMA + commit
+    t[4] = clock64();
+    for (int i = 0; i < R; ++i) { umma_bf16(tmem, ad, bd, idesc, 0u); umma_commit(b1); umma_commit(b1); }
+    t[5] = clock64();
+    uint32_t ph = 0;
+    for (int i = 0; i < R; ++i) { umma_bf16(tmem, ad, bd, idesc, 0u); umma_commit(b0); mbar_wait(b0, ph); ph ^= 1; }   // full round trip
+    t[6] = clock64();
+    for (int i = 0; i < R; ++i) { mbar_wait(b2, 0); mbar_wait(b2, 0); tc_fence_after(); umma_bf16(tmem, ad, bd, idesc, 0u); umma_acc(tmem, ad, bd, idesc); umma_acc(tmem, ad, bd, idesc); umma_commit(b1); umma_commit(b1); }
+    t[7] = clock64();
+    if (blockIdx.x == 0) for (int i = 0; i < 7; ++i) out[i] = (unsigned long long)(t[i + 1] - t[i]) / R;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 64);
+}
+
 int main() {
   unsigned long long* d;
   cudaMalloc(&d, 64);
@@ -149,5 +198,16 @@ int main() {
   // a single CTA on the chip (no neighbours)
   run({64, 1, 2, 0, 1024, 36, 50, 128, 0, 1, 0}, 1);
   run({256, 1, 2, 0, 1024, 36, 50, 128, 0, 1, 0}, 1);
+  {
+    cudaFuncSetAttribute(op_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaMemset(d, 0, 64);
+    op_cost_kernel<<<sms, 64, 100 * 1024>>>(d);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
+    unsigned long long h[8];
+    cudaMemcpy(h, d, 64, cudaMemcpyDeviceToHost);
+    printf("cycles per op (issuing thread): ready mbar_wait %llu | fence::after %llu | commit (idle) %llu | mma+commit %llu | mma+2 commits %llu | mma+commit+wait round trip %llu | stem-like tile loop (2 waits, fence, 3 mma, 2 commits) %llu\n",
+           h[0], h[1], h[2], h[3], h[4], h[5], h[6]);
+  }
   return 0;
 }
