@@ -21,8 +21,10 @@ with torch.no_grad():
         m.detect(x, 300)
     torch.cuda.synchronize()
     Fn.PROFILE = []
+    torch.cuda.cudart().cudaProfilerStart()      # ncu --profile-from-start off captures exactly this step
     m.detect(x, 300)
     torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
 prof, Fn.PROFILE = Fn.PROFILE, None
 rows = [(k, a.elapsed_time(b) * 1e3, fl, by, tag) for (k, a, b, fl, by, tag) in prof]
 tot = sum(r[1] for r in rows)
@@ -36,3 +38,12 @@ for k, (n, us, fl, by) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
 print("\nkind,tag,us,TFLOP/s,GB/s(algorithmic)")
 for k, us, fl, by, tag in sorted(rows, key=lambda r: -r[1])[:45]:
     print(f"{k},{tag},{us:.1f},{fl/us/1e6:.1f},{by/us/1e3:.0f}")
+
+# every op in launch order with its roofline floor (max of FLOPs / tensor peak and bytes / HBM peak); joined by
+# tools/join_ncu.py with the ncu launch list of the same command
+import json
+pk = bench.peaks()
+print("\n#ORDER idx,kind,tag,us_eager,gflop,mbytes,floor_us")
+for i, (k, us, fl, by, tag) in enumerate(rows):
+    floor = max(fl / (pk["tf_burst"] * 1e12), by / (pk["hbm"] * 1e9)) * 1e6
+    print(f"#ORDER {i},{k},{tag},{us:.1f},{fl/1e9:.3f},{by/1e6:.2f},{floor:.1f}")
