@@ -1,4 +1,5 @@
 // api.cu - error string, version and device probes of the C ABI (include/lpcyolo.h).
+#include <cstdlib>
 #include <stdarg.h>
 
 #include <atomic>
@@ -12,6 +13,11 @@ void lpc_set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool lpc_pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("LPC_PDL"); return !(e && e[0] == '0'); }();
+  return on;
 }
 
 static std::atomic<unsigned long long> g_launches{0};

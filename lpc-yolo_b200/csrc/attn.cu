@@ -15,6 +15,8 @@ constexpr int HD_IT = MAX_HD / 16;       // output columns per thread: tx, tx+16
 template <typename T>
 __global__ void __launch_bounds__(ATT_NT)
 psa_attention_kernel(const T* __restrict__ qkv, int ld, int N, int heads, int kd, int hd, T* __restrict__ out, int out_ld) {
+  pdl_trigger();
+  pdl_wait();
   constexpr bool PR = Precise<T>::value;
   extern __shared__ float smem[];
   float* Qs = smem;                       // [kd][BQ+4]   (transposed: Qs[c][i])
@@ -161,6 +163,8 @@ constexpr int MQ = 64, MK = 64, MMA_NT = 128;
 template <int KD, int HD>
 __global__ void __launch_bounds__(MMA_NT)
 psa_attention_mma_kernel(const bf16* __restrict__ qkv, int ld, int N, int heads, bf16* __restrict__ out, int out_ld) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int KDP = (KD + 15) / 16 * 16, KP = pitch_of(KDP), VP = pitch_of(HD);
   constexpr int CH = (KD % 8 == 0) ? 16 : 8;            // global->shared copy granularity in bytes
   constexpr int KCH = KD * 2 / CH, VCH = HD * 2 / 16;   // chunks per row
@@ -337,16 +341,16 @@ extern "C" int lpc_psa_attention(int dtype, const void* qkv, int qkv_ld, int B, 
   static bool attr_done[2] = {false, false};
   if (dtype == LPC_F32) {
     if (!attr_done[0]) { cudaFuncSetAttribute(psa_attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM); attr_done[0] = true; }
-    psa_attention_kernel<float><<<grid, ATT_NT, ATT_SMEM, s>>>((const float*)qkv, qkv_ld, N, heads, kd, hd, (float*)out, out_ld);
+    lpc_launch_pdl(psa_attention_kernel<float>, grid, ATT_NT, ATT_SMEM, s, (const float*)qkv, qkv_ld, N, heads, kd, hd, (float*)out, out_ld);
   } else if (dtype == LPC_BF16 && ((kd == 32 && hd == 64) || (kd == 36 && hd == 72)) && qkv_ld % 8 == 0 && out_ld % 2 == 0 &&
              aligned16(qkv) && (reinterpret_cast<uintptr_t>(out) & 3) == 0) {
     // tensor-core path (the two head geometries of the YOLOv10 / LPC family)
     dim3 g2(cdiv(N, MQ), heads, B);
-    if (kd == 32) psa_attention_mma_kernel<32, 64><<<g2, MMA_NT, 0, s>>>((const bf16*)qkv, qkv_ld, N, heads, (bf16*)out, out_ld);
-    else psa_attention_mma_kernel<36, 72><<<g2, MMA_NT, 0, s>>>((const bf16*)qkv, qkv_ld, N, heads, (bf16*)out, out_ld);
+    if (kd == 32) lpc_launch_pdl(psa_attention_mma_kernel<32, 64>, g2, MMA_NT, 0, s, (const bf16*)qkv, qkv_ld, N, heads, (bf16*)out, out_ld);
+    else lpc_launch_pdl(psa_attention_mma_kernel<36, 72>, g2, MMA_NT, 0, s, (const bf16*)qkv, qkv_ld, N, heads, (bf16*)out, out_ld);
   } else if (dtype == LPC_BF16) {
     if (!attr_done[1]) { cudaFuncSetAttribute(psa_attention_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM); attr_done[1] = true; }
-    psa_attention_kernel<bf16><<<grid, ATT_NT, ATT_SMEM, s>>>((const bf16*)qkv, qkv_ld, N, heads, kd, hd, (bf16*)out, out_ld);
+    lpc_launch_pdl(psa_attention_kernel<bf16>, grid, ATT_NT, ATT_SMEM, s, (const bf16*)qkv, qkv_ld, N, heads, kd, hd, (bf16*)out, out_ld);
   } else {
     LPC_FAIL(LPC_E_ARG, "psa_attention: unknown dtype %d", dtype);
   }

@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <utility>
+
 #include "../../include/lpcyolo.h"
 
 typedef __nv_bfloat16 bf16;
@@ -27,6 +29,31 @@ void lpc_count_launch();
     cudaError_t e__ = cudaGetLastError();                                                 \
     if (e__ != cudaSuccess) LPC_FAIL(LPC_E_CUDA, "%s: %s", name, cudaGetErrorString(e__)); \
   } while (0)
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
+// Kernels launched through lpc_launch_pdl may start while the previous kernel of the stream is still draining: their
+// prologue (barrier init, TMEM allocation, weight / bias staging - nothing the previous kernel produced) overlaps its
+// tail; they call pdl_wait() before touching activations and pdl_trigger() once their own dependents may be scheduled.
+// LPC_PDL=0 in the environment turns the attribute off (plain stream order).
+bool lpc_pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t lpc_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = lpc_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
@@ -129,6 +156,34 @@ template <bool PRECISE> __device__ __forceinline__ float mish_(float x) {
   const float e = ex2_approx(x * 1.4426950408889634f);
   const float d = fmaf(e, e + 2.0f, 2.0f);            // n + 2
   return x * fmaf(-2.0f, rcp_approx(d), 1.0f);        // x (1 - 2/(n+2)) = x n/(n+2)
+}
+// Packed (two elements per instruction: FFMA2 / FMUL2 / FADD2, sm_100) bf16-mode activations for the conv epilogues,
+// which are MUFU- and issue-bound on the small-channel layers (profiles/r01_h_*).  mish2_ spends ONE MUFU op per
+// element (ex2); the reciprocal is an integer-seeded Newton iteration on the FMA pipe (two steps: 6.6e-6 relative
+// error, measured over d in [2, 2^61]; the result x*n/(n+2) is a product, so there is no cancellation for x << 0).
+__device__ __forceinline__ float2 mish2_(float2 x) {
+  const float2 xl = __fmul2_rn(x, make_float2(1.4426950408889634f, 1.4426950408889634f));
+  float2 e;
+  e.x = ex2_approx(fminf(xl.x, 30.0f));      // clamp: d = e^2 + 2e + 2 stays finite; mish(x) = x beyond
+  e.y = ex2_approx(fminf(xl.y, 30.0f));
+  const float2 two = make_float2(2.0f, 2.0f);
+  const float2 t = __fadd2_rn(e, two);
+  const float2 n = __fmul2_rn(e, t);
+  const float2 d = __ffma2_rn(e, t, two);
+  float2 r;
+  r.x = __uint_as_float(0x7EF311C7u - __float_as_uint(d.x));
+  r.y = __uint_as_float(0x7EF311C7u - __float_as_uint(d.y));
+  const float2 nd = make_float2(-d.x, -d.y);
+  r = __fmul2_rn(r, __ffma2_rn(nd, r, two));
+  r = __fmul2_rn(r, __ffma2_rn(nd, r, two));
+  return __fmul2_rn(__fmul2_rn(x, n), r);
+}
+__device__ __forceinline__ float2 silu2_(float2 x) {
+  const float2 h = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  float2 th;
+  th.x = tanh_approx(h.x);
+  th.y = tanh_approx(h.y);
+  return __ffma2_rn(h, th, h);
 }
 template <bool PRECISE> __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {

@@ -18,6 +18,8 @@ conv_direct_kernel(const T* __restrict__ x, int x_ld, int B, int H, int W, int C
                    const T* __restrict__ w, const float* __restrict__ bias, int k, int stride, int pad,
                    int Cout, int Ho, int Wo, T* __restrict__ y, int y_ld, int act,
                    const float* __restrict__ chan_scale, const T* __restrict__ res, int res_ld) {
+  pdl_trigger();
+  pdl_wait();
   constexpr bool PR = Precise<T>::value;
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN];
@@ -122,11 +124,11 @@ extern "C" int lpc_conv2d_direct(int dtype, const void* x, int x_ld, int B, int 
   dim3 grid(cdiv(M, BM), cdiv(Cout, BN));
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == LPC_F32) {
-    conv_direct_kernel<float><<<grid, NT, 0, s>>>((const float*)x, x_ld, B, H, W, Cin, (const float*)w, bias, k,
+    lpc_launch_pdl(conv_direct_kernel<float>, grid, NT, 0, s, (const float*)x, x_ld, B, H, W, Cin, (const float*)w, bias, k,
                                                   stride, pad, Cout, Ho, Wo, (float*)y, y_ld, act, chan_scale,
                                                   (const float*)res, res_ld);
   } else if (dtype == LPC_BF16) {
-    conv_direct_kernel<bf16><<<grid, NT, 0, s>>>((const bf16*)x, x_ld, B, H, W, Cin, (const bf16*)w, bias, k,
+    lpc_launch_pdl(conv_direct_kernel<bf16>, grid, NT, 0, s, (const bf16*)x, x_ld, B, H, W, Cin, (const bf16*)w, bias, k,
                                                  stride, pad, Cout, Ho, Wo, (bf16*)y, y_ld, act, chan_scale,
                                                  (const bf16*)res, res_ld);
   } else {

@@ -51,6 +51,7 @@ struct ConvTcParams {
   int Ho, Wo, B;
   int tiles_x, tiles_y, TW, TH;
   int m_tiles, n_tiles, n_tile, acc_cols, tmem_cols;
+  int n_acc, acc_shift;              // TMEM accumulator buffers (2 or 4) and log2 of it
   int Cout, Cin, ksteps, kc, nsub, chunks_per_tap, real_slots, stages;
   int pix_per_img;
   float inv_tiles_per_img, inv_tiles_x, inv_tw;  // reciprocals for the small integer divisions of the tile scheduler
@@ -60,6 +61,7 @@ struct ConvTcParams {
   int H, W;
   int pitch, slabs, slab_bytes;      // halo patch: bytes per pixel row (32/64/128), 64-channel slabs
   int epi_split;                     // epilogue warps = 4 * epi_split
+  int epi_alt;                       // 1: the two epilogue warp groups take alternate tiles (full width each) instead of half the columns of every tile
   int dbg;                           // LPC_TC_DBG bits (profiling only): 1 skip MMAs, 2 skip A loads, 4 skip stores, 8 trace
   unsigned long long* trace;         // [4 roles][64 tiles][4 stamps] of clock64, CTA 0 only
   signed char tap_map[MAX_TAPS], tap_dx[MAX_TAPS], tap_dy[MAX_TAPS];
@@ -110,9 +112,15 @@ template <int ACT>
 __device__ __forceinline__ void store16(const uint32_t* v, bf16* yrow, const bf16* rrow, const float* srow, bool no_store = false) {
   float f[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const float t = __uint_as_float(v[i]);
-    f[i] = ACT == LPC_ACT_MISH ? mish_<false>(t) : ACT == LPC_ACT_SILU ? silu_<false>(t) : ACT == LPC_ACT_NONE ? t : apply_act<false>(t, ACT);
+  for (int i = 0; i < 16; i += 2) {
+    const float2 t = make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+    float2 r;
+    if (ACT == LPC_ACT_MISH) r = mish2_(t);
+    else if (ACT == LPC_ACT_SILU) r = silu2_(t);
+    else if (ACT == LPC_ACT_NONE) r = t;
+    else r = make_float2(apply_act<false>(t.x, ACT), apply_act<false>(t.y, ACT));
+    f[i] = r.x;
+    f[i + 1] = r.y;
   }
   if (srow) {
 #pragma unroll
@@ -151,7 +159,7 @@ __device__ __forceinline__ void epilogue_cols(uint32_t trow, int c, int c_end, b
 // Per-thread epilogue state that does not depend on the tile: computed once, so the per-tile cost is a handful of
 // integer ops (the whole SM is instruction-issue bound on the small-channel layers, profiles/r01_e_*).
 struct EpiCtx {
-  int ty, tx, c0, c_end;
+  int ty, tx, c0, c_end, group;
   uint32_t lane_off;     // TMEM lane-quarter offset
   bool row_ok;
 };
@@ -162,9 +170,10 @@ __device__ __forceinline__ EpiCtx make_epi_ctx(const ConvTcParams& p, int warp, 
   const int r = q * 32 + lane;
   e.ty = fast_div(r, p.TW, p.inv_tw);
   e.tx = r - e.ty * p.TW;
-  const int cols = p.n_tile / p.epi_split;
-  e.c0 = part * cols;
+  const int cols = p.epi_alt ? p.n_tile : p.n_tile / p.epi_split;
+  e.c0 = p.epi_alt ? 0 : part * cols;
   e.c_end = e.c0 + cols;
+  e.group = part;
   e.lane_off = (uint32_t)(q * 32) << 16;
   e.row_ok = e.ty < p.TH && !(p.dbg & 4);
   return e;
@@ -206,7 +215,7 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvTcParams& p, int m_idx
 __global__ void __launch_bounds__(320, 2)
 conv_tc_taps_kernel(const __grid_constant__ TmapPack maps, const __grid_constant__ ConvTcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  __shared__ __align__(8) unsigned long long bars[2 * MAX_STAGES + 4];
+  __shared__ __align__(8) unsigned long long bars[2 * MAX_STAGES + 8];
   __shared__ uint32_t tmem_base_slot;
 
   const uint32_t ones_addr = (smem_u32(smem_raw) + 1023u) & ~1023u;   // [ones | bias | pad] precede the stage ring
@@ -219,7 +228,7 @@ conv_tc_taps_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
   auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * MAX_STAGES + b); };
-  auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * MAX_STAGES + 2 + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * MAX_STAGES + 4 + b); };
 
   const int n_idx = blockIdx.x % p.n_tiles;
   const int m_first = blockIdx.x / p.n_tiles, m_step = gridDim.x / p.n_tiles;
@@ -232,9 +241,9 @@ conv_tc_taps_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < p.n_acc; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 4 * p.epi_split);
+      mbar_init(tempty_bar(b), p.epi_alt ? 4 : 4 * p.epi_split);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -244,6 +253,8 @@ conv_tc_taps_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_trigger();      // the next kernel's prologue may overlap this kernel
+  pdl_wait();         // everything above touched only weights / bias / on-chip state
 
   if (warp == 0) {
     if (elect_one_sync()) {
@@ -285,8 +296,8 @@ conv_tc_taps_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
       const int last_real = (p.real_slots * p.kc - (p.ksteps - 1) * 64) / 16;   // real K=16 slices of the last step
       int it = 0, tcount = 0;
       for (int m = m_first; m < p.m_tiles; m += m_step, ++tcount) {
-        const int buf = tcount & 1;
-        mbar_wait(tempty_bar(buf), (uint32_t)(((tcount >> 1) & 1) ^ 1));
+        const int buf = tcount & (p.n_acc - 1);
+        mbar_wait(tempty_bar(buf), (uint32_t)(((tcount >> p.acc_shift) & 1) ^ 1));
         tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)(buf * p.acc_cols);
         issue_bias_mma(acc, ones_addr, bias_addr, p.n_tile, idesc);      // accumulator := bias
@@ -309,9 +320,10 @@ conv_tc_taps_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
     const EpiCtx ectx = make_epi_ctx(p, warp, lane);
     int tcount = 0;
     for (int m = m_first; m < p.m_tiles; m += m_step, ++tcount) {
+      if (p.epi_alt && (tcount & 1) != ectx.group) continue;   // the other warp group's tile
       const TileCoord t = tile_coord(p, m);
-      const int buf = tcount & 1;
-      mbar_wait(tfull_bar(buf), (uint32_t)((tcount >> 1) & 1));
+      const int buf = tcount & (p.n_acc - 1);
+      mbar_wait(tfull_bar(buf), (uint32_t)((tcount >> p.acc_shift) & 1));
       tc_fence_after();
       epilogue_tile(p, ectx, tmem_base + (uint32_t)(buf * p.acc_cols), t.img, t.x0, t.y0, n0);
       tc_fence_before();
@@ -335,7 +347,7 @@ template <int CIN, int BRES>   // CIN > 0: patch geometry and the MMA issue sequ
 __global__ void __launch_bounds__(448, 2)
 conv_tc_halo_kernel(const __grid_constant__ TmapPack maps, const __grid_constant__ ConvTcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  __shared__ __align__(8) unsigned long long bars[4 * MAX_STAGES + 4];
+  __shared__ __align__(8) unsigned long long bars[4 * MAX_STAGES + 8];
   __shared__ uint32_t tmem_base_slot;
 
   const uint32_t ones_addr = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -355,7 +367,7 @@ conv_tc_halo_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
   auto afull_bar = [&](int s) { return bar0 + 8u * (2 * MAX_STAGES + s); };
   auto aempty_bar = [&](int s) { return bar0 + 8u * (3 * MAX_STAGES + s); };
   auto tfull_bar = [&](int b) { return bar0 + 8u * (4 * MAX_STAGES + b); };
-  auto tempty_bar = [&](int b) { return bar0 + 8u * (4 * MAX_STAGES + 2 + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (4 * MAX_STAGES + 4 + b); };
 
   const int n_idx = blockIdx.x % p.n_tiles;
   const int m_first = blockIdx.x / p.n_tiles, m_step = gridDim.x / p.n_tiles;
@@ -372,9 +384,9 @@ conv_tc_halo_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
       mbar_init(afull_bar(s), HALO_LOADERS);
       mbar_init(aempty_bar(s), 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < p.n_acc; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 4 * p.epi_split);
+      mbar_init(tempty_bar(b), p.epi_alt ? 4 : 4 * p.epi_split);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -384,6 +396,8 @@ conv_tc_halo_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_trigger();      // the next kernel's prologue may overlap this kernel
+  if (warp != 0) pdl_wait();   // warp 0 only streams weights (constants); every other role touches activations
 
   if (warp == 0) {
     if (elect_one_sync()) {
@@ -485,10 +499,10 @@ conv_tc_halo_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
       if (b_res) mbar_wait(bfull_bar(0), 0);
       int tcount = 0, bit = 0;
       for (int m = m_first; m < p.m_tiles; m += m_step, ++tcount) {
-        const int buf = tcount & 1;
+        const int buf = tcount & (p.n_acc - 1);
         const int ab = tcount % p.a_bufs;
         TRACE(1, tcount, 0);
-        mbar_wait(tempty_bar(buf), (uint32_t)(((tcount >> 1) & 1) ^ 1));
+        mbar_wait(tempty_bar(buf), (uint32_t)(((tcount >> p.acc_shift) & 1) ^ 1));
         TRACE(1, tcount, 1);
         mbar_wait(afull_bar(ab), (uint32_t)((tcount / p.a_bufs) & 1));
         TRACE(1, tcount, 2);
@@ -560,10 +574,11 @@ conv_tc_halo_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
     const EpiCtx ectx = make_epi_ctx(p, warp, lane);
     int tcount = 0;
     for (int m = m_first; m < p.m_tiles; m += m_step, ++tcount) {
+      if (p.epi_alt && (tcount & 1) != ectx.group) continue;   // the other warp group's tile
       const TileCoord t = tile_coord(p, m);
-      const int buf = tcount & 1;
+      const int buf = tcount & (p.n_acc - 1);
       if (threadIdx.x == 64) TRACE(2, tcount, 0);
-      mbar_wait(tfull_bar(buf), (uint32_t)((tcount >> 1) & 1));
+      mbar_wait(tfull_bar(buf), (uint32_t)((tcount >> p.acc_shift) & 1));
       if (threadIdx.x == 64) TRACE(2, tcount, 1);
       tc_fence_after();
       epilogue_tile(p, ectx, tmem_base + (uint32_t)(buf * p.acc_cols), t.img, t.x0, t.y0, n0);
@@ -578,6 +593,8 @@ conv_tc_halo_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
+
+#include "conv_tc_pair.cuh"
 
 // ---- host side -------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -719,7 +736,7 @@ extern "C" int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int C
   { const char* e = getenv("LPC_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
 
   // ---- choose the kernel -------------------------------------------------------------------------------
-  bool halo = false;
+  bool halo = false, pair = false;
   if (k == 3 && stride == 1 && g_force_mode != 1 && (Cin == 16 || Cin == 32 || Cin % 64 == 0) && Cin <= 256) {
     const long long tiles = (long long)((Wo + HALO_TW - 1) / HALO_TW) * ((Ho + HALO_TH - 1) / HALO_TH);
     const double eff = (double)Ho * Wo / (double)(tiles * 128);
@@ -739,7 +756,26 @@ extern "C" int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int C
       resident = 0;
       need = (size_t)3 * nt * 128 + 2 * halo_bytes;
     }
-    if ((eff >= 0.7 || g_force_mode == 2) && need <= SMEM_LIMIT) {
+    // CTA pairs (cta_group::2, conv_tc_pair.cuh): full-width N with HALF the weight rows resident per CTA
+    {
+      static const int pair_env = [] { const char* e = getenv("LPC_TC_PAIR"); return e ? atoi(e) : 1; }();
+      const int ntp = pick_ntile(Cout, 256);
+      const size_t bp = (size_t)p.ksteps * (ntp / 2) * 128;
+      const long long tot_tiles = tiles * B;
+      // Worth it where the tile is MMA-instruction bound (>= 36 MMAs of N >= 128, or Cin >= 128); the small-channel
+      // layers are bound by per-tile role latency and lose to the extra cross-CTA hops (measured: 16->32 327 vs 217 us,
+      // 32->64 147 vs 138, 64->64 tie, 64->128 79 vs 121).  LPC_TC_PAIR=2 forces pairs wherever they fit (tests).
+      const bool wanted = pair_env == 2 || (Cin >= 64 && Cout >= 128) || Cin >= 128;
+      if (pair_env && wanted && (eff >= 0.7 || g_force_mode == 2) && bp + 2 * halo_bytes <= SMEM_LIMIT && tot_tiles >= 4) {
+        halo = pair = true;
+        p.n_tile = ntp;
+        p.b_resident = 1;
+        const size_t budget = (ntp <= 128 && bp + 3 * halo_bytes <= 100 * 1024) ? 100 * 1024 : SMEM_LIMIT;
+        int ab = (int)((budget - bp) / halo_bytes);
+        p.a_bufs = ab > MAX_STAGES ? MAX_STAGES : (ab < 2 ? 2 : ab);
+      }
+    }
+    if (!pair && (eff >= 0.7 || g_force_mode == 2) && need <= SMEM_LIMIT) {
       halo = true;
       p.n_tile = nt;
       p.b_resident = resident;
@@ -755,8 +791,9 @@ extern "C" int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int C
   p.n_tiles = Cout / p.n_tile;
   p.acc_cols = 32;
   while (p.acc_cols < p.n_tile) p.acc_cols <<= 1;
+  p.n_acc = 2;
+  p.acc_shift = 1;
   p.tmem_cols = 2 * p.acc_cols;
-  if ((p.dbg & 16) && p.acc_cols <= 32) p.tmem_cols = 256;   // experiment: spread dependent MMAs over 4 accumulators
   p.epi_split = (p.n_tile % 32 == 0) ? 2 : 1;
 
   size_t smem = 0;
@@ -768,7 +805,7 @@ extern "C" int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int C
     p.pitch = (Cin >= 64 ? 64 : Cin) * 2;
     p.slabs = (Cin + 63) / 64;
     p.slab_bytes = HALO_PH * HALO_SPW * p.pitch;
-    smem = (size_t)(p.b_resident ? p.ksteps : p.b_stages) * p.n_tile * 128 + (size_t)p.a_bufs * p.slabs * p.slab_bytes + 1024 + BIAS_REGION(p.n_tile);
+    smem = (size_t)(p.b_resident ? p.ksteps : p.b_stages) * (pair ? p.n_tile / 2 : p.n_tile) * 128 + (size_t)p.a_bufs * p.slabs * p.slab_bytes + 1024 + BIAS_REGION(p.n_tile);
   } else {
     p.kc = pick_kc(Cin);
     p.nsub = 64 / p.kc;
@@ -821,7 +858,7 @@ extern "C" int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int C
   {
     cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)Cout};
     cuuint64_t strides[1] = {(cuuint64_t)kpad * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)p.n_tile};
+    cuuint32_t box[2] = {64, (cuuint32_t)(pair ? p.n_tile / 2 : p.n_tile)};   // a CTA of a pair loads its half of the rows
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&maps.b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -834,17 +871,43 @@ extern "C" int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int C
     cudaError_t e2 = cudaSuccess;
     const int lim = (int)SMEM_LIMIT + 16 * 1024;
 #define HALO_ATTR(C_, R_) if (cudaFuncSetAttribute(conv_tc_halo_kernel<C_, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess) e2 = cudaErrorUnknown;
+#define PAIR_ATTR(C_) if (cudaFuncSetAttribute(conv_tc_halo2_kernel<C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess) e2 = cudaErrorUnknown;
+    PAIR_ATTR(0) PAIR_ATTR(16) PAIR_ATTR(32) PAIR_ATTR(64) PAIR_ATTR(128)
+#undef PAIR_ATTR
     HALO_ATTR(0, -1) HALO_ATTR(16, 1) HALO_ATTR(32, 1) HALO_ATTR(64, 1) HALO_ATTR(128, 1) HALO_ATTR(128, 0)
 #undef HALO_ATTR
     if (e1 != cudaSuccess || e2 != cudaSuccess) LPC_FAIL(LPC_E_CUDA, "conv2d_tc: smem attribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
     attr_set = true;
   }
+  // Four accumulator buffers when TMEM allows without costing a resident CTA: with two, the per-buffer chain
+  // MMA(t) -> epilogue(t) -> MMA(t+2) makes the tile period (M + E) / 2 instead of max(M, E / groups).
+  {
+    static const int force = [] { const char* e = getenv("LPC_TC_NACC"); return e ? atoi(e) : 0; }();
+    const bool one_cta = smem > 110 * 1024;
+    if (4 * p.acc_cols <= 256 || (one_cta && 4 * p.acc_cols <= 512)) p.n_acc = 4;
+    if (force == 2 || (force == 4 && 4 * p.acc_cols <= 512)) p.n_acc = force;
+    p.acc_shift = p.n_acc == 4 ? 2 : 1;
+    p.tmem_cols = p.n_acc * p.acc_cols;
+  }
   const int ctas_per_sm = (p.tmem_cols <= 256 && smem <= 110 * 1024) ? 2 : 1;
   int per_n = (num_sms() * ctas_per_sm) / p.n_tiles;
   if (per_n < 1) per_n = 1;
   if (per_n > p.m_tiles) per_n = p.m_tiles;
-  const unsigned grid = (unsigned)(per_n * p.n_tiles);
+  if (pair) {                                   // per_n counts CTA PAIRS here; each pair walks two M tiles at a time
+    per_n = (num_sms() * ctas_per_sm / 2) / p.n_tiles;
+    if (per_n < 1) per_n = 1;
+    if (per_n > (p.m_tiles + 1) / 2) per_n = (p.m_tiles + 1) / 2;
+  }
+  const unsigned grid = (unsigned)(per_n * p.n_tiles) * (pair ? 2u : 1u);
   const unsigned threads = 64 + 128 * p.epi_split;
+  // Each role is latency-bound per tile (~1.5-2k cycles: barrier round trips, tcgen05.ld, MUFU chains), so with enough
+  // tiles per CTA the two epilogue warp groups take alternate tiles (two epilogues in flight) instead of splitting the
+  // columns of one; LPC_TC_EPI_ALT=0/1 overrides (profiling).
+  {
+    static const int force = [] { const char* e = getenv("LPC_TC_EPI_ALT"); return e ? atoi(e) : -1; }();
+    p.epi_alt = (p.epi_split == 2 && p.m_tiles / (per_n * (pair ? 2 : 1)) >= 4) ? 1 : 0;
+    if (force >= 0 && p.epi_split == 2) p.epi_alt = force;
+  }
   static unsigned long long* trace_buf = nullptr;
   if (p.dbg & 8) {
     if (!trace_buf) cudaMalloc(&trace_buf, 4 * 64 * 4 * 8);
@@ -855,16 +918,25 @@ extern "C" int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int C
     LPC_REQUIRE((long long)H * W * x_ld < (1ll << 31), "conv2d_tc: image too large for 32-bit offsets");
     const unsigned th = threads + HALO_LOADERS;
     cudaStream_t st = (cudaStream_t)stream;
+    if (pair) {
+      switch (Cin) {
+        case 16: lpc_launch_pdl(conv_tc_halo2_kernel<16>, grid, th, smem, st, maps, p); break;
+        case 32: lpc_launch_pdl(conv_tc_halo2_kernel<32>, grid, th, smem, st, maps, p); break;
+        case 64: lpc_launch_pdl(conv_tc_halo2_kernel<64>, grid, th, smem, st, maps, p); break;
+        case 128: lpc_launch_pdl(conv_tc_halo2_kernel<128>, grid, th, smem, st, maps, p); break;
+        default: lpc_launch_pdl(conv_tc_halo2_kernel<0>, grid, th, smem, st, maps, p); break;
+      }
+    } else
     switch (Cin) {
-      case 16: if (p.b_resident) { conv_tc_halo_kernel<16, 1><<<grid, th, smem, st>>>(maps, p); break; }
-      case 32: if (p.b_resident && Cin == 32) { conv_tc_halo_kernel<32, 1><<<grid, th, smem, st>>>(maps, p); break; }
-      case 64: if (p.b_resident && Cin == 64) { conv_tc_halo_kernel<64, 1><<<grid, th, smem, st>>>(maps, p); break; }
-      case 128: if (Cin == 128) { if (p.b_resident) conv_tc_halo_kernel<128, 1><<<grid, th, smem, st>>>(maps, p); else conv_tc_halo_kernel<128, 0><<<grid, th, smem, st>>>(maps, p); break; }
-      default: conv_tc_halo_kernel<0, -1><<<grid, th, smem, st>>>(maps, p); break;
+      case 16: if (p.b_resident) { lpc_launch_pdl(conv_tc_halo_kernel<16, 1>, grid, th, smem, st, maps, p); break; }
+      case 32: if (p.b_resident && Cin == 32) { lpc_launch_pdl(conv_tc_halo_kernel<32, 1>, grid, th, smem, st, maps, p); break; }
+      case 64: if (p.b_resident && Cin == 64) { lpc_launch_pdl(conv_tc_halo_kernel<64, 1>, grid, th, smem, st, maps, p); break; }
+      case 128: if (Cin == 128) { if (p.b_resident) lpc_launch_pdl(conv_tc_halo_kernel<128, 1>, grid, th, smem, st, maps, p); else lpc_launch_pdl(conv_tc_halo_kernel<128, 0>, grid, th, smem, st, maps, p); break; }
+      default: lpc_launch_pdl(conv_tc_halo_kernel<0, -1>, grid, th, smem, st, maps, p); break;
     }
   }
   else
-    conv_tc_taps_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(maps, p);
+    lpc_launch_pdl(conv_tc_taps_kernel, grid, threads, smem, (cudaStream_t)stream, maps, p);
   LPC_CHECK_LAUNCH("conv2d_tc");
   if ((p.dbg & 8) && halo) {
     static int dumps = 0;

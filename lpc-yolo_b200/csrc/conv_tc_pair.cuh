@@ -1,0 +1,211 @@
+// conv_tc_pair.cuh - the 3x3 stride-1 halo-patch convolution on CTA PAIRS (tcgen05 cta_group::2).
+// Included by conv_tc.cu inside its anonymous namespace (shares ConvTcParams, the epilogue and the tile scheduler).
+//
+// The small-channel 3x3 layers are bound by the rate of tcgen05.mma INSTRUCTIONS, not by the tensor pipe: a
+// cta_group::1 MMA (M = 128) costs ~70 cycles for any N <= 64, a cta_group::2 MMA (M = 256 over two SMs) ~50
+// (tools/mma_bench.cu, profiles/r01_i_mma_rates.txt).  So two CTAs of a cluster each own one 8 x 16-pixel M tile (their
+// halo patch sits at the same shared-memory offset in both), each keeps HALF of the weight rows resident
+// ([n_tile/2][K], which also lets Cout = 128 layers issue N = 128), and the leader CTA's single thread issues M = 256
+// MMAs for the pair.  Signalling:
+//   loaders  (both CTAs, per warp) --arrive.cluster--> leader afull[s]      (count 2 x 4)
+//   leader MMA --commit.multicast--> aempty[s], tfull[b] in BOTH CTAs
+//   epilogue (both CTAs, per warp) --arrive.cluster--> leader tempty[b]     (count 2 x warps per tile)
+//   weights: each CTA TMA-loads its half, then its warp 0 arrives on the leader's wready barrier (count 2)
+template <int CIN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(448, 2)
+conv_tc_halo2_kernel(const __grid_constant__ TmapPack maps, const __grid_constant__ ConvTcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long bars[2 * MAX_STAGES + 10];
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t rank = cluster_ctarank();
+  const int half = p.n_tile >> 1;                                     // weight rows held by this CTA
+  const uint32_t ones_addr = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bias_addr = ones_addr + ONES_BYTES;
+  const uint32_t smem_base = (bias_addr + (uint32_t)half * 32u + 1023u) & ~1023u;
+  const int b_block = half * 128;                                     // bytes of one 64-wide K step of this CTA's half
+  const int halo_bytes = p.slabs * p.slab_bytes;
+  const int chunks_px = p.Cin / 8;
+  const int chunks_row = p.pitch / 16;
+  const uint32_t a_region = smem_base + (uint32_t)(p.ksteps * b_block);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(&bars[0]);
+  auto afull_bar = [&](int s) { return bar0 + 8u * s; };                       // used in the leader only
+  auto aempty_bar = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * MAX_STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * MAX_STAGES + 4 + b); };  // leader only
+  const uint32_t bfull_bar = bar0 + 8u * (2 * MAX_STAGES + 8);                 // local: this CTA's weights landed
+  const uint32_t wready_bar = bar0 + 8u * (2 * MAX_STAGES + 9);                // leader: both halves landed
+
+  const int pair = blockIdx.x >> 1, pairs = gridDim.x >> 1;
+  const int n_idx = pair % p.n_tiles;
+  const int mp_first = pair / p.n_tiles, mp_step = pairs / p.n_tiles;
+  const int n0 = n_idx * p.n_tile;
+  const int epi_warps_per_tile = p.epi_alt ? 4 : 4 * p.epi_split;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&maps.b);
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      mbar_init(afull_bar(s), 2 * (HALO_LOADERS / 32));
+      mbar_init(aempty_bar(s), 1);
+    }
+    for (int b = 0; b < 4; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 2 * epi_warps_per_tile);
+    }
+    mbar_init(bfull_bar, 1);
+    mbar_init(wready_bar, 2);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc2(smem_u32(&tmem_base_slot), (uint32_t)p.tmem_cols);
+  write_bias_tiles(ones_addr, bias_addr, p.bias, n0 + (int)rank * half, half);
+  tc_fence_before();
+  cluster_sync_all();             // barriers of both CTAs initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  pdl_trigger();
+  if (warp != 0) pdl_wait();      // warp 0 only streams weights (constants)
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      mbar_expect_tx(bfull_bar, (uint32_t)(p.ksteps * b_block));
+      for (int ks = 0; ks < p.ksteps; ++ks) tma_load_2d(smem_base + (uint32_t)(ks * b_block), &maps.b, bfull_bar, ks * 64, n0 + (int)rank * half);
+      mbar_wait(bfull_bar, 0);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive_rank(wready_bar, 0);
+    }
+  } else if (warp >= 2 + 4 * p.epi_split) {
+    // ===== activation loaders (as in conv_tc_halo_kernel; one arrival per warp on the leader's barrier) =====
+    const int lt = threadIdx.x - (2 + 4 * p.epi_split) * 32;
+    const int look = p.a_bufs >= 6 ? 3 : (p.a_bufs >= 4 ? 2 : 1);
+    int ppy[2], ppx[2];
+    uint32_t row_off[2], phase[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int pix = lt + q * HALO_LOADERS;
+      ppy[q] = pix / HALO_PW;
+      ppx[q] = pix - ppy[q] * HALO_PW;
+      row_off[q] = (uint32_t)((ppy[q] * HALO_SPW + ppx[q]) * p.pitch);
+      phase[q] = (row_off[q] >> 7) & (uint32_t)(chunks_row - 1);
+    }
+    const bool second = lt + HALO_LOADERS < HALO_PW * HALO_PH;
+    const int img_elems = p.H * p.W * (int)p.x_ld;
+    int tcount = 0;
+    for (int mp = mp_first; 2 * mp < p.m_tiles; mp += mp_step, ++tcount) {
+      const int m = 2 * mp + (int)rank;
+      const bool live = m < p.m_tiles;                    // odd tile count: the last pair's second CTA only signals
+      const TileCoord t = tile_coord(p, live ? m : 0);
+      const int ab = tcount % p.a_bufs;
+      mbar_wait(aempty_bar(ab), (uint32_t)(((tcount / p.a_bufs) & 1) ^ 1));
+      const uint32_t a_dst = a_region + (uint32_t)(ab * halo_bytes);
+      const bf16* img_base = p.x + (long long)t.img * img_elems;
+      if (live) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          if (q == 0 || second) {
+            const int iy = t.y0 - 1 + ppy[q], ix = t.x0 - 1 + ppx[q];
+            const bool in = (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
+            const bf16* src = in ? img_base + (iy * p.W + ix) * (int)p.x_ld : p.x;
+            const uint32_t nb = in ? 16u : 0u;
+            uint32_t dst_row = a_dst + row_off[q];
+            if (CIN > 0) {
+              constexpr int CROW = (CIN < 64 ? CIN : 64) / 8, NSLAB = (CIN + 63) / 64;
+              constexpr int SLABB = HALO_PH * HALO_SPW * (CIN < 64 ? CIN : 64) * 2;
+#pragma unroll
+              for (int sl = 0; sl < NSLAB; ++sl)
+#pragma unroll
+                for (int cw = 0; cw < CROW; ++cw)
+                  cp_async16(dst_row + (uint32_t)(sl * SLABB) + (((uint32_t)cw ^ phase[q]) << 4), src + (in ? (sl * CROW + cw) * 8 : 0), nb);
+            } else {
+              for (int c0 = 0; c0 < chunks_px; c0 += chunks_row, dst_row += (uint32_t)p.slab_bytes)
+#pragma unroll 4
+                for (int cw = 0; cw < chunks_row; ++cw)
+                  cp_async16(dst_row + (((uint32_t)cw ^ phase[q]) << 4), src + (in ? (c0 + cw) * 8 : 0), nb);
+            }
+          }
+        }
+      }
+      cp_async_commit();
+      if (tcount >= look) {
+        cp_async_wait_dyn(look);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_rank(afull_bar((tcount - look) % p.a_bufs), 0);
+      }
+    }
+    cp_async_wait_dyn(0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0)
+      for (int i = (tcount > look ? tcount - look : 0); i < tcount; ++i) mbar_arrive_rank(afull_bar(i % p.a_bufs), 0);
+  } else if (warp == 1) {
+    // ===== MMA issuer: the leader CTA's elected thread, M = 256 over the pair =====
+    if (rank == 0 && elect_one_sync()) {
+      const uint32_t idesc = make_idesc_m(p.n_tile, 256);
+      const uint32_t a_layout = p.pitch == 128 ? 2u : (p.pitch == 64 ? 4u : 6u);
+      const uint32_t a_hi = desc_hi((uint32_t)(HALO_SPW * p.pitch), a_layout), b_hi = desc_hi(1024u, 2u);
+      const uint32_t pitch16 = (uint32_t)p.pitch >> 4, slab16 = (uint32_t)p.slab_bytes >> 4, bblk16 = (uint32_t)b_block >> 4;
+      const int groups = (p.Cin < 64 ? p.Cin : 64) / 16;
+      const uint32_t b_lo0 = desc_lo(smem_base, 16u);
+      const uint64_t ones_desc = smem_desc(ones_addr, 16u, 256u, 6u), bias_desc = smem_desc(bias_addr, 16u, 256u, 6u);
+      mbar_wait_cluster(wready_bar, 0);
+      int tcount = 0;
+      for (int mp = mp_first; 2 * mp < p.m_tiles; mp += mp_step, ++tcount) {
+        const int buf = tcount & (p.n_acc - 1);
+        const int ab = tcount % p.a_bufs;
+        mbar_wait_cluster(tempty_bar(buf), (uint32_t)(((tcount >> p.acc_shift) & 1) ^ 1));
+        mbar_wait_cluster(afull_bar(ab), (uint32_t)((tcount / p.a_bufs) & 1));
+        tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)(buf * p.acc_cols);
+        const uint32_t a_lo0 = desc_lo(a_region + (uint32_t)(ab * halo_bytes), 16u);
+        umma2_bf16(acc, ones_desc, bias_desc, idesc, 0u);                  // accumulator := bias
+        if (CIN > 0) {
+          constexpr int C_ROW = CIN < 64 ? CIN : 64, PITCH16 = C_ROW * 2 / 16, GROUPS = C_ROW / 16, SLABS = (CIN + 63) / 64;
+          constexpr int SLAB16 = HALO_PH * HALO_SPW * C_ROW * 2 / 16;
+#pragma unroll
+          for (int j = 0; j < 9 * SLABS * GROUPS; ++j) {
+            const int tap = j / (SLABS * GROUPS), sl = (j / GROUPS) % SLABS, g = j % GROUPS;
+            const int kin_c = j & 3, ks_c = j >> 2;
+            umma2_acc(acc, desc64(a_lo0 + (uint32_t)(((tap / 3) * HALO_SPW + tap % 3) * PITCH16 + sl * SLAB16 + 2 * g), a_hi),
+                      desc64(b_lo0 + (uint32_t)ks_c * bblk16 + 2u * (uint32_t)kin_c, b_hi), idesc);
+          }
+        } else {
+          int kin = 0, ks = 0;
+          for (int ty = 0; ty < 3; ++ty)
+            for (int tx = 0; tx < 3; ++tx) {
+              const uint32_t tap_lo = a_lo0 + (uint32_t)(ty * HALO_SPW + tx) * pitch16;
+              for (int sl = 0; sl < p.slabs; ++sl)
+                for (int g = 0; g < groups; ++g) {
+                  umma2_acc(acc, desc64(tap_lo + (uint32_t)sl * slab16 + 2u * (uint32_t)g, a_hi),
+                            desc64(b_lo0 + (uint32_t)ks * bblk16 + 2u * (uint32_t)kin, b_hi), idesc);
+                  if (++kin == 4) { kin = 0; ++ks; }
+                }
+            }
+        }
+        umma2_commit_both(aempty_bar(ab));
+        umma2_commit_both(tfull_bar(buf));
+      }
+    }
+  } else {
+    // ===== epilogue (local accumulator rows; arrival on the leader's tempty) =====
+    const EpiCtx ectx = make_epi_ctx(p, warp, lane);
+    int tcount = 0;
+    for (int mp = mp_first; 2 * mp < p.m_tiles; mp += mp_step, ++tcount) {
+      if (p.epi_alt && (tcount & 1) != ectx.group) continue;
+      const int m = 2 * mp + (int)rank;
+      const int buf = tcount & (p.n_acc - 1);
+      mbar_wait(tfull_bar(buf), (uint32_t)((tcount >> p.acc_shift) & 1));
+      tc_fence_after();
+      if (m < p.m_tiles) {
+        const TileCoord t = tile_coord(p, m);
+        epilogue_tile(p, ectx, tmem_base + (uint32_t)(buf * p.acc_cols), t.img, t.x0, t.y0, n0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_rank(tempty_bar(buf), 0);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();             // the peer's shared memory / barriers stay alive until both CTAs are done
+  if (warp == 1) tmem_dealloc2(tmem_base, (uint32_t)p.tmem_cols);
+}

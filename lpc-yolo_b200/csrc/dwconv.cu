@@ -17,6 +17,8 @@ dwconv_kernel(const T* __restrict__ x, int x_ld, int B, int H, int W, int C,
               const float* __restrict__ w, const float* __restrict__ bias, int pad,
               int Ho, int Wo, T* __restrict__ y, int y_ld, int act,
               const T* __restrict__ res, int res_ld) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int V = Vec<T>::N;
   constexpr bool PR = Precise<T>::value;
   constexpr int NV = (PX - 1) * S + (K - 1) * D + 1;
@@ -142,6 +144,8 @@ dwconv_kernel(const T* __restrict__ x, int x_ld, int B, int H, int W, int C,
 template <typename T>
 __global__ void __launch_bounds__(256)
 sppf_pool_kernel(const T* __restrict__ x, int x_ld, int H, int W, int C, T* __restrict__ y, int y_ld) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int V = Vec<T>::N;
   extern __shared__ float4 sp4[];
   const int HW = H * W;
@@ -204,7 +208,7 @@ int launch_dw(const void* x, int x_ld, int B, int H, int W, int C, const float* 
   const long long per_strip = (long long)8 * ((Wo + PX - 1) / PX) * (C / V);
   LPC_REQUIRE(per_strip < (1ll << 31) && B <= 65535 && (Ho + 7) / 8 <= 65535, "dwconv2d: shape too large");
   dim3 grid(cdiv(per_strip, 128), (Ho + 7) / 8, B);
-  dwconv_kernel<T, K, S, D, PX><<<grid, 128, 0, s>>>((const T*)x, x_ld, B, H, W, C, w, bias, pad, Ho, Wo,
+  lpc_launch_pdl(dwconv_kernel<T, K, S, D, PX>, grid, 128, 0, s, (const T*)x, x_ld, B, H, W, C, w, bias, pad, Ho, Wo,
                                                                 (T*)y, y_ld, act, (const T*)res, res_ld);
   LPC_CHECK_LAUNCH("dwconv2d");
   return LPC_OK;
@@ -254,10 +258,10 @@ extern "C" int lpc_sppf_pool(int dtype, const void* x, int x_ld, int B, int H, i
   dim3 grid(C / 8, B);
   if (dtype == LPC_F32) {
     cudaFuncSetAttribute(sppf_pool_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    sppf_pool_kernel<float><<<grid, 256, smem, s>>>((const float*)x, x_ld, H, W, C, (float*)y, y_ld);
+    lpc_launch_pdl(sppf_pool_kernel<float>, grid, 256, smem, s, (const float*)x, x_ld, H, W, C, (float*)y, y_ld);
   } else if (dtype == LPC_BF16) {
     cudaFuncSetAttribute(sppf_pool_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    sppf_pool_kernel<bf16><<<grid, 256, smem, s>>>((const bf16*)x, x_ld, H, W, C, (bf16*)y, y_ld);
+    lpc_launch_pdl(sppf_pool_kernel<bf16>, grid, 256, smem, s, (const bf16*)x, x_ld, H, W, C, (bf16*)y, y_ld);
   } else
     LPC_FAIL(LPC_E_ARG, "sppf_pool: unknown dtype %d", dtype);
   LPC_CHECK_LAUNCH("sppf_pool");

@@ -8,6 +8,8 @@ namespace {
 // y[n, y, x, :] = x[n, y/2, x/2, :]
 template <typename T>
 __global__ void upsample2x_kernel(const T* __restrict__ x, int x_ld, int B, int H, int W, int C, T* __restrict__ y, int y_ld) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int V = Vec<T>::N;
   const int cvecs = C / V;
   const long long total = (long long)B * H * W * cvecs;  // one thread per INPUT vector, writes 4 outputs
@@ -30,6 +32,8 @@ __global__ void upsample2x_kernel(const T* __restrict__ x, int x_ld, int B, int 
 
 template <typename T>
 __global__ void copy_channels_kernel(const T* __restrict__ x, int x_ld, long long npix, int C, T* __restrict__ y, int y_ld) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int V = Vec<T>::N;
   const int cvecs = C / V;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -43,6 +47,8 @@ __global__ void copy_channels_kernel(const T* __restrict__ x, int x_ld, long lon
 // (block.py:4070: [::2,::2], [1::2,::2], [::2,1::2], [1::2,1::2] -> row parity varies fastest)
 template <typename T>
 __global__ void space_to_depth_kernel(const T* __restrict__ x, int x_ld, int B, int H, int W, int C, T* __restrict__ y, int y_ld) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int V = Vec<T>::N;
   const int cvecs = C / V;
   const int Ho = H / 2, Wo = W / 2;
@@ -65,6 +71,8 @@ __global__ void space_to_depth_kernel(const T* __restrict__ x, int x_ld, int B, 
 // y[p, j] = x[p, 2j], y[p, C/2 + j] = x[p, 2j+1]
 template <typename T>
 __global__ void deinterleave_kernel(const T* __restrict__ x, int x_ld, long long npix, int C, T* __restrict__ y, int y_ld) {
+  pdl_trigger();
+  pdl_wait();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= npix * C) return;
   const int c = (int)(idx % C);
@@ -75,6 +83,8 @@ __global__ void deinterleave_kernel(const T* __restrict__ x, int x_ld, long long
 
 template <typename T>
 __global__ void pack_input_kernel(const float* __restrict__ x, int B, int C, int H, int W, T* __restrict__ y, int y_ld, int Cpad) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)B * H * W;
   long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= total) return;
@@ -91,6 +101,8 @@ __global__ void pack_input_kernel(const float* __restrict__ x, int B, int C, int
 // 256 threads = 8 pixel lanes x 32 channel lanes looping over channel blocks.
 template <typename T>
 __global__ void global_avgpool_kernel(const T* __restrict__ x, int x_ld, int HW, int C, int chunk_pix, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float part[8][33];
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int p0 = chunk * chunk_pix, p1 = min(HW, p0 + chunk_pix);
@@ -118,6 +130,8 @@ __global__ void global_avgpool_kernel(const T* __restrict__ x, int x_ld, int HW,
 __global__ void channel_mlp_kernel(const float* __restrict__ in, int parts, float in_scale, int C0, const float* __restrict__ W1,
                                    const float* __restrict__ b1, int C1, int act1, const float* __restrict__ W2,
                                    const float* __restrict__ b2, int C2, int act2, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   float* v0 = sm;
   float* v1 = sm + C0;
@@ -149,6 +163,8 @@ __global__ void channel_mlp_kernel(const float* __restrict__ in, int parts, floa
 template <typename T>
 __global__ void cbam_stats_kernel(const T* __restrict__ x, int x_ld, int B, int HW, int C, int lpp, const float* __restrict__ ca,
                                   float* __restrict__ stats) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int V = Vec<T>::N;
   const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long gp = gt / lpp;
@@ -185,6 +201,8 @@ template <typename T>
 __global__ void cbam_apply_kernel(const T* __restrict__ x, int x_ld, int B, int H, int W, int C, int lpp, const float* __restrict__ ca,
                                   const float* __restrict__ stats, const float* __restrict__ w, int k,
                                   T* __restrict__ y, int y_ld) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int V = Vec<T>::N;
   const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long gp = gt / lpp;
@@ -248,8 +266,8 @@ extern "C" int lpc_upsample2x(int dtype, const void* x, int x_ld, int B, int H, 
   cudaStream_t s = (cudaStream_t)stream;
   const int V = dtype == LPC_F32 ? 4 : 8;
   const int g = cdiv((long long)B * H * W * (C / V), 256);
-  DISPATCH_T(dtype, (upsample2x_kernel<float><<<g, 256, 0, s>>>((const float*)x, x_ld, B, H, W, C, (float*)y, y_ld)),
-             (upsample2x_kernel<bf16><<<g, 256, 0, s>>>((const bf16*)x, x_ld, B, H, W, C, (bf16*)y, y_ld)), "upsample2x")
+  DISPATCH_T(dtype, (lpc_launch_pdl(upsample2x_kernel<float>, g, 256, 0, s, (const float*)x, x_ld, B, H, W, C, (float*)y, y_ld)),
+             (lpc_launch_pdl(upsample2x_kernel<bf16>, g, 256, 0, s, (const bf16*)x, x_ld, B, H, W, C, (bf16*)y, y_ld)), "upsample2x")
 }
 
 extern "C" int lpc_copy_channels(int dtype, const void* x, int x_ld, long long npix, int C, void* y, int y_ld, void* stream) {
@@ -257,8 +275,8 @@ extern "C" int lpc_copy_channels(int dtype, const void* x, int x_ld, long long n
   cudaStream_t s = (cudaStream_t)stream;
   const int V = dtype == LPC_F32 ? 4 : 8;
   const int g = cdiv(npix * (C / V), 256);
-  DISPATCH_T(dtype, (copy_channels_kernel<float><<<g, 256, 0, s>>>((const float*)x, x_ld, npix, C, (float*)y, y_ld)),
-             (copy_channels_kernel<bf16><<<g, 256, 0, s>>>((const bf16*)x, x_ld, npix, C, (bf16*)y, y_ld)), "copy_channels")
+  DISPATCH_T(dtype, (lpc_launch_pdl(copy_channels_kernel<float>, g, 256, 0, s, (const float*)x, x_ld, npix, C, (float*)y, y_ld)),
+             (lpc_launch_pdl(copy_channels_kernel<bf16>, g, 256, 0, s, (const bf16*)x, x_ld, npix, C, (bf16*)y, y_ld)), "copy_channels")
 }
 
 extern "C" int lpc_space_to_depth(int dtype, const void* x, int x_ld, int B, int H, int W, int C, void* y, int y_ld, void* stream) {
@@ -267,24 +285,24 @@ extern "C" int lpc_space_to_depth(int dtype, const void* x, int x_ld, int B, int
   cudaStream_t s = (cudaStream_t)stream;
   const int V = dtype == LPC_F32 ? 4 : 8;
   const int g = cdiv((long long)B * H * W * (C / V), 256);
-  DISPATCH_T(dtype, (space_to_depth_kernel<float><<<g, 256, 0, s>>>((const float*)x, x_ld, B, H, W, C, (float*)y, y_ld)),
-             (space_to_depth_kernel<bf16><<<g, 256, 0, s>>>((const bf16*)x, x_ld, B, H, W, C, (bf16*)y, y_ld)), "space_to_depth")
+  DISPATCH_T(dtype, (lpc_launch_pdl(space_to_depth_kernel<float>, g, 256, 0, s, (const float*)x, x_ld, B, H, W, C, (float*)y, y_ld)),
+             (lpc_launch_pdl(space_to_depth_kernel<bf16>, g, 256, 0, s, (const bf16*)x, x_ld, B, H, W, C, (bf16*)y, y_ld)), "space_to_depth")
 }
 
 extern "C" int lpc_channel_deinterleave(int dtype, const void* x, int x_ld, long long npix, int C, void* y, int y_ld, void* stream) {
   LPC_REQUIRE(x && y && C % 2 == 0 && x_ld >= C && y_ld >= C, "channel_deinterleave: bad argument");
   cudaStream_t s = (cudaStream_t)stream;
   const int g = cdiv(npix * C, 256);
-  DISPATCH_T(dtype, (deinterleave_kernel<float><<<g, 256, 0, s>>>((const float*)x, x_ld, npix, C, (float*)y, y_ld)),
-             (deinterleave_kernel<bf16><<<g, 256, 0, s>>>((const bf16*)x, x_ld, npix, C, (bf16*)y, y_ld)), "channel_deinterleave")
+  DISPATCH_T(dtype, (lpc_launch_pdl(deinterleave_kernel<float>, g, 256, 0, s, (const float*)x, x_ld, npix, C, (float*)y, y_ld)),
+             (lpc_launch_pdl(deinterleave_kernel<bf16>, g, 256, 0, s, (const bf16*)x, x_ld, npix, C, (bf16*)y, y_ld)), "channel_deinterleave")
 }
 
 extern "C" int lpc_pack_input(int dtype, const float* x, int B, int C, int H, int W, void* y, int y_ld, int Cpad, void* stream) {
   LPC_REQUIRE(x && y && C > 0 && Cpad >= C && y_ld >= Cpad, "pack_input: bad argument");
   cudaStream_t s = (cudaStream_t)stream;
   const int g = cdiv((long long)B * H * W, 256);
-  DISPATCH_T(dtype, (pack_input_kernel<float><<<g, 256, 0, s>>>(x, B, C, H, W, (float*)y, y_ld, Cpad)),
-             (pack_input_kernel<bf16><<<g, 256, 0, s>>>(x, B, C, H, W, (bf16*)y, y_ld, Cpad)), "pack_input")
+  DISPATCH_T(dtype, (lpc_launch_pdl(pack_input_kernel<float>, g, 256, 0, s, x, B, C, H, W, (float*)y, y_ld, Cpad)),
+             (lpc_launch_pdl(pack_input_kernel<bf16>, g, 256, 0, s, x, B, C, H, W, (bf16*)y, y_ld, Cpad)), "pack_input")
 }
 
 extern "C" int lpc_global_avgpool_chunks(int B, int HW) {
@@ -301,15 +319,15 @@ extern "C" int lpc_global_avgpool(int dtype, const void* x, int x_ld, int B, int
   const int chunks = lpc_global_avgpool_chunks(B, HW);
   const int chunk_pix = (HW + chunks - 1) / chunks;
   dim3 g(chunks, B);
-  DISPATCH_T(dtype, (global_avgpool_kernel<float><<<g, 256, 0, s>>>((const float*)x, x_ld, HW, C, chunk_pix, partial)),
-             (global_avgpool_kernel<bf16><<<g, 256, 0, s>>>((const bf16*)x, x_ld, HW, C, chunk_pix, partial)), "global_avgpool")
+  DISPATCH_T(dtype, (lpc_launch_pdl(global_avgpool_kernel<float>, g, 256, 0, s, (const float*)x, x_ld, HW, C, chunk_pix, partial)),
+             (lpc_launch_pdl(global_avgpool_kernel<bf16>, g, 256, 0, s, (const bf16*)x, x_ld, HW, C, chunk_pix, partial)), "global_avgpool")
 }
 
 extern "C" int lpc_channel_mlp(const float* in, int B, int parts, float in_scale, int C0, const float* W1, const float* b1, int C1,
                                int act1, const float* W2, const float* b2, int C2, int act2, float* out, void* stream) {
   LPC_REQUIRE(in && W1 && out && B > 0 && C0 > 0 && C1 > 0 && parts > 0, "channel_mlp: bad argument");
   LPC_REQUIRE((size_t)(C0 + C1) * 4 <= 48 * 1024, "channel_mlp: vectors too large");
-  channel_mlp_kernel<<<B, 256, (size_t)(C0 + C1) * 4, (cudaStream_t)stream>>>(in, parts, in_scale, C0, W1, b1, C1, act1, W2, b2, C2, act2, out);
+  lpc_launch_pdl(channel_mlp_kernel, B, 256, (size_t)(C0 + C1) * 4, (cudaStream_t)stream, in, parts, in_scale, C0, W1, b1, C1, act1, W2, b2, C2, act2, out);
   LPC_CHECK_LAUNCH("channel_mlp");
   return LPC_OK;
 }
@@ -327,8 +345,8 @@ extern "C" int lpc_cbam_stats(int dtype, const void* x, int x_ld, int B, int HW,
   cudaStream_t s = (cudaStream_t)stream;
   const int lpp = lanes_per_pixel(dtype, C);
   const int g = cdiv((long long)B * HW * lpp, 256);
-  DISPATCH_T(dtype, (cbam_stats_kernel<float><<<g, 256, 0, s>>>((const float*)x, x_ld, B, HW, C, lpp, ca, stats)),
-             (cbam_stats_kernel<bf16><<<g, 256, 0, s>>>((const bf16*)x, x_ld, B, HW, C, lpp, ca, stats)), "cbam_stats")
+  DISPATCH_T(dtype, (lpc_launch_pdl(cbam_stats_kernel<float>, g, 256, 0, s, (const float*)x, x_ld, B, HW, C, lpp, ca, stats)),
+             (lpc_launch_pdl(cbam_stats_kernel<bf16>, g, 256, 0, s, (const bf16*)x, x_ld, B, HW, C, lpp, ca, stats)), "cbam_stats")
 }
 
 extern "C" int lpc_cbam_apply(int dtype, const void* x, int x_ld, int B, int H, int W, int C, const float* ca,
@@ -338,6 +356,6 @@ extern "C" int lpc_cbam_apply(int dtype, const void* x, int x_ld, int B, int H, 
   cudaStream_t s = (cudaStream_t)stream;
   const int lpp = lanes_per_pixel(dtype, C);
   const int g = cdiv((long long)B * H * W * lpp, 256);
-  DISPATCH_T(dtype, (cbam_apply_kernel<float><<<g, 256, 0, s>>>((const float*)x, x_ld, B, H, W, C, lpp, ca, stats, w, k, (float*)y, y_ld)),
-             (cbam_apply_kernel<bf16><<<g, 256, 0, s>>>((const bf16*)x, x_ld, B, H, W, C, lpp, ca, stats, w, k, (bf16*)y, y_ld)), "cbam_apply")
+  DISPATCH_T(dtype, (lpc_launch_pdl(cbam_apply_kernel<float>, g, 256, 0, s, (const float*)x, x_ld, B, H, W, C, lpp, ca, stats, w, k, (float*)y, y_ld)),
+             (lpc_launch_pdl(cbam_apply_kernel<bf16>, g, 256, 0, s, (const bf16*)x, x_ld, B, H, W, C, lpp, ca, stats, w, k, (bf16*)y, y_ld)), "cbam_apply")
 }

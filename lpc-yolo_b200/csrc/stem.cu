@@ -30,6 +30,8 @@ template <typename T, int S>
 __global__ void __launch_bounds__(ST_NT)
 stem_conv_kernel(const T* __restrict__ x, int B, int H, int W, const float* __restrict__ w, const float* __restrict__ bias,
                  int Cout, int Ho, int Wo, T* __restrict__ y, int y_ld, int act) {
+  pdl_trigger();
+  pdl_wait();
   typedef typename In4<T>::V V;
   constexpr bool PR = Precise<T>::value;
   constexpr int IN_H = (ST_TH - 1) * S + 3, IN_W = (ST_TW - 1) * S + 3;
@@ -133,7 +135,7 @@ extern "C" int lpc_stem_conv(int dtype, const void* x, int B, int H, int W, cons
     const int r = lpc_stem_conv_tc(x, B, H, W, w, bias, Cout, y, y_ld, act, s);
     if (r != LPC_E_UNSUPPORTED) return r;
   }
-#define STEM(T_, S_) stem_conv_kernel<T_, S_><<<grid, ST_NT, 0, s>>>((const T_*)x, B, H, W, w, bias, Cout, Ho, Wo, (T_*)y, y_ld, act)
+#define STEM(T_, S_) lpc_launch_pdl(stem_conv_kernel<T_, S_>, grid, ST_NT, 0, s, (const T_*)x, B, H, W, w, bias, Cout, Ho, Wo, (T_*)y, y_ld, act)
   if (dtype == LPC_BF16) { if (stride == 2) STEM(bf16, 2); else STEM(bf16, 1); }
   else if (dtype == LPC_F32) { if (stride == 2) STEM(float, 2); else STEM(float, 1); }
   else LPC_FAIL(LPC_E_ARG, "stem_conv: unknown dtype %d", dtype);

@@ -114,6 +114,8 @@ stem_tc_kernel(const __grid_constant__ StemTcParams p) {
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
   const int per_img = p.tiles_x * p.tiles_y;
+  pdl_trigger();
+  pdl_wait();          // the prologue above read only weights / bias
 
   if (warp < 4) {
     // ===== builders =====
@@ -291,7 +293,7 @@ int lpc_stem_conv_tc(const void* x, int B, int H, int W, const float* w, const f
     cudaMemset(trace_buf, 0, 3 * 64 * 4 * 8);
     p.trace = trace_buf;
   }
-  kern<<<(unsigned)grid, SB_THREADS, smem, stream>>>(p);
+  lpc_launch_pdl(kern, (unsigned)grid, SB_THREADS, smem, stream, p);
   LPC_CHECK_LAUNCH("stem_conv_tc");
   if (dbg) {
     static int calls = 0;

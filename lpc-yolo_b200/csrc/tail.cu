@@ -52,6 +52,8 @@ __device__ __forceinline__ const T* anchor_row(const TailSrc& s, int b, int a) {
 template <typename T, bool VECTOR>
 __global__ void __launch_bounds__(256)
 amax_keys_kernel(TailSrc s, int B, uint32_t* __restrict__ amax) {
+  pdl_trigger();
+  pdl_wait();
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= (long long)B * s.A) return;
   const int b = (int)(gid / s.A), a = (int)(gid - (long long)b * s.A);
@@ -180,6 +182,8 @@ __global__ void __launch_bounds__(SEL_NT)
 select_decode_kernel(TailSrc s, int K, int sortn, const uint32_t* __restrict__ amax, int cache_cap_keys,
                      int img_h, int img_w, float* __restrict__ dets, int* __restrict__ anchor_idx,
                      float* __restrict__ boxes_out, float* __restrict__ scores_out, long long* __restrict__ labels_out) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) unsigned char dsm[];
   __shared__ SelShared sh;
   unsigned long long* sortbuf = reinterpret_cast<unsigned long long*>(dsm);      // [sortn]
@@ -287,6 +291,8 @@ select_decode_kernel(TailSrc s, int K, int sortn, const uint32_t* __restrict__ a
 template <typename T>
 __global__ void __launch_bounds__(128)
 decode_kernel(TailSrc s, int B, float* __restrict__ y) {
+  pdl_trigger();
+  pdl_wait();
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= (long long)B * s.A) return;
   const int b = (int)(gid / s.A), a = (int)(gid - (long long)b * s.A);
@@ -364,7 +370,7 @@ int launch_select(const TailSrc& s, int B, int K, const uint32_t* amax, int img_
   auto kern = select_decode_kernel<T, PASSES, MODE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) LPC_FAIL(LPC_E_CUDA, "select_decode: smem attribute: %s", cudaGetErrorString(e));
-  kern<<<B, SEL_NT, smem, st>>>(s, K, sortn, amax, cap, img_h, img_w, dets, aidx, boxes, scores, labels);
+  lpc_launch_pdl(kern, B, SEL_NT, smem, st, s, K, sortn, amax, cap, img_h, img_w, dets, aidx, boxes, scores, labels);
   LPC_CHECK_LAUNCH("select_decode");
   return LPC_OK;
 }
@@ -383,8 +389,8 @@ extern "C" int lpc_v10_decode(int dtype, const void* raw0, const void* raw1, con
   LPC_REQUIRE(y, "v10_decode: null output");
   cudaStream_t st = (cudaStream_t)stream;
   const int g = cdiv((long long)B * s.A, 128);
-  if (dtype == LPC_F32) decode_kernel<float><<<g, 128, 0, st>>>(s, B, y);
-  else if (dtype == LPC_BF16) decode_kernel<bf16><<<g, 128, 0, st>>>(s, B, y);
+  if (dtype == LPC_F32) lpc_launch_pdl(decode_kernel<float>, g, 128, 0, st, s, B, y);
+  else if (dtype == LPC_BF16) lpc_launch_pdl(decode_kernel<bf16>, g, 128, 0, st, s, B, y);
   else LPC_FAIL(LPC_E_ARG, "v10_decode: unknown dtype %d", dtype);
   LPC_CHECK_LAUNCH("v10_decode");
   return LPC_OK;
@@ -403,14 +409,14 @@ extern "C" int lpc_v10_decode_topk(int dtype, const void* raw0, const void* raw1
   const int g = cdiv((long long)B * s.A, 256);
   if (dtype == LPC_BF16) {
     const bool vec = (nc % 8 == 0) && (ld % 8 == 0) && aligned16(raw0) && aligned16(raw1) && aligned16(raw2);
-    if (vec) amax_keys_kernel<bf16, true><<<g, 256, 0, st>>>(s, B, amax);
-    else amax_keys_kernel<bf16, false><<<g, 256, 0, st>>>(s, B, amax);
+    if (vec) lpc_launch_pdl(amax_keys_kernel<bf16, true>, g, 256, 0, st, s, B, amax);
+    else lpc_launch_pdl(amax_keys_kernel<bf16, false>, g, 256, 0, st, s, B, amax);
     LPC_CHECK_LAUNCH("amax_keys");
     return launch_select<bf16, 2, 0>(s, B, K, amax, img_h, img_w, dets, anchor_idx, nullptr, nullptr, nullptr, st);
   } else if (dtype == LPC_F32) {
     const bool vec = (nc % 4 == 0) && (ld % 4 == 0) && aligned16(raw0) && aligned16(raw1) && aligned16(raw2);
-    if (vec) amax_keys_kernel<float, true><<<g, 256, 0, st>>>(s, B, amax);
-    else amax_keys_kernel<float, false><<<g, 256, 0, st>>>(s, B, amax);
+    if (vec) lpc_launch_pdl(amax_keys_kernel<float, true>, g, 256, 0, st, s, B, amax);
+    else lpc_launch_pdl(amax_keys_kernel<float, false>, g, 256, 0, st, s, B, amax);
     LPC_CHECK_LAUNCH("amax_keys");
     return launch_select<float, 4, 0>(s, B, K, amax, img_h, img_w, dets, anchor_idx, nullptr, nullptr, nullptr, st);
   }
@@ -431,7 +437,7 @@ extern "C" int lpc_v10_postprocess(const float* preds, long long stride_b, long 
   cudaStream_t st = (cudaStream_t)stream;
   uint32_t* amax = reinterpret_cast<uint32_t*>(workspace);
   const int g = cdiv((long long)B * A, 256);
-  amax_keys_kernel<float, false><<<g, 256, 0, st>>>(s, B, amax);
+  lpc_launch_pdl(amax_keys_kernel<float, false>, g, 256, 0, st, s, B, amax);
   LPC_CHECK_LAUNCH("amax_keys");
   return launch_select<float, 4, 1>(s, B, K, amax, 0, 0, nullptr, nullptr, boxes, scores, labels, st);
 }

@@ -144,6 +144,59 @@ __global__ void __launch_bounds__(64, 1) op_cost_kernel(unsigned long long* out)
   if (warp == 1) tmem_dealloc(tmem, 64);
 }
 
+// ---- cta_group::2: one instruction drives the tensor cores of a CTA pair (M = 256) ---------------------------
+// Does the ~70-cycle per-instruction floor of small-N MMAs halve per SM when one issue serves two SMs?
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64, 1) pair_bench_kernel(int n, int chain, int iters, unsigned long long* out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const uint32_t base = (smem_u32(smem) + 1023u) & ~1023u;
+  for (int i = threadIdx.x; i < 20 * 1024; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (rank == 0 && warp == 1 && elect_one_sync()) {
+    const uint32_t idesc = (make_idesc(n) & ~(0x1Fu << 24)) | ((256u >> 4) << 24);     // M = 256 across the pair
+    const uint32_t a_hi = desc_hi(1024u, 2u), b_hi = desc_hi(1024u, 2u);
+    const uint32_t a_lo = desc_lo(base, 16u), b_lo = desc_lo(base + 40 * 1024, 16u);
+    uint32_t ph = 0;
+    auto mma2 = [&](uint32_t acc, uint32_t k, uint32_t accumulate) {
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                   ::"r"(acc), "l"(desc64(a_lo + 2u * (k & 3), a_hi)), "l"(desc64(b_lo + 2u * (k & 3), b_hi)), "r"(idesc), "r"(accumulate) : "memory");
+    };
+    auto commit2 = [&]() {
+      asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "h"((unsigned short)1) : "memory");
+    };
+    for (int k = 0; k < 8; ++k) mma2(tmem, k, 0u);
+    commit2();
+    mbar_wait(smem_u32(&bar), ph); ph ^= 1;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      for (int k = 0; k < chain; ++k) mma2(tmem, (uint32_t)k, 1u);
+      commit2();
+      mbar_wait(smem_u32(&bar), ph); ph ^= 1;
+    }
+    const long long t1 = clock64();
+    if (blockIdx.x == 0) out[0] = (unsigned long long)(t1 - t0);
+  }
+  tc_fence_before();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+}
+
 int main() {
   unsigned long long* d;
   cudaMalloc(&d, 64);
@@ -198,6 +251,19 @@ int main() {
   // a single CTA on the chip (no neighbours)
   run({64, 1, 2, 0, 1024, 36, 50, 128, 0, 1, 0}, 1);
   run({256, 1, 2, 0, 1024, 36, 50, 128, 0, 1, 0}, 1);
+  {
+    cudaFuncSetAttribute(pair_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    for (int n : {32, 64, 128, 256}) {
+      cudaMemset(d, 0, 64);
+      pair_bench_kernel<<<sms / 2 * 2, 64, 100 * 1024>>>(n, 36, 50, d);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("pair bench error: %s\n", cudaGetErrorString(e)); return 1; }
+      unsigned long long h[1];
+      cudaMemcpy(h, d, 8, cudaMemcpyDeviceToHost);
+      printf("cta_group::2  M256 N%3d chain 36 | %10.1f cycles per MMA (covers 2 SMs; single-CTA floor 128*N/256 = %.0f)\n", n, h[0] / (36.0 * 50), 128.0 * n / 256.0);
+      fflush(stdout);
+    }
+  }
   {
     cudaFuncSetAttribute(op_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaMemset(d, 0, 64);
