@@ -118,6 +118,12 @@ int lpc_space_to_depth(int dtype, const void* x, int x_ld, int B, int H, int W, 
 int lpc_channel_deinterleave(int dtype, const void* x, int x_ld, long long npix, int C, void* y, int y_ld, void* stream);
 /* fp32 NCHW image batch -> NHWC view (channels c >= C zero filled up to Cpad). predictor.py:115-133. */
 int lpc_pack_input(int dtype, const float* x_nchw, int B, int C, int H, int W, void* y, int y_ld, int Cpad, void* stream);
+/* uint8 HWC image batch [B,Hs,Ws,3] (device) -> NHWC network input [B,H,W,4] (pixel pitch 4, channel 3 = 0), values / 255:
+ * the array-source preprocess (engine/predictor.py:115-133: BGR->RGB when swap_rb, BHWC->BCHW, float, /255) fused with
+ * LetterBox's constant border (data/augment.py:725-731): the image lands at (top, left), the rest is pad_value / 255.
+ * No resize (LetterBox ratio 1) in this round. */
+int lpc_pack_u8(int dtype, const void* src_u8, int B, int Hs, int Ws, int top, int left, int H, int W, int pad_value,
+                int swap_rb, void* y, void* stream);
 
 /* ---- CBAM / SPCA pooled gates (conv.py:278-320, block.py:5735-5747) */
 /* partial[b][chunk][c] = sum of x over the chunk's pixels, chunk count = lpc_global_avgpool_chunks(B, HW)

@@ -97,6 +97,47 @@ __global__ void pack_input_kernel(const float* __restrict__ x, int B, int C, int
   }
 }
 
+
+// uint8 HWC (cv2 / BGR) image batch -> NHWC network input with C padded to 4: the reference's preprocess for array sources
+// (engine/predictor.py:115-133: stack -> BGR->RGB -> BHWC->BCHW -> float -> /255) plus LetterBox's constant border
+// (data/augment.py:725-731, value 114) for the no-resize case, in ONE pass: the image is already NHWC, so the
+// reference's transpose disappears.  Thread = output pixel: 3 byte loads (a warp reads 96 contiguous bytes), one
+// 8-byte (bf16) / 16-byte (fp32) store.  v / 255 is an IEEE division: bit-identical to torch's `im /= 255` in fp32.
+template <typename T>
+__global__ void pack_u8_kernel(const unsigned char* __restrict__ src, int B, int Hs, int Ws, int top, int left, int H, int W,
+                               float pad, int swap_rb, T* __restrict__ y) {
+  pdl_trigger();
+  pdl_wait();
+  const long long total = (long long)B * H * W;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= total) return;
+  const int w = (int)(p % W);
+  const long long t = p / W;
+  const int h = (int)(t % H);
+  const int n = (int)(t / H);
+  const int sy = h - top, sx = w - left;
+  float c0 = pad, c1 = pad, c2 = pad;
+  if ((unsigned)sy < (unsigned)Hs && (unsigned)sx < (unsigned)Ws) {
+    const unsigned char* q = src + (((long long)n * Hs + sy) * Ws + sx) * 3;
+    const float a = (float)q[0], b = (float)q[1], c = (float)q[2];
+    c0 = swap_rb ? c : a;
+    c1 = b;
+    c2 = swap_rb ? a : c;
+  }
+  c0 = __fdiv_rn(c0, 255.0f);
+  c1 = __fdiv_rn(c1, 255.0f);
+  c2 = __fdiv_rn(c2, 255.0f);
+  if (sizeof(T) == 2) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(c0, c1), hi = __floats2bfloat162_rn(c2, 0.f);
+    uint2 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&lo);
+    o.y = *reinterpret_cast<const uint32_t*>(&hi);
+    reinterpret_cast<uint2*>(y)[p] = o;
+  } else {
+    reinterpret_cast<float4*>(y)[p] = make_float4(c0, c1, c2, 0.f);
+  }
+}
+
 // partial[b, chunk, c] = sum over the chunk's pixels (fixed order: deterministic, no atomics).  grid (chunks, B);
 // 256 threads = 8 pixel lanes x 32 channel lanes looping over channel blocks.
 template <typename T>
@@ -303,6 +344,18 @@ extern "C" int lpc_pack_input(int dtype, const float* x, int B, int C, int H, in
   const int g = cdiv((long long)B * H * W, 256);
   DISPATCH_T(dtype, (lpc_launch_pdl(pack_input_kernel<float>, g, 256, 0, s, x, B, C, H, W, (float*)y, y_ld, Cpad)),
              (lpc_launch_pdl(pack_input_kernel<bf16>, g, 256, 0, s, x, B, C, H, W, (bf16*)y, y_ld, Cpad)), "pack_input")
+}
+
+extern "C" int lpc_pack_u8(int dtype, const void* src, int B, int Hs, int Ws, int top, int left, int H, int W, int pad_value,
+                           int swap_rb, void* y, void* stream) {
+  LPC_REQUIRE(src && y && B > 0 && Hs > 0 && Ws > 0 && H >= Hs && W >= Ws, "pack_u8: bad argument");
+  LPC_REQUIRE(top >= 0 && left >= 0 && top + Hs <= H && left + Ws <= W, "pack_u8: the image does not fit at (%d, %d)", top, left);
+  LPC_REQUIRE(pad_value >= 0 && pad_value <= 255, "pack_u8: pad value must be a byte");
+  LPC_REQUIRE(aligned16(y), "pack_u8: output must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int g = cdiv((long long)B * H * W, 256);
+  DISPATCH_T(dtype, (lpc_launch_pdl(pack_u8_kernel<float>, g, 256, 0, s, (const unsigned char*)src, B, Hs, Ws, top, left, H, W, (float)pad_value, swap_rb, (float*)y)),
+             (lpc_launch_pdl(pack_u8_kernel<bf16>, g, 256, 0, s, (const unsigned char*)src, B, Hs, Ws, top, left, H, W, (float)pad_value, swap_rb, (bf16*)y)), "pack_u8")
 }
 
 extern "C" int lpc_global_avgpool_chunks(int B, int HW) {

@@ -204,6 +204,112 @@ class YOLOv10DetectionPredictor:
             done.append(d)
         return preds
 
+    # ---- array sources: uint8 HWC (cv2 / BGR) images, SURVEY.md section 8(f) row 1 ------------------------------
+    @staticmethod
+    def letterbox_geometry(shape, imgsz, stride=32, auto=True):
+        """data/augment.py:700-731 LetterBox for one image shape (h, w): -> (H, W, top, left) of the network input.
+        Only ratio 1 (no resize) is implemented; the resize path is listed under "next" in DESIGN.md."""
+        new_shape = (imgsz, imgsz) if isinstance(imgsz, int) else tuple(imgsz)
+        r = min(new_shape[0] / shape[0], new_shape[1] / shape[1])
+        if r != 1.0:
+            raise NotImplementedError(f"LetterBox resize (ratio {r:.4f}) is not implemented: pass images whose longer side is imgsz")
+        new_unpad = int(round(shape[1] * r)), int(round(shape[0] * r))
+        dw, dh = new_shape[1] - new_unpad[0], new_shape[0] - new_unpad[1]
+        if auto:                                    # minimum rectangle (:716-717)
+            dw, dh = dw % stride, dh % stride
+        dw, dh = dw / 2, dh / 2                     # center=True (:723-725)
+        top, bottom = int(round(dh - 0.1)), int(round(dh + 0.1))
+        left, right = int(round(dw - 0.1)), int(round(dw + 0.1))
+        return shape[0] + top + bottom, shape[1] + left + right, top, left
+
+    class _GraphedU8:
+        """Two CUDA graphs of pack_u8 + ``model.detect`` on two static uint8 input buffers."""
+
+        def __init__(self, model, cb, hs, ws, geom, max_det):
+            dev = next(model.parameters()).device
+            H, W, top, left = geom
+            self.inp = [torch.full((cb, hs, ws, 3), 114, dtype=torch.uint8, device=dev) for _ in range(2)]
+            self.net = [torch.empty((cb, H, W, 4), dtype=model.compute_dtype, device=dev) for _ in range(2)]
+
+            def run(i):
+                x = F.pack_u8(self.inp[i], model.compute_dtype, top, left, H, W, 114, True, out=self.net[i])
+                return model.detect(x, max_det, clip=True)
+
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    run(0)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            self.graphs, self.outs = [], []
+            for i in range(2):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    out = run(i)
+                self.graphs.append(g)
+                self.outs.append(out)
+
+    def inference_from_host_u8(self, im_host):
+        """[B,h,w,3] uint8 host tensor (BGR) -> [B,K,6] on the device, in network-input coordinates.  Same chunked
+        copy / replay overlap as ``inference_from_host``; the H2D copy moves 3 bytes per pixel instead of 12."""
+        B, hs, ws, _ = im_host.shape
+        geom = self.letterbox_geometry((hs, ws), self.args.imgsz, int(max(self.model.stride)), auto=True)
+        n = 4 if B % 4 == 0 and B >= 16 else (2 if B % 2 == 0 and B >= 4 else 1)
+        cb = B // n
+        key = ("u8", cb, hs, ws, geom, self.args.max_det, self.model.compute_dtype)
+        cache = self.__dict__.setdefault("_graphed", {})
+        if key not in cache:
+            cache[key] = self._GraphedU8(self.model, cb, hs, ws, geom, self.args.max_det)
+        gd = cache[key]
+        if not im_host.is_pinned():
+            im_host = im_host.pin_memory()
+        cur = torch.cuda.current_stream(self.device)
+        cs = self.__dict__.setdefault("_copy_stream", torch.cuda.Stream(device=self.device))
+        cs.wait_stream(cur)
+        preds = torch.empty((B, self.args.max_det, 6), dtype=torch.float32, device=self.device)
+        done = []
+        for i in range(n):
+            b = i & 1
+            ev = torch.cuda.Event()
+            with torch.cuda.stream(cs):
+                if i >= 2:
+                    cs.wait_event(done[i - 2])
+                gd.inp[b].copy_(im_host[i * cb:(i + 1) * cb], non_blocking=True)
+                ev.record(cs)
+            cur.wait_event(ev)
+            gd.graphs[b].replay()
+            preds[i * cb:(i + 1) * cb].copy_(gd.outs[b])
+            d = torch.cuda.Event()
+            d.record(cur)
+            done.append(d)
+        self._pad = (geom[2], geom[3], hs, ws)
+        return preds
+
+    @staticmethod
+    def as_u8_batch(source):
+        """list of [h,w,3] uint8 arrays (one shape) / one [B,h,w,3] array / uint8 BHWC host tensor -> host tensor."""
+        if isinstance(source, (list, tuple)):
+            if len({tuple(a.shape) for a in source}) != 1:
+                raise NotImplementedError("array sources of different shapes are not batched in this round")
+            source = np.stack(source)
+        if isinstance(source, np.ndarray):
+            if source.ndim == 3:
+                source = source[None]
+            source = torch.from_numpy(np.ascontiguousarray(source))
+        if not (torch.is_tensor(source) and source.dtype == torch.uint8 and source.dim() == 4 and source.shape[3] == 3):
+            raise ValueError(f"array sources must be uint8 HWC images, got {getattr(source, 'dtype', type(source))} {tuple(getattr(source, 'shape', ()))}")
+        return source.contiguous()
+
+    def scale_back(self, preds):
+        """utils/ops.py:89-124 scale_boxes / :305-324 clip_boxes for gain 1: subtract the LetterBox pad, clip to the image."""
+        top, left, hs, ws = self._pad
+        if top == 0 and left == 0:
+            return preds
+        preds = preds.clone()
+        preds[..., [0, 2]] = (preds[..., [0, 2]] - left).clamp_(0, ws)
+        preds[..., [1, 3]] = (preds[..., [1, 3]] - top).clamp_(0, hs)
+        return preds
+
     def postprocess(self, preds, img, orig_imgs):
         """models/yolov10/predict.py:22-38: confidence / class filter, wrap in Results.  preds are already
         [B,K,6] xyxy (the export-mode contract, head.py:521-523), clipped to the image (scale_boxes is the
@@ -228,7 +334,15 @@ class YOLOv10DetectionPredictor:
         self.batch = source
         self.run_callbacks("on_predict_batch_start")
         with torch.no_grad():
-            if torch.is_tensor(source) and not source.is_cuda and source.dtype == torch.float32 and source.dim() == 4:
+            if not torch.is_tensor(source) or source.dtype == torch.uint8:
+                with profilers[0]:
+                    im = self.as_u8_batch(source)
+                with profilers[1]:
+                    preds = self.scale_back(self.inference_from_host_u8(im))
+                orig = list(source) if isinstance(source, (list, tuple)) else [a for a in (source if not torch.is_tensor(source) else source.numpy())]
+                with profilers[2]:
+                    self.results = self.postprocess(preds, im, orig)
+            elif torch.is_tensor(source) and not source.is_cuda and source.dtype == torch.float32 and source.dim() == 4:
                 with profilers[0]:
                     im = check_tensor_source(source)
                 with profilers[1]:
@@ -238,8 +352,9 @@ class YOLOv10DetectionPredictor:
                     im = self.preprocess(source)
                 with profilers[1]:
                     preds = self.inference(im)
-            with profilers[2]:
-                self.results = self.postprocess(preds, im, im)
+            if torch.is_tensor(source) and source.dtype != torch.uint8:
+                with profilers[2]:
+                    self.results = self.postprocess(preds, im, im)
         self.run_callbacks("on_predict_postprocess_end")
         n = len(self.results)
         for r in self.results:
@@ -284,8 +399,9 @@ class YOLO:
         unknown = set(kwargs) - set(DEFAULTS)
         if unknown:  # cfg/__init__.py:302-325 check_dict_alignment raises SyntaxError on unknown keys
             raise SyntaxError(f"'{sorted(unknown)}' are not valid predict() arguments")
-        if not torch.is_tensor(source):
-            raise NotImplementedError("this round handles torch.Tensor sources [B,3,H,W] in [0,1] (LoadTensor contract)")
+        if not torch.is_tensor(source) and not isinstance(source, (np.ndarray, list, tuple)):
+            raise NotImplementedError("sources: torch.Tensor [B,3,H,W] in [0,1] (LoadTensor contract) or uint8 HWC BGR arrays "
+                                      "(LoadPilAndNumpy contract); files / streams are out of scope")
         args = {**self.overrides, **kwargs}
         if self.predictor is None or args != getattr(self, "_last_args", None):
             self.predictor = (predictor or YOLOv10DetectionPredictor)(overrides=args, _callbacks=self.callbacks)

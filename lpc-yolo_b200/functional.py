@@ -17,6 +17,10 @@ _DT = {torch.bfloat16: BF16, torch.float32: F32}
 # Optional per-launch profiling (bench.py): when PROFILE is a list, every op appends
 # (kind, start_event, end_event, algorithmic_flops, algorithmic_bytes, shape tag).
 PROFILE = None
+# Optional launch recording (bench.py): when REPLAY is a list, the tcgen05 conv and fused-tail ops append
+# (kind, closure, algorithmic_flops, algorithmic_bytes, tag); calling a closure re-issues exactly that launch (same
+# pointers), so bench.py can capture e.g. all dense-conv launches of one step into a CUDA graph and time them back to back.
+REPLAY = None
 
 
 class _prof:
@@ -121,6 +125,21 @@ def pack_input(x, dtype, cpad=4):
     return buf.permute(0, 3, 1, 2)[:, :Cc]
 
 
+@_profiled
+def pack_u8(src, dtype, top=0, left=0, H=None, W=None, pad_value=114, swap_rb=True, out=None):
+    """uint8 HWC images [B,Hs,Ws,3] on the device -> NHWC network input (logical [B,3,H,W]), /255, BGR->RGB,
+    LetterBox border (no resize).  ``out``: an optional [B,H,W,4] buffer of ``dtype`` (CUDA-graph static input)."""
+    if not src.is_cuda:
+        raise LpcError("lpc-yolo_b200 ops run on CUDA tensors only (there is no CPU fallback)")
+    assert src.dtype == torch.uint8 and src.dim() == 4 and src.shape[3] == 3 and src.is_contiguous()
+    B, Hs, Ws, _ = src.shape
+    H, W = H or Hs, W or Ws
+    buf = out if out is not None else torch.empty((B, H, W, 4), dtype=dtype, device=src.device)
+    assert buf.shape == (B, H, W, 4) and buf.dtype == dtype and buf.is_contiguous()
+    check(_lib.lib().lpc_pack_u8(dt_code(dtype), _fp(src), B, Hs, Ws, top, left, H, W, pad_value, int(swap_rb), _fp(buf), _stream()), "pack_u8")
+    return buf.permute(0, 3, 1, 2)[:, :3]
+
+
 def conv2d(x, pc, out=None, res=None, chan_scale=None):
     """Dense conv through a PackedConv ``pc`` (see pack.py). Chooses tcgen05 when the shape allows."""
     B, Cin, H, W = x.shape
@@ -146,9 +165,13 @@ def conv2d(x, pc, out=None, res=None, chan_scale=None):
     nbytes = x.element_size() * (B * H * W * Cin + B * Ho * Wo * pc.cout * (2 if res is not None else 1) + pc.cout * Cin * pc.k * pc.k)
     tag = f"{Cin}->{pc.cout} k{pc.k}s{pc.s} {H}x{W} B{B}"
     if use_tc:
-        with _prof("conv2d_tc", flops, nbytes, tag):
+        def launch(keep=(x, out, res, chan_scale, pc)):
             check(L.lpc_conv2d_tc(xp, xld, B, H, W, Cin, _fp(pc.w_tc), _fp(pc.bias), pc.k, pc.s, pc.p, pc.cout, yp, yld,
                                   pc.act, _fp(chan_scale), rp or None, rld, _stream()), "conv2d_tc")
+        if REPLAY is not None:
+            REPLAY.append(("conv2d_tc", launch, flops, nbytes, tag))
+        with _prof("conv2d_tc", flops, nbytes, tag):
+            launch()
     else:
         with _prof("conv2d_direct", flops, nbytes, tag):
             check(L.lpc_conv2d_direct(dt_code(x.dtype), xp, xld, B, H, W, Cin, _fp(pc.w_direct), _fp(pc.bias), pc.k, pc.s,
@@ -325,9 +348,13 @@ def v10_decode_topk(raw, strides, nc, max_det=300, img_hw=None, return_index=Fal
     ih, iw = (img_hw if img_hw is not None else (0, 0))
     # algorithmic bytes: raw maps read once + detections written
     nbytes = B * A * (64 + nc) * raw[0].element_size() + B * max_det * 6 * 4
-    with _prof("v10_decode_topk", 0.0, nbytes):
+    def launch(keep=(raw, ws, dets, aidx)):
         check(L.lpc_v10_decode_topk(dt_code(raw[0].dtype), ptrs[0], ptrs[1], ptrs[2], ld, B, H0, W0, nc, st, max_det, ih, iw,
                                     _fp(ws), ws_bytes, _fp(dets), _fp(aidx), _stream()), "v10_decode_topk")
+    if REPLAY is not None:
+        REPLAY.append(("v10_decode_topk", launch, 0.0, nbytes, ""))
+    with _prof("v10_decode_topk", 0.0, nbytes):
+        launch()
     return (dets, aidx) if return_index else dets
 
 

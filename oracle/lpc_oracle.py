@@ -640,3 +640,51 @@ def build(name: str, seed: int = 0, calibrate: bool = True, nc: Optional[int] = 
 def synth_input(batch: int, size: int, seed: int = 1) -> torch.Tensor:
     g = torch.Generator().manual_seed(seed)
     return torch.rand(batch, 3, size, size, generator=g)
+
+
+# ---- array-source preprocessing ---------------------------------------------------
+def letterbox(img, new_shape=(640, 640), auto=False, stride=32):
+    """data/augment.py:684-742 LetterBox.__call__ for one HWC uint8 image (scaleFill=False, scaleup=True, center=True).
+    Returns (image, (top, left)).  The resize branch calls cv2.resize exactly as the reference does (:727)."""
+    import numpy as np
+    shape = img.shape[:2]
+    if isinstance(new_shape, int):
+        new_shape = (new_shape, new_shape)
+    r = min(new_shape[0] / shape[0], new_shape[1] / shape[1])
+    new_unpad = int(round(shape[1] * r)), int(round(shape[0] * r))
+    dw, dh = new_shape[1] - new_unpad[0], new_shape[0] - new_unpad[1]
+    if auto:
+        dw, dh = np.mod(dw, stride), np.mod(dh, stride)
+    dw /= 2
+    dh /= 2
+    if shape[::-1] != new_unpad:
+        import cv2
+        img = cv2.resize(img, new_unpad, interpolation=cv2.INTER_LINEAR)
+    top, bottom = int(round(dh - 0.1)), int(round(dh + 0.1))
+    left, right = int(round(dw - 0.1)), int(round(dw + 0.1))
+    img = np.pad(img, ((top, bottom), (left, right), (0, 0)), mode="constant", constant_values=114)   # cv2.copyMakeBorder :729-731
+    return img, (top, left)
+
+
+def preprocess_arrays(ims, imgsz=640, stride=32, pt=True):
+    """engine/predictor.py:115-133 + :145-156 for a list of HWC uint8 BGR arrays: LetterBox each (auto = all shapes equal
+    and a PyTorch model), stack, BGR->RGB, BHWC->BCHW, float32, /255.  Returns (x[B,3,H,W] float32, (top, left))."""
+    import numpy as np
+    same = len({x.shape for x in ims}) == 1
+    outs = [letterbox(x, imgsz, auto=same and pt, stride=stride) for x in ims]
+    im = np.stack([o[0] for o in outs])
+    im = np.ascontiguousarray(im[..., ::-1].transpose((0, 3, 1, 2)))
+    x = torch.from_numpy(im).float()
+    x /= 255
+    return x, outs[0][1]
+
+
+def scale_boxes_unit_gain(boxes, pad_top_left, orig_hw):
+    """utils/ops.py:89-124 scale_boxes with gain 1 (+ clip_boxes :305-324): boxes [...,4] xyxy in network coordinates."""
+    top, left = pad_top_left
+    b = boxes.clone()
+    b[..., [0, 2]] -= left
+    b[..., [1, 3]] -= top
+    b[..., [0, 2]] = b[..., [0, 2]].clamp(0, orig_hw[1])
+    b[..., [1, 3]] = b[..., [1, 3]].clamp(0, orig_hw[0])
+    return b
