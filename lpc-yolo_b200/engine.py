@@ -129,7 +129,9 @@ class YOLOv10DetectionPredictor:
         """predictor.py:295-310 / autobackend.py:141-151: move, 'fuse' (pack), pick the compute dtype.
         ``half=True`` selects bf16 (the reference's switch means fp16; it has no bf16 switch)."""
         dev = self.args.device
-        self.device = torch.device(dev if dev is not None else "cuda:0") if not isinstance(dev, torch.device) else dev
+        if dev is None:            # the process's current CUDA device (one process per GPU under torchrun)
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(dev) if not isinstance(dev, torch.device) else dev
         if self.device.type != "cuda":
             raise F.LpcError("lpc-yolo_b200 predicts on CUDA devices only (no CPU fallback)")
         self.model = model.to(self.device).eval()
