@@ -237,49 +237,63 @@ __global__ void cbam_stats_kernel(const T* __restrict__ x, int x_ld, int B, int 
   }
 }
 
-// same mapping: gate = sigmoid(conv_kxk(stats)) computed cooperatively by the pixel's lanes; y = x*ca*gate
+// gate = sigmoid(conv_kxk([mean_c, max_c])) ; y = x * ca * gate (conv.py:300-320).  CTA = one 16 x 16 pixel tile of one
+// image: the stats halo ((16+k-1)^2 float2), the 2*k*k filter taps and ca[b][:] are staged in shared memory, each
+// thread computes the gate of one pixel (2*k*k FMAs on shared memory), then the 256 threads stream the tile's channel
+// vectors (16-byte loads / stores).  The earlier version split the taps over the lanes of a pixel with scattered 8-byte
+// global loads and was 5x above its HBM floor (profiles/r01_j_per_launch_lpc_b64.csv).
+constexpr int CB_T = 16;
 template <typename T>
-__global__ void cbam_apply_kernel(const T* __restrict__ x, int x_ld, int B, int H, int W, int C, int lpp, const float* __restrict__ ca,
-                                  const float* __restrict__ stats, const float* __restrict__ w, int k,
-                                  T* __restrict__ y, int y_ld) {
+__global__ void __launch_bounds__(CB_T * CB_T)
+cbam_apply_kernel(const T* __restrict__ x, int x_ld, int H, int W, int C, const float* __restrict__ ca,
+                  const float* __restrict__ stats, const float* __restrict__ w, int k, T* __restrict__ y, int y_ld) {
   pdl_trigger();
   pdl_wait();
   constexpr int V = Vec<T>::N;
-  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long gp = gt / lpp;
-  const int sub = (int)(gt - gp * lpp);
-  const long long HW = (long long)H * W;
-  const bool live = gp < (long long)B * HW;
-  float s = 0.f;
-  int b = 0;
-  if (live) {
-    b = (int)(gp / HW);
-    const int r = (int)(gp - (long long)b * HW);
-    const int oy = r / W, ox = r - oy * W;
-    const int pad = k / 2;
-    for (int t = sub; t < k * k; t += lpp) {
-      const int ky = t / k, kx = t - ky * k;
-      const int iy = oy - pad + ky, ix = ox - pad + kx;
-      if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
-      const float2 st = __ldg(reinterpret_cast<const float2*>(stats) + (long long)b * HW + (long long)iy * W + ix);
-      s = fmaf(st.x, __ldg(w + t), s);
-      s = fmaf(st.y, __ldg(w + k * k + t), s);
-    }
+  extern __shared__ float cb_sm[];
+  const int pad = k / 2, hw = CB_T + k - 1;
+  float2* st = reinterpret_cast<float2*>(cb_sm);          // [hw][hw]
+  float* wsm = cb_sm + 2 * hw * hw;                        // [2][k*k]
+  float* casm = wsm + 2 * k * k;                           // [C]
+  float* gate = casm + C;                                  // [256]
+  const int b = blockIdx.z, y0 = blockIdx.y * CB_T, x0 = blockIdx.x * CB_T;
+  const int tid = threadIdx.x;
+  const float2* sb = reinterpret_cast<const float2*>(stats) + (long long)b * H * W;
+  for (int i = tid; i < hw * hw; i += CB_T * CB_T) {
+    const int r = i / hw, c = i - r * hw;
+    const int iy = y0 - pad + r, ix = x0 - pad + c;
+    st[i] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(sb + (long long)iy * W + ix) : make_float2(0.f, 0.f);
   }
-  for (int o = lpp >> 1; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (!live) return;
-  const float gate = sigmoid_<true>(s);
-  const T* px = x + gp * x_ld;
-  T* py = y + gp * y_ld;
-  const float* cab = ca + (long long)b * C;
-  for (int c = sub * V; c < C; c += lpp * V) {
+  for (int i = tid; i < 2 * k * k; i += CB_T * CB_T) wsm[i] = w[i];
+  for (int i = tid; i < C; i += CB_T * CB_T) casm[i] = ca[(long long)b * C + i];
+  __syncthreads();
+  {
+    const int ty = tid / CB_T, tx = tid - ty * CB_T;
+    float s = 0.f;
+    for (int ky = 0; ky < k; ++ky)
+      for (int kx = 0; kx < k; ++kx) {
+        const float2 v = st[(ty + ky) * hw + tx + kx];
+        s = fmaf(v.x, wsm[ky * k + kx], s);
+        s = fmaf(v.y, wsm[k * k + ky * k + kx], s);
+      }
+    gate[tid] = sigmoid_<true>(s);
+  }
+  __syncthreads();
+  const int cvecs = C / V;
+  for (int i = tid; i < CB_T * CB_T * cvecs; i += CB_T * CB_T) {
+    const int pix = i / cvecs, cv = i - pix * cvecs;
+    const int ty = pix / CB_T, tx = pix - ty * CB_T;
+    const int oy = y0 + ty, ox = x0 + tx;
+    if (oy >= H || ox >= W) continue;
+    const long long gp = ((long long)b * H + oy) * W + ox;
     float f[V];
-    ldg_vec<T>(px + c).unpack(f);
+    ldg_vec<T>(x + gp * x_ld + cv * V).unpack(f);
+    const float g = gate[pix];
 #pragma unroll
-    for (int v = 0; v < V; ++v) f[v] *= __ldg(cab + c + v) * gate;
+    for (int v = 0; v < V; ++v) f[v] *= casm[cv * V + v] * g;
     Vec<T> o;
     o.pack(f);
-    st_vec<T>(py + c, o);
+    st_vec<T>(y + gp * y_ld + cv * V, o);
   }
 }
 
@@ -407,8 +421,11 @@ extern "C" int lpc_cbam_apply(int dtype, const void* x, int x_ld, int B, int H, 
   LPC_REQUIRE(x && ca && stats && w && y && (k == 3 || k == 7), "cbam_apply: bad argument");
   if (int e = check_vec("cbam_apply", dtype, C, x_ld, y_ld, x, y)) return e;
   cudaStream_t s = (cudaStream_t)stream;
-  const int lpp = lanes_per_pixel(dtype, C);
-  const int g = cdiv((long long)B * H * W * lpp, 256);
-  DISPATCH_T(dtype, (lpc_launch_pdl(cbam_apply_kernel<float>, g, 256, 0, s, (const float*)x, x_ld, B, H, W, C, lpp, ca, stats, w, k, (float*)y, y_ld)),
-             (lpc_launch_pdl(cbam_apply_kernel<bf16>, g, 256, 0, s, (const bf16*)x, x_ld, B, H, W, C, lpp, ca, stats, w, k, (bf16*)y, y_ld)), "cbam_apply")
+  dim3 g(cdiv(W, CB_T), cdiv(H, CB_T), B);
+  LPC_REQUIRE(B <= 65535 && cdiv(H, CB_T) <= 65535, "cbam_apply: shape too large");
+  const int hw = CB_T + k - 1;
+  const size_t smem = sizeof(float) * (size_t)(2 * hw * hw + 2 * k * k + C + CB_T * CB_T);
+  LPC_REQUIRE(smem <= 48 * 1024, "cbam_apply: C too large for the shared-memory gate kernel");
+  DISPATCH_T(dtype, (lpc_launch_pdl(cbam_apply_kernel<float>, g, CB_T * CB_T, smem, s, (const float*)x, x_ld, H, W, C, ca, stats, w, k, (float*)y, y_ld)),
+             (lpc_launch_pdl(cbam_apply_kernel<bf16>, g, CB_T * CB_T, smem, s, (const bf16*)x, x_ld, H, W, C, ca, stats, w, k, (bf16*)y, y_ld)), "cbam_apply")
 }
