@@ -48,29 +48,44 @@ __device__ __forceinline__ const T* anchor_row(const TailSrc& s, int b, int a) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// kernel 1: per-anchor max key.  One thread per anchor; VECTOR path uses 16-byte loads along classes.
+// kernel 1: per-anchor max key.  VECTOR: 4 lanes share one anchor, lane j loads every 4th 16-byte class vector (an
+// anchor's classes are one contiguous run: a warp-wide load covers 8 anchors x 64 B instead of 32 distinct
+// lines when every thread walks its own row), then a 2-step shuffle max (16 lanes per anchor was slower: 4x the thread instructions).  Scalar path: one thread
+// per anchor (strided class layouts of lpc_v10_postprocess).
 template <typename T, bool VECTOR>
 __global__ void __launch_bounds__(256)
 amax_keys_kernel(TailSrc s, int B, uint32_t* __restrict__ amax) {
   pdl_trigger();
   pdl_wait();
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= (long long)B * s.A) return;
-  const int b = (int)(gid / s.A), a = (int)(gid - (long long)b * s.A);
-  const T* row = anchor_row<T>(s, b, a) + s.c_off;
-  float m = -INFINITY;
   if (VECTOR) {
-    constexpr int V = Vec<T>::N;
-    for (int c = 0; c < s.nc; c += V) {
-      float f[V];
-      ldg_vec<T>(row + c).unpack(f);
+    constexpr int V = Vec<T>::N, LPA = 4;
+    const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long gid = gt / LPA;                 // anchor (the grid is sized so that whole lane groups are in or out)
+    const int sub = (int)(gt & (LPA - 1));
+    const bool live = gid < (long long)B * s.A;
+    float m = -INFINITY;
+    if (live) {
+      const int b = (int)(gid / s.A), a = (int)(gid - (long long)b * s.A);
+      const T* row = anchor_row<T>(s, b, a) + s.c_off;
+      for (int c = sub * V; c < s.nc; c += LPA * V) {
+        float f[V];
+        ldg_vec<T>(row + c).unpack(f);
 #pragma unroll
-      for (int v = 0; v < V; ++v) m = fmaxf(m, f[v]);
+        for (int v = 0; v < V; ++v) m = fmaxf(m, f[v]);
+      }
     }
+#pragma unroll
+    for (int o = LPA / 2; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (live && sub == 0) amax[gid] = fkey(m);
   } else {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)B * s.A) return;
+    const int b = (int)(gid / s.A), a = (int)(gid - (long long)b * s.A);
+    const T* row = anchor_row<T>(s, b, a) + s.c_off;
+    float m = -INFINITY;
     for (int c = 0; c < s.nc; ++c) m = fmaxf(m, to_f(row[(long long)c * s.sc]));
+    amax[gid] = fkey(m);
   }
-  amax[gid] = fkey(m);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -84,9 +99,11 @@ struct SelShared {
 
 // Radix select over n keys provided by key(i).  On return: elements with (key >> kshift) > sh.prefix are
 // all winners; the first sh.need elements (in index order) with (key >> kshift) == sh.prefix complete K.
+// Three block barriers per pass: the 256-bin suffix scan and the digit search run inside warp 0 (8 bins per lane +
+// shuffles) instead of a 16-barrier Hillis-Steele scan over shared memory.
 template <int PASSES, typename KeyFn>
 __device__ void radix_select(SelShared& sh, int n, int K, KeyFn key) {
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
   if (tid == 0) { sh.prefix = 0; sh.need = (uint32_t)K; }
   for (int pass = 0; pass < PASSES; ++pass) {
     if (tid < 256) sh.hist[tid] = 0;
@@ -98,29 +115,33 @@ __device__ void radix_select(SelShared& sh, int n, int K, KeyFn key) {
       if (pass == 0 || (k >> (shift + 8)) == prefix) atomicAdd(&sh.hist[(k >> shift) & 255u], 1u);
     }
     __syncthreads();
-    // suffix sums cum[t] = sum_{i>=t} hist[i]  (Hillis-Steele over 256 bins)
-    if (tid < 256) sh.cum[tid] = sh.hist[tid];
-    __syncthreads();
-    for (int off = 1; off < 256; off <<= 1) {
-      uint32_t v = 0;
-      if (tid < 256 && tid + off < 256) v = sh.cum[tid + off];
-      __syncthreads();
-      if (tid < 256) sh.cum[tid] += v;
-      __syncthreads();
+    if (tid < 32) {
+      uint32_t h[8], tot = 0;                      // h[j] = sum of this lane's bins j..7
+#pragma unroll
+      for (int j = 7; j >= 0; --j) { tot += sh.hist[8 * lane + j]; h[j] = tot; }
+      uint32_t incl = tot;                         // -> sum of the lane totals of lanes >= lane
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t v = __shfl_down_sync(0xffffffffu, incl, off);
+        if (lane + off < 32) incl += v;
+      }
+      const uint32_t above_lane = incl - tot, need = sh.need;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t cum = h[j] + above_lane, above = (j == 7 ? 0u : h[j + 1]) + above_lane;
+        if (cum >= need && above < need) { sh.digit = (uint32_t)(8 * lane + j); sh.gt_count = above; }
+      }
+      __syncwarp();
+      if (lane == 0) { sh.prefix = (sh.prefix << 8) | sh.digit; sh.need -= sh.gt_count; }
     }
-    if (tid < 256) {
-      const uint32_t need = sh.need;
-      const uint32_t above = (tid == 255) ? 0u : sh.cum[tid + 1];
-      if (sh.cum[tid] >= need && above < need) { sh.digit = (uint32_t)tid; sh.gt_count = above; }
-    }
-    __syncthreads();
-    if (tid == 0) { sh.prefix = (sh.prefix << 8) | sh.digit; sh.need -= sh.gt_count; }
     __syncthreads();
   }
 }
 
-// Collect winners of a finished radix_select: emit(i, key) is called exactly K times in total; ties are
-// admitted in ascending i.  Output slots: [0, n_gt) for strictly-greater (arbitrary order), then ties.
+// Collect winners of a finished radix_select: emit(i, key, slot) is called exactly K times in total; ties are
+// admitted in ascending i.  Output slots: [0, n_gt) for strictly-greater (arbitrary order), then ties in index order.
+// Every thread owns a CONTIGUOUS index range (odd length: conflict-free shared-memory reads), so the tie ranks come
+// from one block-wide exclusive scan of per-thread tie counts (4 barriers in total, not 3 per 1024 elements).
 template <int PASSES, typename KeyFn, typename EmitFn>
 __device__ void collect(SelShared& sh, int n, int K, KeyFn key, EmitFn emit) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -128,67 +149,75 @@ __device__ void collect(SelShared& sh, int n, int K, KeyFn key, EmitFn emit) {
   const uint32_t prefix = sh.prefix, need = sh.need;
   const uint32_t n_gt = (uint32_t)K - need;
   __syncthreads();
-  if (tid == 0) { sh.gt_count = 0; sh.eq_base = 0; }
+  if (tid == 0) sh.gt_count = 0;
   __syncthreads();
-  for (int i0 = 0; i0 < n; i0 += SEL_NT) {
-    const int i = i0 + tid;
-    uint32_t k = 0;
-    bool gt = false, eq = false;
-    if (i < n) {
-      k = key(i);
-      const uint32_t hi = k >> kshift;
-      gt = hi > prefix;
-      eq = hi == prefix;
-    }
-    if (gt) emit(i, k, (int)atomicAdd(&sh.gt_count, 1u));
-    const uint32_t bal = __ballot_sync(0xffffffffu, eq);
-    if (lane == 0) sh.warp_cnt[wid] = __popc(bal);
-    __syncthreads();
-    if (eq) {
-      uint32_t before = sh.eq_base + __popc(bal & ((1u << lane) - 1u));
-      for (int w = 0; w < wid; ++w) before += sh.warp_cnt[w];
-      if (before < need) emit(i, k, (int)(n_gt + before));
-    }
-    __syncthreads();
-    if (tid == 0) {
-      uint32_t t = 0;
-      for (int w = 0; w < SEL_NT / 32; ++w) t += sh.warp_cnt[w];
-      sh.eq_base += t;
-    }
-    __syncthreads();
+  const int per = ((n + SEL_NT - 1) / SEL_NT) | 1;
+  const int lo = min(n, tid * per), hi = min(n, lo + per);
+  uint32_t cnt = 0;
+  for (int i = lo; i < hi; ++i) {
+    const uint32_t k = key(i), top = k >> kshift;
+    if (top > prefix) emit(i, k, (int)atomicAdd(&sh.gt_count, 1u));
+    else if (top == prefix) ++cnt;
   }
+  uint32_t incl = cnt;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += v;
+  }
+  if (lane == 31) sh.warp_cnt[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t w = sh.warp_cnt[lane], wi = w;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, wi, off);
+      if (lane >= off) wi += v;
+    }
+    sh.warp_cnt[lane] = wi - w;                    // exclusive prefix of the warp totals
+  }
+  __syncthreads();
+  uint32_t r = sh.warp_cnt[wid] + incl - cnt;      // ties before this thread's range
+  if (cnt && r < need)
+    for (int i = lo; i < hi && r < need; ++i) {
+      const uint32_t k = key(i);
+      if ((k >> kshift) == prefix) { emit(i, k, (int)(n_gt + r)); ++r; }
+    }
 }
 
-template <typename U>
-__device__ void bitonic_sort_desc(U* a, int n /*pow2*/) {
-  for (int k = 2; k <= n; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < n; i += SEL_NT) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const U x = a[i], y = a[ixj];
-          const bool desc = (i & k) == 0;
-          if (desc ? (x < y) : (x > y)) { a[i] = y; a[ixj] = x; }
-        }
-      }
-      __syncthreads();
+// out[rank] = in[i] where rank = number of entries of in[0..n) that precede in[i] (DESC: larger first).  Entries are
+// distinct, so the ranks are a permutation; every comparison operand is a shared-memory broadcast.  One barrier on
+// each side replaces the 45 barrier steps of a 512-element bitonic network.
+template <bool DESC, typename U>
+__device__ void rank_sort(const U* in, U* out, int n) {
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += SEL_NT) {
+    const U e = in[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const U o = in[j];
+      rank += DESC ? (o > e) : (o < e);
     }
+    out[rank] = e;
   }
+  __syncthreads();
 }
 
 // MODE 0: raw head maps -> decoded xyxy dets[B][K][6] (+anchor_idx);  MODE 1: preds passthrough.
 template <typename T, int PASSES, int MODE>
 __global__ void __launch_bounds__(SEL_NT)
-select_decode_kernel(TailSrc s, int K, int sortn, const uint32_t* __restrict__ amax, int cache_cap_keys,
+select_decode_kernel(TailSrc s, int K, int sortn, const uint32_t* __restrict__ amax, int cache_cap_keys, int vec_ok,
                      int img_h, int img_w, float* __restrict__ dets, int* __restrict__ anchor_idx,
                      float* __restrict__ boxes_out, float* __restrict__ scores_out, long long* __restrict__ labels_out) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ __align__(16) unsigned char dsm[];
   __shared__ SelShared sh;
-  unsigned long long* sortbuf = reinterpret_cast<unsigned long long*>(dsm);      // [sortn]
-  uint32_t* sel = reinterpret_cast<uint32_t*>(sortbuf + sortn);                  // [sortn] selected anchors
-  uint32_t* cache = sel + sortn;                                                 // [cache_cap_keys]
+  unsigned long long* sortbuf = reinterpret_cast<unsigned long long*>(dsm);      // [sortn] stage-2 winners (unsorted)
+  unsigned long long* sorted = sortbuf + sortn;                                  // [sortn] ... sorted
+  uint32_t* sel = reinterpret_cast<uint32_t*>(sorted + sortn);                   // [sortn] selected anchors (ascending)
+  uint32_t* sel_raw = sel + sortn;                                               // [sortn] ... in collection order
+  uint32_t* cache = sel_raw + sortn;                                             // [cache_cap_keys]
   const int b = blockIdx.x, tid = threadIdx.x;
   const int A = s.A, nc = s.nc;
   const uint32_t* ak = amax + (long long)b * A;
@@ -201,16 +230,9 @@ select_decode_kernel(TailSrc s, int K, int sortn, const uint32_t* __restrict__ a
   }
   auto key1 = [&](int i) -> uint32_t { return cache1 ? cache[i] : ak[i]; };
   radix_select<PASSES>(sh, A, K, key1);
-  for (int i = tid; i < sortn; i += SEL_NT) sel[i] = 0x7FFFFFFFu;
-  __syncthreads();
-  collect<PASSES>(sh, A, K, key1, [&](int i, uint32_t, int slot) { sel[slot] = (uint32_t)i; });
-  __syncthreads();
+  collect<PASSES>(sh, A, K, key1, [&](int i, uint32_t, int slot) { sel_raw[slot] = (uint32_t)i; });
   // ascending anchor order (so that candidate position order == flat (anchor, class) order)
-  for (int i = tid; i < sortn; i += SEL_NT) sortbuf[i] = ~(unsigned long long)sel[i];
-  __syncthreads();
-  bitonic_sort_desc(sortbuf, sortn);
-  for (int i = tid; i < sortn; i += SEL_NT) sel[i] = (uint32_t)(~sortbuf[i]);
-  __syncthreads();
+  rank_sort<false>(sel_raw, sel, K);
 
   // ---- stage 2: K largest of the K*nc pair keys ------------------------------------------------------
   const int n2 = K * nc;
@@ -221,20 +243,31 @@ select_decode_kernel(TailSrc s, int K, int sortn, const uint32_t* __restrict__ a
     return fkey(to_f(row[(long long)c * s.sc]));
   };
   if (cache2) {
-    for (int i = tid; i < n2; i += SEL_NT) cache[i] = load2(i);
+    constexpr int V = Vec<T>::N;
+    if (vec_ok) {                                  // 16-byte loads along the classes of each selected anchor
+      const int cvn = nc / V;
+      for (int v = tid; v < K * cvn; v += SEL_NT) {
+        const int slot = v / cvn, cv = v - slot * cvn;
+        const T* row = anchor_row<T>(s, b, (int)sel[slot]) + s.c_off + cv * V;
+        float f[V];
+        ldg_vec<T>(row).unpack(f);
+#pragma unroll
+        for (int j = 0; j < V; ++j) cache[slot * nc + cv * V + j] = fkey(f[j]);
+      }
+    } else {
+      for (int i = tid; i < n2; i += SEL_NT) cache[i] = load2(i);
+    }
     __syncthreads();
   }
   auto key2 = [&](int i) -> uint32_t { return cache2 ? cache[i] : load2(i); };
   radix_select<PASSES>(sh, n2, K, key2);
-  for (int i = tid; i < sortn; i += SEL_NT) sortbuf[i] = 0ull;
-  __syncthreads();
   collect<PASSES>(sh, n2, K, key2, [&](int i, uint32_t k, int slot) {
     const int sl = i / nc, c = i - sl * nc;
     const uint32_t flat = sel[sl] * (uint32_t)nc + (uint32_t)c;
     sortbuf[slot] = ((unsigned long long)k << 32) | (unsigned long long)(0xFFFFFFFFu - flat);
   });
-  __syncthreads();
-  bitonic_sort_desc(sortbuf, sortn);  // key desc, then flat index asc
+  rank_sort<true>(sortbuf, sorted, K);   // key desc, then flat index asc (entries are distinct)
+  sortbuf = sorted;
 
   // ---- winners: scores, labels, boxes ------------------------------------------------------------------
   for (int r = tid; r < K; r += SEL_NT) {
@@ -252,8 +285,16 @@ select_decode_kernel(TailSrc s, int K, int sortn, const uint32_t* __restrict__ a
 #pragma unroll
       for (int side = 0; side < 4; ++side) {
         float v[REG_MAX], mx = -INFINITY;
+        if (vec_ok) {
+          constexpr int V = Vec<T>::N;
 #pragma unroll
-        for (int i = 0; i < REG_MAX; ++i) { v[i] = to_f(row[side * REG_MAX + i]); mx = fmaxf(mx, v[i]); }
+          for (int i = 0; i < REG_MAX; i += V) ldg_vec<T>(row + side * REG_MAX + i).unpack(v + i);
+        } else {
+#pragma unroll
+          for (int i = 0; i < REG_MAX; ++i) v[i] = to_f(row[side * REG_MAX + i]);
+        }
+#pragma unroll
+        for (int i = 0; i < REG_MAX; ++i) mx = fmaxf(mx, v[i]);
         float se = 0.f;
 #pragma unroll
         for (int i = 0; i < REG_MAX; ++i) { v[i] = expf(v[i] - mx); se += v[i]; }
@@ -362,7 +403,7 @@ template <typename T, int PASSES, int MODE>
 int launch_select(const TailSrc& s, int B, int K, const uint32_t* amax, int img_h, int img_w, float* dets, int* aidx,
                   float* boxes, float* scores, long long* labels, cudaStream_t st) {
   const int sortn = next_pow2(K);
-  const size_t fixed = (size_t)sortn * (8 + 4);
+  const size_t fixed = (size_t)sortn * (8 + 8 + 4 + 4);
   int cap = (int)((SEL_SMEM_BUDGET - fixed) / 4);
   const int want = s.A > K * s.nc ? s.A : K * s.nc;
   if (cap > want) cap = want;
@@ -370,7 +411,11 @@ int launch_select(const TailSrc& s, int B, int K, const uint32_t* amax, int img_
   auto kern = select_decode_kernel<T, PASSES, MODE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) LPC_FAIL(LPC_E_CUDA, "select_decode: smem attribute: %s", cudaGetErrorString(e));
-  lpc_launch_pdl(kern, B, SEL_NT, smem, st, s, K, sortn, amax, cap, img_h, img_w, dets, aidx, boxes, scores, labels);
+  // 16-byte loads along an anchor row: contiguous classes, rows and class block 16-byte aligned
+  constexpr int V = Vec<T>::N;
+  const int vec_ok = MODE == 0 && s.sc == 1 && s.nc % V == 0 && s.sa % V == 0 && s.c_off % V == 0 && aligned16(s.ptr[0]) && aligned16(s.ptr[1]) &&
+                     aligned16(s.ptr[2]) && s.img_stride[0] % V == 0 && s.img_stride[1] % V == 0 && s.img_stride[2] % V == 0;
+  lpc_launch_pdl(kern, B, SEL_NT, smem, st, s, K, sortn, amax, cap, vec_ok, img_h, img_w, dets, aidx, boxes, scores, labels);
   LPC_CHECK_LAUNCH("select_decode");
   return LPC_OK;
 }
@@ -409,13 +454,13 @@ extern "C" int lpc_v10_decode_topk(int dtype, const void* raw0, const void* raw1
   const int g = cdiv((long long)B * s.A, 256);
   if (dtype == LPC_BF16) {
     const bool vec = (nc % 8 == 0) && (ld % 8 == 0) && aligned16(raw0) && aligned16(raw1) && aligned16(raw2);
-    if (vec) lpc_launch_pdl(amax_keys_kernel<bf16, true>, g, 256, 0, st, s, B, amax);
+    if (vec) lpc_launch_pdl(amax_keys_kernel<bf16, true>, cdiv((long long)B * s.A * 4, 256), 256, 0, st, s, B, amax);
     else lpc_launch_pdl(amax_keys_kernel<bf16, false>, g, 256, 0, st, s, B, amax);
     LPC_CHECK_LAUNCH("amax_keys");
     return launch_select<bf16, 2, 0>(s, B, K, amax, img_h, img_w, dets, anchor_idx, nullptr, nullptr, nullptr, st);
   } else if (dtype == LPC_F32) {
     const bool vec = (nc % 4 == 0) && (ld % 4 == 0) && aligned16(raw0) && aligned16(raw1) && aligned16(raw2);
-    if (vec) lpc_launch_pdl(amax_keys_kernel<float, true>, g, 256, 0, st, s, B, amax);
+    if (vec) lpc_launch_pdl(amax_keys_kernel<float, true>, cdiv((long long)B * s.A * 4, 256), 256, 0, st, s, B, amax);
     else lpc_launch_pdl(amax_keys_kernel<float, false>, g, 256, 0, st, s, B, amax);
     LPC_CHECK_LAUNCH("amax_keys");
     return launch_select<float, 4, 0>(s, B, K, amax, img_h, img_w, dets, anchor_idx, nullptr, nullptr, nullptr, st);
