@@ -56,6 +56,7 @@ struct ConvTcParams {
   int pix_per_img;
   float inv_tiles_per_img, inv_tiles_x, inv_tw;  // reciprocals for the small integer divisions of the tile scheduler
   int a_bufs, b_resident, b_stages;  // halo kernel
+  int a_tma;                         // halo kernel: 1 = the patch arrives by TMA (one 4-D box per 64-channel slab), no loader warps
   const bf16* x;                     // halo kernel: activation base, pixel pitch, input geometry
   long long x_ld;
   int H, W;
@@ -381,7 +382,7 @@ conv_tc_halo_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
       mbar_init(bempty_bar(s), 1);
     }
     for (int s = 0; s < MAX_STAGES; ++s) {
-      mbar_init(afull_bar(s), HALO_LOADERS);
+      mbar_init(afull_bar(s), p.a_tma ? 1 : HALO_LOADERS);
       mbar_init(aempty_bar(s), 1);
     }
     for (int b = 0; b < p.n_acc; ++b) {
@@ -404,6 +405,23 @@ conv_tc_halo_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
       if (b_res) {
         mbar_expect_tx(bfull_bar(0), (uint32_t)(p.ksteps * b_block));
         for (int ks = 0; ks < p.ksteps; ++ks) tma_load_2d(smem_base + (uint32_t)(ks * b_block), &maps.b, bfull_bar(0), ks * 64, n0);
+      }
+      if (p.a_tma) {
+        // The halo patch by TMA: per 64-channel slab ONE 4-D box [min(Cin,64) ch, 16 px, 18 rows, 1 image] at (x0-1, y0-1);
+        // the box lands exactly in the pixel-major swizzled slab layout the MMA descriptors view (row pitch 16 pixels) and
+        // out-of-image pixels are zero-filled by the TMA unit.  It moves 288 pixels for the 180 the taps read (L2 -> SM
+        // traffic only) and replaces ~900 loader warp instructions per tile (profiles/r01_j_ncu_full_conv_16_32.md).
+        pdl_wait();                               // activations of the previous kernel
+        int tcount = 0;
+        for (int m = m_first; m < p.m_tiles; m += m_step, ++tcount) {
+          const TileCoord t = tile_coord(p, m);
+          const int ab = tcount % p.a_bufs;
+          mbar_wait(aempty_bar(ab), (uint32_t)(((tcount / p.a_bufs) & 1) ^ 1));
+          mbar_expect_tx(afull_bar(ab), (uint32_t)halo_bytes);
+          const uint32_t a_dst = a_region + (uint32_t)(ab * halo_bytes);
+          for (int sl = 0; sl < p.slabs; ++sl)
+            tma_load_4d(a_dst + (uint32_t)(sl * p.slab_bytes), &maps.a[0], afull_bar(ab), sl * 64, t.x0 - 1, t.y0 - 1, t.img);
+        }
       }
       if (!b_res) {
         int bit = 0;
@@ -806,6 +824,14 @@ extern "C" int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int C
     p.slabs = (Cin + 63) / 64;
     p.slab_bytes = HALO_PH * HALO_SPW * p.pitch;
     smem = (size_t)(p.b_resident ? p.ksteps : p.b_stages) * (pair ? p.n_tile / 2 : p.n_tile) * 128 + (size_t)p.a_bufs * p.slabs * p.slab_bytes + 1024 + BIAS_REGION(p.n_tile);
+    {
+      static const int atma_env = [] { const char* e = getenv("LPC_TC_ATMA"); return e ? atoi(e) : 1; }();
+      p.a_tma = (atma_env && !pair && p.b_resident) ? 1 : 0;
+      if (p.a_tma) {
+        const int cb = Cin >= 64 ? 64 : Cin;
+        if (int e = encode_act_map(&maps.a[0], xb, Cin, W, H, B, x_ld, (long long)W * x_ld, (long long)H * W * x_ld, cb, HALO_SPW, HALO_PH, swizzle_of(cb))) return e;
+      }
+    }
   } else {
     p.kc = pick_kc(Cin);
     p.nsub = 64 / p.kc;
@@ -916,7 +942,7 @@ extern "C" int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int C
   }
   if (halo) {
     LPC_REQUIRE((long long)H * W * x_ld < (1ll << 31), "conv2d_tc: image too large for 32-bit offsets");
-    const unsigned th = threads + HALO_LOADERS;
+    const unsigned th = threads + (p.a_tma ? 0 : HALO_LOADERS);
     cudaStream_t st = (cudaStream_t)stream;
     if (pair) {
       switch (Cin) {
