@@ -158,10 +158,9 @@ template <bool PRECISE> __device__ __forceinline__ float mish_(float x) {
   return x * fmaf(-2.0f, rcp_approx(d), 1.0f);        // x (1 - 2/(n+2)) = x n/(n+2)
 }
 // Packed (two elements per instruction: FFMA2 / FMUL2 / FADD2, sm_100) bf16-mode activations for the conv epilogues,
-// which are MUFU- and issue-bound on the small-channel layers (profiles/r01_h_*).  mish2_ spends ONE MUFU op per
-// element (ex2); the reciprocal is an integer-seeded Newton iteration on the FMA pipe (two steps: 6.6e-6 relative
-// error, measured over d in [2, 2^61]; the result x*n/(n+2) is a product, so there is no cancellation for x << 0).
+// which are issue-bound on the small-channel layers (profiles/r01_j_ncu_full_conv_16_32.md).
 __device__ __forceinline__ float2 mish2_(float2 x) {
+#ifdef LPC_MISH_ONE_MUFU
   const float2 xl = __fmul2_rn(x, make_float2(1.4426950408889634f, 1.4426950408889634f));
   float2 e;
   e.x = ex2_approx(fminf(xl.x, 30.0f));      // clamp: d = e^2 + 2e + 2 stays finite; mish(x) = x beyond
@@ -177,6 +176,22 @@ __device__ __forceinline__ float2 mish2_(float2 x) {
   r = __fmul2_rn(r, __ffma2_rn(nd, r, two));
   r = __fmul2_rn(r, __ffma2_rn(nd, r, two));
   return __fmul2_rn(__fmul2_rn(x, n), r);
+#else
+  // 9 instructions per PAIR (2 MUFU per element).  The conv epilogues are bound by instruction issue, not by the MUFU
+  // pipe (ncu: issue 68 %, xu 31 %), so this beats the 19-instruction one-MUFU variant above (integer-seeded Newton
+  // reciprocal on the FMA pipe, 6.6e-6 relative error) that is kept under LPC_MISH_ONE_MUFU.
+  // x (1 - 2/(n+2)) with n + 2 = e (e + 2) + 2; no clamp: e = +inf gives rcp = 0 and the result x.
+  const float2 xl = __fmul2_rn(x, make_float2(1.4426950408889634f, 1.4426950408889634f));
+  float2 e;
+  e.x = ex2_approx(xl.x);
+  e.y = ex2_approx(xl.y);
+  const float2 two = make_float2(2.0f, 2.0f);
+  const float2 d = __ffma2_rn(e, __fadd2_rn(e, two), two);
+  float2 r;
+  r.x = rcp_approx(d.x);
+  r.y = rcp_approx(d.y);
+  return __fmul2_rn(x, __ffma2_rn(r, make_float2(-2.0f, -2.0f), make_float2(1.0f, 1.0f)));
+#endif
 }
 __device__ __forceinline__ float2 silu2_(float2 x) {
   const float2 h = __fmul2_rn(x, make_float2(0.5f, 0.5f));

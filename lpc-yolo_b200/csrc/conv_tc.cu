@@ -780,10 +780,11 @@ extern "C" int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int C
       const int ntp = pick_ntile(Cout, 256);
       const size_t bp = (size_t)p.ksteps * (ntp / 2) * 128;
       const long long tot_tiles = tiles * B;
-      // Worth it where the tile is MMA-instruction bound (>= 36 MMAs of N >= 128, or Cin >= 128); the small-channel
-      // layers are bound by per-tile role latency and lose to the extra cross-CTA hops (measured: 16->32 327 vs 217 us,
-      // 32->64 147 vs 138, 64->64 tie, 64->128 79 vs 121).  LPC_TC_PAIR=2 forces pairs wherever they fit (tests).
-      const bool wanted = pair_env == 2 || (Cin >= 64 && Cout >= 128) || Cin >= 128;
+      // Worth it where the tile is MMA-instruction bound (Cin >= 64: >= 36 MMAs per tile); the Cin 16 / 32 layers are
+      // bound by per-tile role latency and lose to the cluster-scope hops.  Measured with TMA patches in both kernels
+      // (us, single vs pair): 16->32 169 / 265, 32->64 104 / 124, 32->32 17.5 / 21.2, 64->64@80 49.3 / 44.1,
+      // 64->64@40 17.9 / 16.2, 64->128 (N = 64 twice) 121 / 66.  LPC_TC_PAIR=2 forces pairs wherever they fit (tests).
+      const bool wanted = pair_env == 2 || Cin >= 64;
       if (pair_env && wanted && (eff >= 0.7 || g_force_mode == 2) && bp + 2 * halo_bytes <= SMEM_LIMIT && tot_tiles >= 4) {
         halo = pair = true;
         p.n_tile = ntp;
@@ -826,7 +827,7 @@ extern "C" int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int C
     smem = (size_t)(p.b_resident ? p.ksteps : p.b_stages) * (pair ? p.n_tile / 2 : p.n_tile) * 128 + (size_t)p.a_bufs * p.slabs * p.slab_bytes + 1024 + BIAS_REGION(p.n_tile);
     {
       static const int atma_env = [] { const char* e = getenv("LPC_TC_ATMA"); return e ? atoi(e) : 1; }();
-      p.a_tma = (atma_env && !pair && p.b_resident) ? 1 : 0;
+      p.a_tma = (atma_env && p.b_resident) ? 1 : 0;   // LPC_TC_ATMA=0: cp.async loader warps (both kernels keep that path)
       if (p.a_tma) {
         const int cb = Cin >= 64 ? 64 : Cin;
         if (int e = encode_act_map(&maps.a[0], xb, Cin, W, H, B, x_ld, (long long)W * x_ld, (long long)H * W * x_ld, cb, HALO_SPW, HALO_PH, swizzle_of(cb))) return e;

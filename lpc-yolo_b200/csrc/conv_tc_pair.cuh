@@ -45,8 +45,9 @@ conv_tc_halo2_kernel(const __grid_constant__ TmapPack maps, const __grid_constan
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&maps.b);
+    if (p.a_tma) prefetch_tmap(&maps.a[0]);
     for (int s = 0; s < MAX_STAGES; ++s) {
-      mbar_init(afull_bar(s), 2 * (HALO_LOADERS / 32));
+      mbar_init(afull_bar(s), p.a_tma ? 2 : 2 * (HALO_LOADERS / 32));
       mbar_init(aempty_bar(s), 1);
     }
     for (int b = 0; b < 4; ++b) {
@@ -73,6 +74,24 @@ conv_tc_halo2_kernel(const __grid_constant__ TmapPack maps, const __grid_constan
       mbar_wait(bfull_bar, 0);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive_rank(wready_bar, 0);
+      if (p.a_tma) {
+        // Halo patches by TMA (as in conv_tc_halo_kernel): each CTA loads its own tile's patch into its own shared memory;
+        // both report (expect_tx + complete_tx) to the LEADER's afull barrier (count 2), which the MMA thread waits on.
+        pdl_wait();
+        int tcount = 0;
+        for (int mp = mp_first; 2 * mp < p.m_tiles; mp += mp_step, ++tcount) {
+          const int m = 2 * mp + (int)rank;
+          const bool live = m < p.m_tiles;
+          const TileCoord t = tile_coord(p, live ? m : p.m_tiles - 1);     // odd tile count: the idle half re-loads the last tile
+          const int ab = tcount % p.a_bufs;
+          mbar_wait(aempty_bar(ab), (uint32_t)(((tcount / p.a_bufs) & 1) ^ 1));
+          const uint32_t lead_bar = mapa_rank(afull_bar(ab), 0);
+          mbar_expect_tx_cluster(lead_bar, (uint32_t)halo_bytes);
+          const uint32_t a_dst = a_region + (uint32_t)(ab * halo_bytes);
+          for (int sl = 0; sl < p.slabs; ++sl)
+            tma_load_4d_pair(a_dst + (uint32_t)(sl * p.slab_bytes), &maps.a[0], lead_bar, sl * 64, t.x0 - 1, t.y0 - 1, t.img);
+        }
+      }
     }
   } else if (warp >= 2 + 4 * p.epi_split) {
     // ===== activation loaders (as in conv_tc_halo_kernel; one arrival per warp on the leader's barrier) =====
