@@ -294,7 +294,7 @@ conv_tc_taps_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
         const int e = k * 16, j = e / p.kc;
         a_off[k] = (uint32_t)((j * sub_bytes + (e - j * p.kc) * 2) >> 4);
       }
-      const int last_real = (p.real_slots * p.kc - (p.ksteps - 1) * 64) / 16;   // real K=16 slices of the last step
+      const int last_real = (min(p.real_slots * p.kc, p.Cin * (p.real_slots / p.chunks_per_tap)) - (p.ksteps - 1) * 64 + 15) / 16;   // real K=16 slices of the last step
       int it = 0, tcount = 0;
       for (int m = m_first; m < p.m_tiles; m += m_step, ++tcount) {
         const int buf = tcount & (p.n_acc - 1);
@@ -834,9 +834,12 @@ extern "C" int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int C
       }
     }
   } else {
-    p.kc = pick_kc(Cin);
+    // 1x1: always 64-channel boxes in the 128B-swizzled layout; when Cin is not a multiple of 64 the last box runs past the
+    // tensor's channel extent and TMA zero-fills the rest (the packed weights are zero there too), e.g. Cin = 80:
+    // 2 requests per tile instead of 5 boxes of 16 channels in the slow 32B-swizzled layout.
+    p.kc = (k == 1) ? 64 : pick_kc(Cin);
     p.nsub = 64 / p.kc;
-    p.chunks_per_tap = Cin / p.kc;
+    p.chunks_per_tap = (Cin + p.kc - 1) / p.kc;
     p.real_slots = ntaps * p.chunks_per_tap;
     const CUtensorMapSwizzle sw = swizzle_of(p.kc);
     if (k == 1) {
