@@ -108,9 +108,16 @@ __device__ __forceinline__ void issue_bias_mma(uint32_t acc, uint32_t ones_addr,
   umma_bf16(acc, smem_desc(ones_addr, 16u, 256u, 6u), smem_desc(bias_addr, 16u, 256u, 6u), idesc, 0u);
 }
 
+// Residual (shortcut) vectors of the first 32 columns of this thread's output row, loaded BEFORE the wait on the
+// accumulator: the epilogue is a latency chain (tcgen05.ld -> math -> store) and a global load inside it cost the
+// shortcut layers ~30 us each (16->16 160x160 B64: 77 vs 45 us without the shortcut).
+struct ResPre {
+  uint4 v[4];
+};
+
 // ---- epilogue: one accumulator tile (128 rows x n_tile columns) -> NHWC bf16 --------------------------------
 template <int ACT>
-__device__ __forceinline__ void store16(const uint32_t* v, bf16* yrow, const bf16* rrow, const float* srow, bool no_store = false) {
+__device__ __forceinline__ void store16(const uint32_t* v, bf16* yrow, const bf16* rrow, const float* srow, bool no_store = false, bool has_pre = false, uint4 pre0 = uint4(), uint4 pre1 = uint4()) {
   float f[16];
 #pragma unroll
   for (int i = 0; i < 16; i += 2) {
@@ -129,10 +136,13 @@ __device__ __forceinline__ void store16(const uint32_t* v, bf16* yrow, const bf1
   }
   if (rrow) {
     float r8[8];
-    ld_vec<bf16>(rrow).unpack(r8);
+    Vec<bf16> rv;
+    if (has_pre) rv.raw = pre0; else rv = ld_vec<bf16>(rrow);      // pre: residual vectors fetched before the accumulator wait
+    rv.unpack(r8);
 #pragma unroll
     for (int i = 0; i < 8; ++i) f[i] += r8[i];
-    ld_vec<bf16>(rrow + 8).unpack(r8);
+    if (has_pre) rv.raw = pre1; else rv = ld_vec<bf16>(rrow + 8);
+    rv.unpack(r8);
 #pragma unroll
     for (int i = 0; i < 8; ++i) f[8 + i] += r8[i];
   }
@@ -148,14 +158,24 @@ __device__ __forceinline__ void store16(const uint32_t* v, bf16* yrow, const bf1
 }
 
 template <int ACT>
-__device__ __forceinline__ void epilogue_cols(uint32_t trow, int c, int c_end, bool valid, bf16* yrow, const bf16* rrow, const float* srow, bool no_store) {
+__device__ __forceinline__ void epilogue_cols(uint32_t trow, int c, int c_end, bool valid, bf16* yrow, const bf16* rrow, const float* srow, bool no_store,
+                                              const ResPre* pre) {
+  const int c_first = c;
   for (; c < c_end; c += 16) {
     uint32_t v0[16];
     tmem_ld16(trow + (uint32_t)c, v0);
     tmem_ld_wait();
-    if (valid) store16<ACT>(v0, yrow + c, rrow ? rrow + c : nullptr, srow ? srow + c : nullptr, no_store);
+    const int ci = (c - c_first) >> 4;
+    const bool hp = pre != nullptr && ci < 2;
+    uint4 pa = uint4(), pb = uint4();
+    if (hp) {                              // static indices + selects: the prefetched vectors stay in registers
+      pa = ci == 0 ? pre->v[0] : pre->v[2];
+      pb = ci == 0 ? pre->v[1] : pre->v[3];
+    }
+    if (valid) store16<ACT>(v0, yrow + c, rrow ? rrow + c : nullptr, srow ? srow + c : nullptr, no_store, hp, pa, pb);
   }
 }
+
 
 // Per-thread epilogue state that does not depend on the tile: computed once, so the per-tile cost is a handful of
 // integer ops (the whole SM is instruction-issue bound on the small-channel layers, profiles/r01_e_*).
@@ -179,7 +199,17 @@ __device__ __forceinline__ EpiCtx make_epi_ctx(const ConvTcParams& p, int warp, 
   e.row_ok = e.ty < p.TH && !(p.dbg & 4);
   return e;
 }
-__device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, const EpiCtx& e, uint32_t tmem_acc, int img, int x0, int y0, int n0) {
+__device__ __forceinline__ void res_prefetch(const ConvTcParams& p, const EpiCtx& e, int img, int x0, int y0, int n0, ResPre& r) {
+  if (!p.res) return;
+  const int ox = x0 + e.tx, oy = y0 + e.ty;
+  if (!(e.row_ok && ox < p.Wo && oy < p.Ho)) return;
+  const long long pix = ((long long)img * p.Ho + oy) * p.Wo + ox;
+  const bf16* rrow = p.res + pix * p.res_ld + n0 + e.c0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (e.c0 + 8 * j < e.c_end) r.v[j] = *reinterpret_cast<const uint4*>(rrow + 8 * j);
+}
+__device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, const EpiCtx& e, uint32_t tmem_acc, int img, int x0, int y0, int n0, const ResPre* rp = nullptr) {
   const int ox = x0 + e.tx, oy = y0 + e.ty;
   const bool valid = e.row_ok && ox < p.Wo && oy < p.Ho;
   const long long pix = ((long long)img * p.Ho + oy) * p.Wo + ox;
@@ -189,12 +219,13 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, const EpiCt
   if (p.chan_scale) srow = p.chan_scale + (pix / p.pix_per_img) * p.Cout + n0;
   const uint32_t trow = tmem_acc + e.lane_off;
   const bool ns = (p.dbg & 32) != 0;
+  const ResPre* pre = (rp && rrow) ? rp : nullptr;
   switch (p.act) {
-    case LPC_ACT_MISH: epilogue_cols<LPC_ACT_MISH>(trow, e.c0, e.c_end, valid, yrow, rrow, srow, ns); break;
-    case LPC_ACT_SILU: epilogue_cols<LPC_ACT_SILU>(trow, e.c0, e.c_end, valid, yrow, rrow, srow, ns); break;
-    case LPC_ACT_NONE: epilogue_cols<LPC_ACT_NONE>(trow, e.c0, e.c_end, valid, yrow, rrow, srow, ns); break;
-    case LPC_ACT_SIGMOID: epilogue_cols<LPC_ACT_SIGMOID>(trow, e.c0, e.c_end, valid, yrow, rrow, srow, ns); break;
-    default: epilogue_cols<LPC_ACT_RELU>(trow, e.c0, e.c_end, valid, yrow, rrow, srow, ns); break;
+    case LPC_ACT_MISH: epilogue_cols<LPC_ACT_MISH>(trow, e.c0, e.c_end, valid, yrow, rrow, srow, ns, pre); break;
+    case LPC_ACT_SILU: epilogue_cols<LPC_ACT_SILU>(trow, e.c0, e.c_end, valid, yrow, rrow, srow, ns, pre); break;
+    case LPC_ACT_NONE: epilogue_cols<LPC_ACT_NONE>(trow, e.c0, e.c_end, valid, yrow, rrow, srow, ns, pre); break;
+    case LPC_ACT_SIGMOID: epilogue_cols<LPC_ACT_SIGMOID>(trow, e.c0, e.c_end, valid, yrow, rrow, srow, ns, pre); break;
+    default: epilogue_cols<LPC_ACT_RELU>(trow, e.c0, e.c_end, valid, yrow, rrow, srow, ns, pre); break;
   }
 }
 
@@ -324,9 +355,11 @@ conv_tc_taps_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
       if (p.epi_alt && (tcount & 1) != ectx.group) continue;   // the other warp group's tile
       const TileCoord t = tile_coord(p, m);
       const int buf = tcount & (p.n_acc - 1);
+      ResPre rp;
+      res_prefetch(p, ectx, t.img, t.x0, t.y0, n0, rp);
       mbar_wait(tfull_bar(buf), (uint32_t)((tcount >> p.acc_shift) & 1));
       tc_fence_after();
-      epilogue_tile(p, ectx, tmem_base + (uint32_t)(buf * p.acc_cols), t.img, t.x0, t.y0, n0);
+      epilogue_tile(p, ectx, tmem_base + (uint32_t)(buf * p.acc_cols), t.img, t.x0, t.y0, n0, &rp);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(buf));
@@ -344,8 +377,8 @@ conv_tc_taps_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
 // patch is gathered with 16-byte cp.async (coalesced in global memory, scattered into the planar layout, zero-filled
 // outside the image): TMA would need one request per 16-byte element here, and its per-request rate (~5 cycles)
 // made it the bottleneck of every small-Cin layer (profiles/r01_c_*).
-template <int CIN, int BRES>   // CIN > 0: patch geometry and the MMA issue sequence are compile-time; BRES: 1 weights resident, 0 streamed, -1 runtime
-__global__ void __launch_bounds__(448, 2)
+template <int CIN>   // CIN > 0: patch geometry and the MMA issue sequence are compile-time
+__global__ void __launch_bounds__(320, 2)
 conv_tc_halo_kernel(const __grid_constant__ TmapPack maps, const __grid_constant__ ConvTcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long bars[4 * MAX_STAGES + 8];
@@ -354,7 +387,7 @@ conv_tc_halo_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
   const uint32_t ones_addr = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bias_addr = ones_addr + ONES_BYTES;
   const uint32_t smem_base = (bias_addr + (uint32_t)p.n_tile * 32u + 1023u) & ~1023u;
-  const bool b_res = BRES < 0 ? (p.b_resident != 0) : (BRES != 0);
+  constexpr bool b_res = true;                  // weights stay resident (the host routes everything else to the taps kernel)
   const int b_block = p.n_tile * 128;
   const int b_blocks = b_res ? p.ksteps : p.b_stages;
   const int halo_bytes = p.slabs * p.slab_bytes;
@@ -382,7 +415,7 @@ conv_tc_halo_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
       mbar_init(bempty_bar(s), 1);
     }
     for (int s = 0; s < MAX_STAGES; ++s) {
-      mbar_init(afull_bar(s), p.a_tma ? 1 : HALO_LOADERS);
+      mbar_init(afull_bar(s), 1);
       mbar_init(aempty_bar(s), 1);
     }
     for (int b = 0; b < p.n_acc; ++b) {
@@ -406,7 +439,7 @@ conv_tc_halo_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
         mbar_expect_tx(bfull_bar(0), (uint32_t)(p.ksteps * b_block));
         for (int ks = 0; ks < p.ksteps; ++ks) tma_load_2d(smem_base + (uint32_t)(ks * b_block), &maps.b, bfull_bar(0), ks * 64, n0);
       }
-      if (p.a_tma) {
+      {
         // The halo patch by TMA: per 64-channel slab ONE 4-D box [min(Cin,64) ch, 16 px, 18 rows, 1 image] at (x0-1, y0-1);
         // the box lands exactly in the pixel-major swizzled slab layout the MMA descriptors view (row pitch 16 pixels) and
         // out-of-image pixels are zero-filled by the TMA unit.  It moves 288 pixels for the 180 the taps read (L2 -> SM
@@ -423,84 +456,7 @@ conv_tc_halo_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
             tma_load_4d(a_dst + (uint32_t)(sl * p.slab_bytes), &maps.a[0], afull_bar(ab), sl * 64, t.x0 - 1, t.y0 - 1, t.img);
         }
       }
-      if (!b_res) {
-        int bit = 0;
-        for (int m = m_first; m < p.m_tiles; m += m_step) {
-          for (int ks = 0; ks < p.ksteps; ++ks, ++bit) {
-            const int s = bit % p.b_stages;
-            mbar_wait(bempty_bar(s), (uint32_t)(((bit / p.b_stages) & 1) ^ 1));
-            mbar_expect_tx(bfull_bar(s), (uint32_t)b_block);
-            tma_load_2d(smem_base + (uint32_t)(s * b_block), &maps.b, bfull_bar(s), ks * 64, n0);
-          }
-        }
-      }
     }
-  } else if (warp >= 2 + 4 * p.epi_split) {
-    // ===== activation loaders =====
-    // Thread t owns patch pixels t and t+128 (of 180): per tile it resolves each pixel's address / in-image test once
-    // and then streams that pixel's Cin/8 16-byte channel groups (contiguous in global memory, one plane apart in
-    // shared memory).  .ca keeps the touched sectors in L1 for the neighbouring groups of the same pixel.
-    const int lt = threadIdx.x - (2 + 4 * p.epi_split) * 32;
-    const int look = p.a_bufs >= 6 ? 3 : (p.a_bufs >= 4 ? 2 : 1);   // tiles in flight per CTA before the oldest is awaited
-    int ppy[2], ppx[2];
-    uint32_t row_off[2], phase[2];
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int pix = lt + q * HALO_LOADERS;
-      ppy[q] = pix / HALO_PW;
-      ppx[q] = pix - ppy[q] * HALO_PW;
-      row_off[q] = (uint32_t)((ppy[q] * HALO_SPW + ppx[q]) * p.pitch);        // buffers are 1024-B aligned
-      phase[q] = (row_off[q] >> 7) & (uint32_t)(chunks_row - 1);              // Swizzle<b,4,3> on the address
-    }
-    const bool second = lt + HALO_LOADERS < HALO_PW * HALO_PH;
-    const int img_elems = p.H * p.W * (int)p.x_ld;                             // < 2^31 (checked on the host)
-    int tcount = 0;
-    for (int m = m_first; m < p.m_tiles; m += m_step, ++tcount) {
-      const TileCoord t = tile_coord(p, m);
-      const int ab = tcount % p.a_bufs;
-      if (lt == 0) TRACE(0, tcount, 0);
-      mbar_wait(aempty_bar(ab), (uint32_t)(((tcount / p.a_bufs) & 1) ^ 1));
-      if (lt == 0) TRACE(0, tcount, 1);
-      const uint32_t a_dst = a_region + (uint32_t)(ab * halo_bytes);
-      const bf16* img_base = p.x + (long long)t.img * img_elems;
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        if (q == 0 || second) {
-          const int iy = t.y0 - 1 + ppy[q], ix = t.x0 - 1 + ppx[q];
-          const bool in = (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
-          const bf16* src = in ? img_base + (iy * p.W + ix) * (int)p.x_ld : p.x;
-          const uint32_t nb = in ? 16u : 0u;
-          if (!(p.dbg & 2)) {
-            uint32_t dst_row = a_dst + row_off[q];
-            if (CIN > 0) {
-              constexpr int CROW = (CIN < 64 ? CIN : 64) / 8, NSLAB = (CIN + 63) / 64;
-              constexpr int SLABB = HALO_PH * HALO_SPW * (CIN < 64 ? CIN : 64) * 2;
-#pragma unroll
-              for (int sl = 0; sl < NSLAB; ++sl)
-#pragma unroll
-                for (int cw = 0; cw < CROW; ++cw)
-                  cp_async16(dst_row + (uint32_t)(sl * SLABB) + (((uint32_t)cw ^ phase[q]) << 4), src + (in ? (sl * CROW + cw) * 8 : 0), nb);
-            } else {
-              for (int c0 = 0; c0 < chunks_px; c0 += chunks_row, dst_row += (uint32_t)p.slab_bytes)   // one 64-channel slab per pass
-#pragma unroll 4
-                for (int cw = 0; cw < chunks_row; ++cw)
-                  cp_async16(dst_row + (((uint32_t)cw ^ phase[q]) << 4), src + (in ? (c0 + cw) * 8 : 0), nb);
-            }
-          }
-        }
-      }
-      cp_async_commit();
-      if (lt == 0) TRACE(0, tcount, 2);
-      if (tcount >= look) {                      // the tile issued `look` iterations ago has landed
-        cp_async_wait_dyn(look);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(afull_bar((tcount - look) % p.a_bufs));
-      }
-      if (lt == 0) TRACE(0, tcount, 3);
-    }
-    cp_async_wait_dyn(0);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    for (int i = (tcount > look ? tcount - look : 0); i < tcount; ++i) mbar_arrive(afull_bar(i % p.a_bufs));
   } else if (warp == 1) {
     // Descriptors are derived arithmetically from kernel parameters and loop counters only (no table look-ups), so the
     // compiler keeps them in the uniform datapath: per MMA a couple of UIADDs + UTCHMMA.  Slice (tap, slab, g) views the
@@ -596,10 +552,12 @@ conv_tc_halo_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
       const TileCoord t = tile_coord(p, m);
       const int buf = tcount & (p.n_acc - 1);
       if (threadIdx.x == 64) TRACE(2, tcount, 0);
+      ResPre rp;
+      res_prefetch(p, ectx, t.img, t.x0, t.y0, n0, rp);
       mbar_wait(tfull_bar(buf), (uint32_t)((tcount >> p.acc_shift) & 1));
       if (threadIdx.x == 64) TRACE(2, tcount, 1);
       tc_fence_after();
-      epilogue_tile(p, ectx, tmem_base + (uint32_t)(buf * p.acc_cols), t.img, t.x0, t.y0, n0);
+      epilogue_tile(p, ectx, tmem_base + (uint32_t)(buf * p.acc_cols), t.img, t.x0, t.y0, n0, &rp);
       if (threadIdx.x == 64) TRACE(2, tcount, 2);
       tc_fence_before();
       __syncwarp();
@@ -770,10 +728,7 @@ extern "C" int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int C
       nt /= 2;
       need = (size_t)p.ksteps * nt * 128 + 2 * halo_bytes;
     }
-    if (need > SMEM_LIMIT) {
-      resident = 0;
-      need = (size_t)3 * nt * 128 + 2 * halo_bytes;
-    }
+    if (need > SMEM_LIMIT) resident = 0;          // weights do not fit next to two patches: the per-tap TMA kernel streams them
     // CTA pairs (cta_group::2, conv_tc_pair.cuh): full-width N with HALF the weight rows resident per CTA
     {
       static const int pair_env = [] { const char* e = getenv("LPC_TC_PAIR"); return e ? atoi(e) : 1; }();
@@ -794,7 +749,7 @@ extern "C" int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int C
         p.a_bufs = ab > MAX_STAGES ? MAX_STAGES : (ab < 2 ? 2 : ab);
       }
     }
-    if (!pair && (eff >= 0.7 || g_force_mode == 2) && need <= SMEM_LIMIT) {
+    if (!pair && resident && (eff >= 0.7 || g_force_mode == 2) && need <= SMEM_LIMIT) {
       halo = true;
       p.n_tile = nt;
       p.b_resident = resident;
@@ -826,12 +781,9 @@ extern "C" int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int C
     p.slab_bytes = HALO_PH * HALO_SPW * p.pitch;
     smem = (size_t)(p.b_resident ? p.ksteps : p.b_stages) * (pair ? p.n_tile / 2 : p.n_tile) * 128 + (size_t)p.a_bufs * p.slabs * p.slab_bytes + 1024 + BIAS_REGION(p.n_tile);
     {
-      static const int atma_env = [] { const char* e = getenv("LPC_TC_ATMA"); return e ? atoi(e) : 1; }();
-      p.a_tma = (atma_env && p.b_resident) ? 1 : 0;   // LPC_TC_ATMA=0: cp.async loader warps (both kernels keep that path)
-      if (p.a_tma) {
-        const int cb = Cin >= 64 ? 64 : Cin;
-        if (int e = encode_act_map(&maps.a[0], xb, Cin, W, H, B, x_ld, (long long)W * x_ld, (long long)H * W * x_ld, cb, HALO_SPW, HALO_PH, swizzle_of(cb))) return e;
-      }
+      p.a_tma = 1;                                // both halo kernels receive their patches by TMA
+      const int cb = Cin >= 64 ? 64 : Cin;
+      if (int e = encode_act_map(&maps.a[0], xb, Cin, W, H, B, x_ld, (long long)W * x_ld, (long long)H * W * x_ld, cb, HALO_SPW, HALO_PH, swizzle_of(cb))) return e;
     }
   } else {
     // 1x1: always 64-channel boxes in the 128B-swizzled layout; when Cin is not a multiple of 64 the last box runs past the
@@ -900,11 +852,11 @@ extern "C" int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int C
     cudaError_t e1 = cudaFuncSetAttribute(conv_tc_taps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT + 16 * 1024);
     cudaError_t e2 = cudaSuccess;
     const int lim = (int)SMEM_LIMIT + 16 * 1024;
-#define HALO_ATTR(C_, R_) if (cudaFuncSetAttribute(conv_tc_halo_kernel<C_, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess) e2 = cudaErrorUnknown;
+#define HALO_ATTR(C_) if (cudaFuncSetAttribute(conv_tc_halo_kernel<C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess) e2 = cudaErrorUnknown;
 #define PAIR_ATTR(C_) if (cudaFuncSetAttribute(conv_tc_halo2_kernel<C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess) e2 = cudaErrorUnknown;
     PAIR_ATTR(0) PAIR_ATTR(16) PAIR_ATTR(32) PAIR_ATTR(64) PAIR_ATTR(128)
 #undef PAIR_ATTR
-    HALO_ATTR(0, -1) HALO_ATTR(16, 1) HALO_ATTR(32, 1) HALO_ATTR(64, 1) HALO_ATTR(128, 1) HALO_ATTR(128, 0)
+    HALO_ATTR(0) HALO_ATTR(16) HALO_ATTR(32) HALO_ATTR(64) HALO_ATTR(128)
 #undef HALO_ATTR
     if (e1 != cudaSuccess || e2 != cudaSuccess) LPC_FAIL(LPC_E_CUDA, "conv2d_tc: smem attribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
     attr_set = true;
@@ -946,24 +898,17 @@ extern "C" int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int C
   }
   if (halo) {
     LPC_REQUIRE((long long)H * W * x_ld < (1ll << 31), "conv2d_tc: image too large for 32-bit offsets");
-    const unsigned th = threads + (p.a_tma ? 0 : HALO_LOADERS);
+    const unsigned th = threads;
     cudaStream_t st = (cudaStream_t)stream;
-    if (pair) {
-      switch (Cin) {
-        case 16: lpc_launch_pdl(conv_tc_halo2_kernel<16>, grid, th, smem, st, maps, p); break;
-        case 32: lpc_launch_pdl(conv_tc_halo2_kernel<32>, grid, th, smem, st, maps, p); break;
-        case 64: lpc_launch_pdl(conv_tc_halo2_kernel<64>, grid, th, smem, st, maps, p); break;
-        case 128: lpc_launch_pdl(conv_tc_halo2_kernel<128>, grid, th, smem, st, maps, p); break;
-        default: lpc_launch_pdl(conv_tc_halo2_kernel<0>, grid, th, smem, st, maps, p); break;
-      }
-    } else
-    switch (Cin) {
-      case 16: if (p.b_resident) { lpc_launch_pdl(conv_tc_halo_kernel<16, 1>, grid, th, smem, st, maps, p); break; }
-      case 32: if (p.b_resident && Cin == 32) { lpc_launch_pdl(conv_tc_halo_kernel<32, 1>, grid, th, smem, st, maps, p); break; }
-      case 64: if (p.b_resident && Cin == 64) { lpc_launch_pdl(conv_tc_halo_kernel<64, 1>, grid, th, smem, st, maps, p); break; }
-      case 128: if (Cin == 128) { if (p.b_resident) lpc_launch_pdl(conv_tc_halo_kernel<128, 1>, grid, th, smem, st, maps, p); else lpc_launch_pdl(conv_tc_halo_kernel<128, 0>, grid, th, smem, st, maps, p); break; }
-      default: lpc_launch_pdl(conv_tc_halo_kernel<0, -1>, grid, th, smem, st, maps, p); break;
+#define HALO_LAUNCH(K_) switch (Cin) {                                               \
+      case 16: lpc_launch_pdl(K_<16>, grid, th, smem, st, maps, p); break;              \
+      case 32: lpc_launch_pdl(K_<32>, grid, th, smem, st, maps, p); break;              \
+      case 64: lpc_launch_pdl(K_<64>, grid, th, smem, st, maps, p); break;              \
+      case 128: lpc_launch_pdl(K_<128>, grid, th, smem, st, maps, p); break;            \
+      default: lpc_launch_pdl(K_<0>, grid, th, smem, st, maps, p); break;               \
     }
+    if (pair) { HALO_LAUNCH(conv_tc_halo2_kernel) } else { HALO_LAUNCH(conv_tc_halo_kernel) }
+#undef HALO_LAUNCH
   }
   else
     lpc_launch_pdl(conv_tc_taps_kernel, grid, threads, smem, (cudaStream_t)stream, maps, p);

@@ -7,12 +7,13 @@
 // halo patch sits at the same shared-memory offset in both), each keeps HALF of the weight rows resident
 // ([n_tile/2][K], which also lets Cout = 128 layers issue N = 128), and the leader CTA's single thread issues M = 256
 // MMAs for the pair.  Signalling:
-//   loaders  (both CTAs, per warp) --arrive.cluster--> leader afull[s]      (count 2 x 4)
+//   patches: each CTA's warp 0 issues its own TMA boxes (cta_group::2 signalling): expect_tx + complete_tx land on the
+//            LEADER's afull[s] (count 2)
 //   leader MMA --commit.multicast--> aempty[s], tfull[b] in BOTH CTAs
 //   epilogue (both CTAs, per warp) --arrive.cluster--> leader tempty[b]     (count 2 x warps per tile)
 //   weights: each CTA TMA-loads its half, then its warp 0 arrives on the leader's wready barrier (count 2)
 template <int CIN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(448, 2)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 2)
 conv_tc_halo2_kernel(const __grid_constant__ TmapPack maps, const __grid_constant__ ConvTcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long bars[2 * MAX_STAGES + 10];
@@ -25,8 +26,6 @@ conv_tc_halo2_kernel(const __grid_constant__ TmapPack maps, const __grid_constan
   const uint32_t smem_base = (bias_addr + (uint32_t)half * 32u + 1023u) & ~1023u;
   const int b_block = half * 128;                                     // bytes of one 64-wide K step of this CTA's half
   const int halo_bytes = p.slabs * p.slab_bytes;
-  const int chunks_px = p.Cin / 8;
-  const int chunks_row = p.pitch / 16;
   const uint32_t a_region = smem_base + (uint32_t)(p.ksteps * b_block);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(&bars[0]);
@@ -45,9 +44,9 @@ conv_tc_halo2_kernel(const __grid_constant__ TmapPack maps, const __grid_constan
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&maps.b);
-    if (p.a_tma) prefetch_tmap(&maps.a[0]);
+    prefetch_tmap(&maps.a[0]);
     for (int s = 0; s < MAX_STAGES; ++s) {
-      mbar_init(afull_bar(s), p.a_tma ? 2 : 2 * (HALO_LOADERS / 32));
+      mbar_init(afull_bar(s), 2);
       mbar_init(aempty_bar(s), 1);
     }
     for (int b = 0; b < 4; ++b) {
@@ -74,7 +73,7 @@ conv_tc_halo2_kernel(const __grid_constant__ TmapPack maps, const __grid_constan
       mbar_wait(bfull_bar, 0);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive_rank(wready_bar, 0);
-      if (p.a_tma) {
+      {
         // Halo patches by TMA (as in conv_tc_halo_kernel): each CTA loads its own tile's patch into its own shared memory;
         // both report (expect_tx + complete_tx) to the LEADER's afull barrier (count 2), which the MMA thread waits on.
         pdl_wait();
@@ -93,70 +92,6 @@ conv_tc_halo2_kernel(const __grid_constant__ TmapPack maps, const __grid_constan
         }
       }
     }
-  } else if (warp >= 2 + 4 * p.epi_split) {
-    // ===== activation loaders (as in conv_tc_halo_kernel; one arrival per warp on the leader's barrier) =====
-    const int lt = threadIdx.x - (2 + 4 * p.epi_split) * 32;
-    const int look = p.a_bufs >= 6 ? 3 : (p.a_bufs >= 4 ? 2 : 1);
-    int ppy[2], ppx[2];
-    uint32_t row_off[2], phase[2];
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int pix = lt + q * HALO_LOADERS;
-      ppy[q] = pix / HALO_PW;
-      ppx[q] = pix - ppy[q] * HALO_PW;
-      row_off[q] = (uint32_t)((ppy[q] * HALO_SPW + ppx[q]) * p.pitch);
-      phase[q] = (row_off[q] >> 7) & (uint32_t)(chunks_row - 1);
-    }
-    const bool second = lt + HALO_LOADERS < HALO_PW * HALO_PH;
-    const int img_elems = p.H * p.W * (int)p.x_ld;
-    int tcount = 0;
-    for (int mp = mp_first; 2 * mp < p.m_tiles; mp += mp_step, ++tcount) {
-      const int m = 2 * mp + (int)rank;
-      const bool live = m < p.m_tiles;                    // odd tile count: the last pair's second CTA only signals
-      const TileCoord t = tile_coord(p, live ? m : 0);
-      const int ab = tcount % p.a_bufs;
-      mbar_wait(aempty_bar(ab), (uint32_t)(((tcount / p.a_bufs) & 1) ^ 1));
-      const uint32_t a_dst = a_region + (uint32_t)(ab * halo_bytes);
-      const bf16* img_base = p.x + (long long)t.img * img_elems;
-      if (live) {
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          if (q == 0 || second) {
-            const int iy = t.y0 - 1 + ppy[q], ix = t.x0 - 1 + ppx[q];
-            const bool in = (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
-            const bf16* src = in ? img_base + (iy * p.W + ix) * (int)p.x_ld : p.x;
-            const uint32_t nb = in ? 16u : 0u;
-            uint32_t dst_row = a_dst + row_off[q];
-            if (CIN > 0) {
-              constexpr int CROW = (CIN < 64 ? CIN : 64) / 8, NSLAB = (CIN + 63) / 64;
-              constexpr int SLABB = HALO_PH * HALO_SPW * (CIN < 64 ? CIN : 64) * 2;
-#pragma unroll
-              for (int sl = 0; sl < NSLAB; ++sl)
-#pragma unroll
-                for (int cw = 0; cw < CROW; ++cw)
-                  cp_async16(dst_row + (uint32_t)(sl * SLABB) + (((uint32_t)cw ^ phase[q]) << 4), src + (in ? (sl * CROW + cw) * 8 : 0), nb);
-            } else {
-              for (int c0 = 0; c0 < chunks_px; c0 += chunks_row, dst_row += (uint32_t)p.slab_bytes)
-#pragma unroll 4
-                for (int cw = 0; cw < chunks_row; ++cw)
-                  cp_async16(dst_row + (((uint32_t)cw ^ phase[q]) << 4), src + (in ? (c0 + cw) * 8 : 0), nb);
-            }
-          }
-        }
-      }
-      cp_async_commit();
-      if (tcount >= look) {
-        cp_async_wait_dyn(look);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive_rank(afull_bar((tcount - look) % p.a_bufs), 0);
-      }
-    }
-    cp_async_wait_dyn(0);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncwarp();
-    if (lane == 0)
-      for (int i = (tcount > look ? tcount - look : 0); i < tcount; ++i) mbar_arrive_rank(afull_bar(i % p.a_bufs), 0);
   } else if (warp == 1) {
     // ===== MMA issuer: the leader CTA's elected thread, M = 256 over the pair =====
     if (rank == 0 && elect_one_sync()) {
@@ -213,12 +148,13 @@ conv_tc_halo2_kernel(const __grid_constant__ TmapPack maps, const __grid_constan
       if (p.epi_alt && (tcount & 1) != ectx.group) continue;
       const int m = 2 * mp + (int)rank;
       const int buf = tcount & (p.n_acc - 1);
+      const bool live = m < p.m_tiles;
+      const TileCoord t = tile_coord(p, live ? m : 0);
+      ResPre rp;
+      if (live) res_prefetch(p, ectx, t.img, t.x0, t.y0, n0, rp);
       mbar_wait(tfull_bar(buf), (uint32_t)((tcount >> p.acc_shift) & 1));
       tc_fence_after();
-      if (m < p.m_tiles) {
-        const TileCoord t = tile_coord(p, m);
-        epilogue_tile(p, ectx, tmem_base + (uint32_t)(buf * p.acc_cols), t.img, t.x0, t.y0, n0);
-      }
+      if (live) epilogue_tile(p, ectx, tmem_base + (uint32_t)(buf * p.acc_cols), t.img, t.x0, t.y0, n0, &rp);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_rank(tempty_bar(buf), 0);
