@@ -81,6 +81,15 @@ int lpc_conv2d_tc_kpad(int Cin, int k);
 /* Kernel selection override for tests / profiling: 0 = auto, 1 = always the per-tap TMA kernel, 2 = the halo-patch
  * kernel for every 3x3 stride-1 conv whose buffers fit.  Returns the previous mode. */
 int lpc_conv2d_tc_set_mode(int mode);
+/* lpc_conv2d_tc that ALSO writes, per output pixel, the order-preserving uint32 key of max over the output channels of
+ * the (bf16-rounded) outputs: keys[b * img_stride + offset + oy * Wo + ox].  Used on the last conv of the v10Detect class
+ * branch (head.py:504-505) so that stage 1 of ops.v10postprocess (utils/ops.py:853, `scores.amax(-1)`) costs no extra
+ * pass over the class logits.  Returns LPC_E_UNSUPPORTED (nothing launched) when Cout is split over several N tiles or
+ * epilogue warps; rowmax_keys == NULL behaves exactly like lpc_conv2d_tc. */
+int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W, int Cin, const void* w, const float* bias,
+                         int k, int stride, int pad, int Cout, void* y, int y_ld, int act,
+                         const float* chan_scale, const void* res, int res_ld,
+                         unsigned int* rowmax_keys, long long rowmax_img_stride, int rowmax_offset, void* stream);
 /* 1 if lpc_conv2d_tc accepts this shape, else 0. */
 int lpc_conv2d_tc_supported(int Cin, int Cout, int k, int stride, int pad, int x_ld, int y_ld);
 
@@ -160,6 +169,13 @@ int lpc_v10_decode_topk(int dtype, const void* raw0, const void* raw1, const voi
                         int B, int H0, int W0, int nc, const float* strides3_host, int K,
                         int img_h, int img_w, void* workspace, size_t ws_bytes,
                         float* dets, int* anchor_idx, void* stream);
+/* lpc_v10_decode_topk with the per-anchor keys optionally ALREADY in the workspace (keys_ready != 0): written by
+ * lpc_conv2d_tc_rowmax on the three class-branch convs (keys[b * A + level_offset + cell]); stage 1 then needs no pass
+ * over the class logits. */
+int lpc_v10_decode_topk_keys(int dtype, const void* raw0, const void* raw1, const void* raw2, int ld,
+                             int B, int H0, int W0, int nc, const float* strides3_host, int K,
+                             int img_h, int img_w, void* workspace, size_t ws_bytes, int keys_ready,
+                             float* dets, int* anchor_idx, void* stream);
 int lpc_v10_postprocess(const float* preds, long long stride_b, long long stride_a, long long stride_c,
                         int B, int A, int nc, int K, void* workspace, size_t ws_bytes,
                         float* boxes, float* scores, long long* labels, void* stream);

@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "liblpcyolo.so")
 
 BF16, F32 = 0, 1
+E_ARG, E_UNSUPPORTED, E_CUDA, E_WORKSPACE = -1, -2, -3, -4
 ACT_NONE, ACT_SILU, ACT_MISH, ACT_SIGMOID, ACT_RELU = 0, 1, 2, 3, 4
 
 _p, _i, _ll, _f32p, _sz = C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_size_t
@@ -23,6 +24,7 @@ SIGNATURES = {
     "lpc_launch_count": (C.c_ulonglong, []),
     "lpc_conv2d_direct": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _f32p, _i, _i, _i, _i, _p, _i, _i, _f32p, _p, _i, _p]),
     "lpc_conv2d_tc": (_i, [_p, _i, _i, _i, _i, _i, _p, _f32p, _i, _i, _i, _i, _p, _i, _i, _f32p, _p, _i, _p]),
+    "lpc_conv2d_tc_rowmax": (_i, [_p, _i, _i, _i, _i, _i, _p, _f32p, _i, _i, _i, _i, _p, _i, _i, _f32p, _p, _i, _p, _ll, _i, _p]),
     "lpc_conv2d_tc_kpad": (_i, [_i, _i]),
     "lpc_conv2d_tc_set_mode": (_i, [_i]),
     "lpc_conv2d_tc_supported": (_i, [_i, _i, _i, _i, _i, _i, _i]),
@@ -45,6 +47,8 @@ SIGNATURES = {
     "lpc_v10_decode": (_i, [_i, _p, _p, _p, _i, _i, _i, _i, _i, C.POINTER(C.c_float), _f32p, _p]),
     "lpc_v10_decode_topk": (_i, [_i, _p, _p, _p, _i, _i, _i, _i, _i, C.POINTER(C.c_float), _i, _i, _i, _p, _sz,
                                  _f32p, _p, _p]),
+    "lpc_v10_decode_topk_keys": (_i, [_i, _p, _p, _p, _i, _i, _i, _i, _i, C.POINTER(C.c_float), _i, _i, _i, _p, _sz, _i,
+                                      _f32p, _p, _p]),
     "lpc_v10_postprocess": (_i, [_f32p, _ll, _ll, _ll, _i, _i, _i, _i, _p, _sz, _f32p, _f32p, _p, _p]),
 }
 

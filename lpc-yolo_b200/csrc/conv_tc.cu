@@ -73,6 +73,9 @@ struct ConvTcParams {
   bf16* y;
   long long y_ld;
   int act;
+  unsigned int* rowmax;              // optional: per output pixel, order-preserving key of max_c of the bf16 outputs (fused tail stage 1)
+  long long rowmax_img;              // keys between images
+  int rowmax_off;                    // first key of this map inside an image's key array
 };
 
 // ---- bias through the tensor core ---------------------------------------------------------------------------
@@ -117,7 +120,8 @@ struct ResPre {
 
 // ---- epilogue: one accumulator tile (128 rows x n_tile columns) -> NHWC bf16 --------------------------------
 template <int ACT>
-__device__ __forceinline__ void store16(const uint32_t* v, bf16* yrow, const bf16* rrow, const float* srow, bool no_store = false, bool has_pre = false, uint4 pre0 = uint4(), uint4 pre1 = uint4()) {
+__device__ __forceinline__ void store16(const uint32_t* v, bf16* yrow, const bf16* rrow, const float* srow, bool no_store = false, bool has_pre = false, uint4 pre0 = uint4(), uint4 pre1 = uint4(),
+                                        float* row_max = nullptr) {
   float f[16];
 #pragma unroll
   for (int i = 0; i < 16; i += 2) {
@@ -146,6 +150,12 @@ __device__ __forceinline__ void store16(const uint32_t* v, bf16* yrow, const bf1
 #pragma unroll
     for (int i = 0; i < 8; ++i) f[8 + i] += r8[i];
   }
+  if (row_max) {
+    float m = *row_max;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) m = fmaxf(m, f[i]);
+    *row_max = m;
+  }
   Vec<bf16> o, o2;
   o.pack(f);
   o2.pack(f + 8);
@@ -159,7 +169,7 @@ __device__ __forceinline__ void store16(const uint32_t* v, bf16* yrow, const bf1
 
 template <int ACT>
 __device__ __forceinline__ void epilogue_cols(uint32_t trow, int c, int c_end, bool valid, bf16* yrow, const bf16* rrow, const float* srow, bool no_store,
-                                              const ResPre* pre) {
+                                              const ResPre* pre, float* row_max) {
   const int c_first = c;
   for (; c < c_end; c += 16) {
     uint32_t v0[16];
@@ -172,7 +182,7 @@ __device__ __forceinline__ void epilogue_cols(uint32_t trow, int c, int c_end, b
       pa = ci == 0 ? pre->v[0] : pre->v[2];
       pb = ci == 0 ? pre->v[1] : pre->v[3];
     }
-    if (valid) store16<ACT>(v0, yrow + c, rrow ? rrow + c : nullptr, srow ? srow + c : nullptr, no_store, hp, pa, pb);
+    if (valid) store16<ACT>(v0, yrow + c, rrow ? rrow + c : nullptr, srow ? srow + c : nullptr, no_store, hp, pa, pb, row_max);
   }
 }
 
@@ -220,12 +230,21 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, const EpiCt
   const uint32_t trow = tmem_acc + e.lane_off;
   const bool ns = (p.dbg & 32) != 0;
   const ResPre* pre = (rp && rrow) ? rp : nullptr;
+  float rmax = -INFINITY;
+  float* rmp = p.rowmax ? &rmax : nullptr;
   switch (p.act) {
-    case LPC_ACT_MISH: epilogue_cols<LPC_ACT_MISH>(trow, e.c0, e.c_end, valid, yrow, rrow, srow, ns, pre); break;
-    case LPC_ACT_SILU: epilogue_cols<LPC_ACT_SILU>(trow, e.c0, e.c_end, valid, yrow, rrow, srow, ns, pre); break;
-    case LPC_ACT_NONE: epilogue_cols<LPC_ACT_NONE>(trow, e.c0, e.c_end, valid, yrow, rrow, srow, ns, pre); break;
-    case LPC_ACT_SIGMOID: epilogue_cols<LPC_ACT_SIGMOID>(trow, e.c0, e.c_end, valid, yrow, rrow, srow, ns, pre); break;
-    default: epilogue_cols<LPC_ACT_RELU>(trow, e.c0, e.c_end, valid, yrow, rrow, srow, ns, pre); break;
+    case LPC_ACT_MISH: epilogue_cols<LPC_ACT_MISH>(trow, e.c0, e.c_end, valid, yrow, rrow, srow, ns, pre, rmp); break;
+    case LPC_ACT_SILU: epilogue_cols<LPC_ACT_SILU>(trow, e.c0, e.c_end, valid, yrow, rrow, srow, ns, pre, rmp); break;
+    case LPC_ACT_NONE: epilogue_cols<LPC_ACT_NONE>(trow, e.c0, e.c_end, valid, yrow, rrow, srow, ns, pre, rmp); break;
+    case LPC_ACT_SIGMOID: epilogue_cols<LPC_ACT_SIGMOID>(trow, e.c0, e.c_end, valid, yrow, rrow, srow, ns, pre, rmp); break;
+    default: epilogue_cols<LPC_ACT_RELU>(trow, e.c0, e.c_end, valid, yrow, rrow, srow, ns, pre, rmp); break;
+  }
+  if (p.rowmax && valid) {
+    // the thread owns the whole output row (host guarantees one N tile, unsplit columns): max of the ROUNDED outputs =
+    // rounding of the max (round-to-nearest is monotonic); key as in tail.cu (order-preserving uint32 of the float)
+    const uint32_t u = __float_as_uint(__bfloat162float(__float2bfloat16_rn(rmax)));
+    const long long bimg = pix / p.pix_per_img;          // 1x1 convs run on the flat [B*H*W] view: recover (image, pixel)
+    p.rowmax[bimg * p.rowmax_img + p.rowmax_off + (pix - bimg * p.pix_per_img)] = u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
   }
 }
 
@@ -680,6 +699,13 @@ extern "C" int lpc_conv2d_tc_set_mode(int mode) {
 extern "C" int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int Cin, const void* w, const float* bias,
                              int k, int stride, int pad, int Cout, void* y, int y_ld, int act,
                              const float* chan_scale, const void* res, int res_ld, void* stream) {
+  return lpc_conv2d_tc_rowmax(x, x_ld, B, H, W, Cin, w, bias, k, stride, pad, Cout, y, y_ld, act, chan_scale, res, res_ld, nullptr, 0, 0, stream);
+}
+
+extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W, int Cin, const void* w, const float* bias,
+                                    int k, int stride, int pad, int Cout, void* y, int y_ld, int act,
+                                    const float* chan_scale, const void* res, int res_ld,
+                                    unsigned int* rowmax_keys, long long rowmax_img_stride, int rowmax_offset, void* stream) {
   LPC_REQUIRE(x && w && y, "conv2d_tc: null pointer");
   LPC_REQUIRE(B > 0 && H > 0 && W > 0, "conv2d_tc: bad shape");
   if (!lpc_conv2d_tc_supported(Cin, Cout, k, stride, pad, x_ld, y_ld))
@@ -709,6 +735,9 @@ extern "C" int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int C
   p.y = (bf16*)y;
   p.y_ld = y_ld;
   p.act = act;
+  p.rowmax = rowmax_keys;
+  p.rowmax_img = rowmax_img_stride;
+  p.rowmax_off = rowmax_offset;
   { const char* e = getenv("LPC_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
 
   // ---- choose the kernel -------------------------------------------------------------------------------
@@ -896,6 +925,8 @@ extern "C" int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int C
     cudaMemset(trace_buf, 0, 4 * 64 * 4 * 8);
     p.trace = trace_buf;
   }
+  if (p.rowmax && !(p.n_tiles == 1 && (p.epi_split == 1 || p.epi_alt)))
+    LPC_FAIL(LPC_E_UNSUPPORTED, "conv2d_tc_rowmax: needs one N tile whose columns are not split between epilogue warps (Cout=%d)", Cout);
   if (halo) {
     LPC_REQUIRE((long long)H * W * x_ld < (1ll << 31), "conv2d_tc: image too large for 32-bit offsets");
     const unsigned th = threads;

@@ -68,7 +68,7 @@ __global__ void space_to_depth_kernel(const T* __restrict__ x, int x_ld, int B, 
   st_vec<T>(y + ((long long)(n * Ho + oy) * Wo + ox) * y_ld + q * C + cv * V, v);
 }
 
-// y[p, j] = x[p, 2j], y[p, C/2 + j] = x[p, 2j+1]
+// y[p, j] = x[p, 2j], y[p, C/2 + j] = x[p, 2j+1]  (LPC's channel de-interleave, block.py:5824)
 template <typename T>
 __global__ void deinterleave_kernel(const T* __restrict__ x, int x_ld, long long npix, int C, T* __restrict__ y, int y_ld) {
   pdl_trigger();
@@ -79,6 +79,31 @@ __global__ void deinterleave_kernel(const T* __restrict__ x, int x_ld, long long
   const long long p = idx / C;
   const int src = c < C / 2 ? 2 * c : 2 * (c - C / 2) + 1;
   y[p * y_ld + c] = x[p * x_ld + src];
+}
+// Vector version: a thread takes 32 input bytes (16 bf16 / 8 fp32 channels) and writes one 16-byte vector of the even
+// and one of the odd channels (byte permutes, no arithmetic).  Needs C % (2 * V) == 0 and 16-byte aligned rows.
+template <typename T>
+__global__ void deinterleave_vec_kernel(const T* __restrict__ x, int x_ld, unsigned npix, int C, T* __restrict__ y, int y_ld) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int V = Vec<T>::N;
+  const int groups = C / (2 * V);
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= npix * (unsigned)groups) return;
+  const unsigned p = idx / (unsigned)groups;
+  const int g = (int)(idx - p * (unsigned)groups);
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(x + (long long)p * x_ld + g * 2 * V));
+  const uint4 b = __ldg(reinterpret_cast<const uint4*>(x + (long long)p * x_ld + g * 2 * V + V));
+  uint4 ev, od;
+  if (sizeof(T) == 2) {
+    ev = make_uint4(__byte_perm(a.x, a.y, 0x5410), __byte_perm(a.z, a.w, 0x5410), __byte_perm(b.x, b.y, 0x5410), __byte_perm(b.z, b.w, 0x5410));
+    od = make_uint4(__byte_perm(a.x, a.y, 0x7632), __byte_perm(a.z, a.w, 0x7632), __byte_perm(b.x, b.y, 0x7632), __byte_perm(b.z, b.w, 0x7632));
+  } else {
+    ev = make_uint4(a.x, a.z, b.x, b.z);
+    od = make_uint4(a.y, a.w, b.y, b.w);
+  }
+  *reinterpret_cast<uint4*>(y + (long long)p * y_ld + g * V) = ev;
+  *reinterpret_cast<uint4*>(y + (long long)p * y_ld + C / 2 + g * V) = od;
 }
 
 template <typename T>
@@ -347,6 +372,15 @@ extern "C" int lpc_space_to_depth(int dtype, const void* x, int x_ld, int B, int
 extern "C" int lpc_channel_deinterleave(int dtype, const void* x, int x_ld, long long npix, int C, void* y, int y_ld, void* stream) {
   LPC_REQUIRE(x && y && C % 2 == 0 && x_ld >= C && y_ld >= C, "channel_deinterleave: bad argument");
   cudaStream_t s = (cudaStream_t)stream;
+  {
+    const int V = dtype == LPC_F32 ? 4 : 8;
+    if (C % (2 * V) == 0 && x_ld % V == 0 && y_ld % V == 0 && aligned16(x) && aligned16(y) && npix * (C / (2 * V)) < (1ll << 32) &&
+        (dtype == LPC_F32 || dtype == LPC_BF16)) {
+      const int gv = cdiv(npix * (C / (2 * V)), 256);
+      DISPATCH_T(dtype, (lpc_launch_pdl(deinterleave_vec_kernel<float>, gv, 256, 0, s, (const float*)x, x_ld, (unsigned)npix, C, (float*)y, y_ld)),
+                 (lpc_launch_pdl(deinterleave_vec_kernel<bf16>, gv, 256, 0, s, (const bf16*)x, x_ld, (unsigned)npix, C, (bf16*)y, y_ld)), "channel_deinterleave")
+    }
+  }
   const int g = cdiv(npix * C, 256);
   DISPATCH_T(dtype, (lpc_launch_pdl(deinterleave_kernel<float>, g, 256, 0, s, (const float*)x, x_ld, npix, C, (float*)y, y_ld)),
              (lpc_launch_pdl(deinterleave_kernel<bf16>, g, 256, 0, s, (const bf16*)x, x_ld, npix, C, (bf16*)y, y_ld)), "channel_deinterleave")

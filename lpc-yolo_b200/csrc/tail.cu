@@ -444,6 +444,13 @@ extern "C" int lpc_v10_decode(int dtype, const void* raw0, const void* raw1, con
 extern "C" int lpc_v10_decode_topk(int dtype, const void* raw0, const void* raw1, const void* raw2, int ld, int B,
                                    int H0, int W0, int nc, const float* strides, int K, int img_h, int img_w,
                                    void* workspace, size_t ws_bytes, float* dets, int* anchor_idx, void* stream) {
+  return lpc_v10_decode_topk_keys(dtype, raw0, raw1, raw2, ld, B, H0, W0, nc, strides, K, img_h, img_w, workspace, ws_bytes, 0, dets,
+                                  anchor_idx, stream);
+}
+
+extern "C" int lpc_v10_decode_topk_keys(int dtype, const void* raw0, const void* raw1, const void* raw2, int ld, int B,
+                                        int H0, int W0, int nc, const float* strides, int K, int img_h, int img_w,
+                                        void* workspace, size_t ws_bytes, int keys_ready, float* dets, int* anchor_idx, void* stream) {
   TailSrc s;
   if (int e = make_raw_src(s, "v10_decode_topk", dtype, raw0, raw1, raw2, ld, B, H0, W0, nc, strides)) return e;
   LPC_REQUIRE(dets && workspace, "v10_decode_topk: null pointer");
@@ -454,15 +461,19 @@ extern "C" int lpc_v10_decode_topk(int dtype, const void* raw0, const void* raw1
   const int g = cdiv((long long)B * s.A, 256);
   if (dtype == LPC_BF16) {
     const bool vec = (nc % 8 == 0) && (ld % 8 == 0) && aligned16(raw0) && aligned16(raw1) && aligned16(raw2);
-    if (vec) lpc_launch_pdl(amax_keys_kernel<bf16, true>, cdiv((long long)B * s.A * 4, 256), 256, 0, st, s, B, amax);
-    else lpc_launch_pdl(amax_keys_kernel<bf16, false>, g, 256, 0, st, s, B, amax);
-    LPC_CHECK_LAUNCH("amax_keys");
+    if (!keys_ready) {
+      if (vec) lpc_launch_pdl(amax_keys_kernel<bf16, true>, cdiv((long long)B * s.A * 4, 256), 256, 0, st, s, B, amax);
+      else lpc_launch_pdl(amax_keys_kernel<bf16, false>, g, 256, 0, st, s, B, amax);
+      LPC_CHECK_LAUNCH("amax_keys");
+    }
     return launch_select<bf16, 2, 0>(s, B, K, amax, img_h, img_w, dets, anchor_idx, nullptr, nullptr, nullptr, st);
   } else if (dtype == LPC_F32) {
     const bool vec = (nc % 4 == 0) && (ld % 4 == 0) && aligned16(raw0) && aligned16(raw1) && aligned16(raw2);
-    if (vec) lpc_launch_pdl(amax_keys_kernel<float, true>, cdiv((long long)B * s.A * 4, 256), 256, 0, st, s, B, amax);
-    else lpc_launch_pdl(amax_keys_kernel<float, false>, g, 256, 0, st, s, B, amax);
-    LPC_CHECK_LAUNCH("amax_keys");
+    if (!keys_ready) {
+      if (vec) lpc_launch_pdl(amax_keys_kernel<float, true>, cdiv((long long)B * s.A * 4, 256), 256, 0, st, s, B, amax);
+      else lpc_launch_pdl(amax_keys_kernel<float, false>, g, 256, 0, st, s, B, amax);
+      LPC_CHECK_LAUNCH("amax_keys");
+    }
     return launch_select<float, 4, 0>(s, B, K, amax, img_h, img_w, dets, anchor_idx, nullptr, nullptr, nullptr, st);
   }
   LPC_FAIL(LPC_E_ARG, "v10_decode_topk: unknown dtype %d", dtype);

@@ -140,7 +140,7 @@ def pack_u8(src, dtype, top=0, left=0, H=None, W=None, pad_value=114, swap_rb=Tr
     return buf.permute(0, 3, 1, 2)[:, :3]
 
 
-def conv2d(x, pc, out=None, res=None, chan_scale=None):
+def conv2d(x, pc, out=None, res=None, chan_scale=None, rowmax=None):
     """Dense conv through a PackedConv ``pc`` (see pack.py). Chooses tcgen05 when the shape allows."""
     B, Cin, H, W = x.shape
     assert Cin == pc.cin, (Cin, pc.cin)
@@ -165,7 +165,22 @@ def conv2d(x, pc, out=None, res=None, chan_scale=None):
     nbytes = x.element_size() * (B * H * W * Cin + B * Ho * Wo * pc.cout * (2 if res is not None else 1) + pc.cout * Cin * pc.k * pc.k)
     tag = f"{Cin}->{pc.cout} k{pc.k}s{pc.s} {H}x{W} B{B}"
     if use_tc:
-        def launch(keep=(x, out, res, chan_scale, pc)):
+        # rowmax = (uint8 workspace tensor, keys per image, first key of this map): the conv also emits the per-pixel key
+        # of max_c(output) for the fused tail (lpc_conv2d_tc_rowmax); rowmax["ok"] reports whether the kernel took it
+        rm = None
+        if rowmax is not None:
+            rm = (C.c_void_p(rowmax["ws"].data_ptr()), int(rowmax["A"]), int(rowmax["off"]))
+
+        def launch(keep=(x, out, res, chan_scale, pc, rowmax)):
+            if rm is not None:
+                st = L.lpc_conv2d_tc_rowmax(xp, xld, B, H, W, Cin, _fp(pc.w_tc), _fp(pc.bias), pc.k, pc.s, pc.p, pc.cout, yp, yld,
+                                            pc.act, _fp(chan_scale), rp or None, rld, rm[0], rm[1], rm[2], _stream())
+                if st == 0:
+                    rowmax["ok"] = rowmax.get("ok", True)
+                    return
+                if st != _lib.E_UNSUPPORTED:
+                    check(st, "conv2d_tc_rowmax")
+                rowmax["ok"] = False          # shape not taken: plain conv, the tail runs its own key pass
             check(L.lpc_conv2d_tc(xp, xld, B, H, W, Cin, _fp(pc.w_tc), _fp(pc.bias), pc.k, pc.s, pc.p, pc.cout, yp, yld,
                                   pc.act, _fp(chan_scale), rp or None, rld, _stream()), "conv2d_tc")
         if REPLAY is not None:
@@ -173,6 +188,8 @@ def conv2d(x, pc, out=None, res=None, chan_scale=None):
         with _prof("conv2d_tc", flops, nbytes, tag):
             launch()
     else:
+        if rowmax is not None:
+            rowmax["ok"] = False
         with _prof("conv2d_direct", flops, nbytes, tag):
             check(L.lpc_conv2d_direct(dt_code(x.dtype), xp, xld, B, H, W, Cin, _fp(pc.w_direct), _fp(pc.bias), pc.k, pc.s,
                                       pc.p, pc.cout, yp, yld, pc.act, _fp(chan_scale), rp or None, rld, _stream()),
@@ -334,7 +351,13 @@ def v10_decode(raw, strides, nc):
     return y
 
 
-def v10_decode_topk(raw, strides, nc, max_det=300, img_hw=None, return_index=False):
+def topk_workspace(B, A, max_det, device):
+    """Workspace of the fused tail (per-anchor keys first): allocate it BEFORE the head convs to let them fill the keys."""
+    n = _lib.lib().lpc_v10_topk_workspace_bytes(B, A, max_det)
+    return torch.empty((n,), dtype=torch.uint8, device=device)
+
+
+def v10_decode_topk(raw, strides, nc, max_det=300, img_hw=None, return_index=False, ws=None, keys_ready=False):
     """Fused decode + v10postprocess + xywh2xyxy (+clip): -> dets [B,K,6] fp32 (x1,y1,x2,y2,score,label)."""
     ptrs, ld, B, Ct, H0, W0, st = _raw_args(raw, strides)
     assert Ct == 64 + nc
@@ -342,15 +365,17 @@ def v10_decode_topk(raw, strides, nc, max_det=300, img_hw=None, return_index=Fal
     dev = raw[0].device
     L = _lib.lib()
     ws_bytes = L.lpc_v10_topk_workspace_bytes(B, A, max_det)
-    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    if ws is None:
+        ws, keys_ready = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev), False
+    assert ws.numel() >= ws_bytes
     dets = torch.empty((B, max_det, 6), dtype=torch.float32, device=dev)
     aidx = torch.empty((B, max_det), dtype=torch.int32, device=dev) if return_index else None
     ih, iw = (img_hw if img_hw is not None else (0, 0))
     # algorithmic bytes: raw maps read once + detections written
     nbytes = B * A * (64 + nc) * raw[0].element_size() + B * max_det * 6 * 4
     def launch(keep=(raw, ws, dets, aidx)):
-        check(L.lpc_v10_decode_topk(dt_code(raw[0].dtype), ptrs[0], ptrs[1], ptrs[2], ld, B, H0, W0, nc, st, max_det, ih, iw,
-                                    _fp(ws), ws_bytes, _fp(dets), _fp(aidx), _stream()), "v10_decode_topk")
+        check(L.lpc_v10_decode_topk_keys(dt_code(raw[0].dtype), ptrs[0], ptrs[1], ptrs[2], ld, B, H0, W0, nc, st, max_det, ih, iw,
+                                         _fp(ws), ws_bytes, int(bool(keys_ready)), _fp(dets), _fp(aidx), _stream()), "v10_decode_topk")
     if REPLAY is not None:
         REPLAY.append(("v10_decode_topk", launch, 0.0, nbytes, ""))
     with _prof("v10_decode_topk", 0.0, nbytes):

@@ -32,9 +32,9 @@ class _Plain1x1(LpcModule):
         w, b = pack.fold_bn(self.weight, self.bias, None)
         return pack.PackedConv(w, b, 1, 1, 0, ACT_NONE, dtype, device)
 
-    def forward(self, x, out=None):
+    def forward(self, x, out=None, rowmax=None):
         x = self._in(x)
-        return F.conv2d(x, self._packed(x, self._build), out)
+        return F.conv2d(x, self._packed(x, self._build), out, rowmax=rowmax)
 
 
 class Detect(LpcModule):
@@ -111,8 +111,11 @@ class v10Detect(Detect):
         self.one2one_cv2 = copy.deepcopy(self.cv2)
         self.one2one_cv3 = copy.deepcopy(self.cv3)
 
-    def forward_feat(self, x, cv2, cv3):
+    def forward_feat(self, x, cv2, cv3, keys=None):
+        """keys: optional {"ws": tail workspace, "A": anchors per image}: the last class-branch conv of every level also
+        writes the per-anchor max-logit keys there (stage 1 of v10postprocess fused into the conv epilogue)."""
         y = []
+        off = 0
         for i in range(self.nl):
             xi = self._in(x[i])
             B, _, H, W = xi.shape
@@ -120,7 +123,13 @@ class v10Detect(Detect):
             cv2[i][2](cv2[i][1](cv2[i][0](xi)), out=raw[:, : 4 * self.reg_max])
             t = cv3[i][0][1](cv3[i][0][0](xi))
             t = cv3[i][1][1](cv3[i][1][0](t))
-            cv3[i][2](t, out=raw[:, 4 * self.reg_max:])
+            if keys is not None:
+                rm = {"ws": keys["ws"], "A": keys["A"], "off": off}
+                cv3[i][2](t, out=raw[:, 4 * self.reg_max:], rowmax=rm)
+                keys["ok"] = keys.get("ok", True) and rm.get("ok", False)
+            else:
+                cv3[i][2](t, out=raw[:, 4 * self.reg_max:])
+            off += H * W
             y.append(raw)
         return y
 
@@ -138,8 +147,12 @@ class v10Detect(Detect):
 
     def detections(self, x, max_det=None, img_hw=None):
         """Engine fast path: raw one2one maps -> fused decode + top-k (+clip) -> [B,K,6]; y is never built."""
-        one2one = self.forward_feat(x, self.one2one_cv2, self.one2one_cv3)
-        return F.v10_decode_topk(one2one, [float(s) for s in self.stride], self.nc, max_det or self.max_det, img_hw)
+        K = max_det or self.max_det
+        B = x[0].shape[0]
+        A = sum(int(f.shape[2]) * int(f.shape[3]) for f in x)
+        keys = {"ws": F.topk_workspace(B, A, K, x[0].device), "A": A}
+        one2one = self.forward_feat(x, self.one2one_cv2, self.one2one_cv3, keys=keys)
+        return F.v10_decode_topk(one2one, [float(s) for s in self.stride], self.nc, K, img_hw, ws=keys["ws"], keys_ready=keys.get("ok", False))
 
     def bias_init(self):
         super().bias_init()

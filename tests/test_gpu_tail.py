@@ -130,3 +130,30 @@ def test_v10postprocess_api(oracle, Fn, pkg):
         sep[:, -1] = False
         assert torch.equal(l.cpu()[sep], ol[sep]) and torch.equal(b.cpu()[sep], ob[sep])
         assert l.dtype == torch.int64
+
+
+def test_conv_rowmax_keys_bit_exact(pkg, Fn):
+    """lpc_conv2d_tc_rowmax (stage 1 of v10postprocess fused into the class-branch conv): keys == key(max_c(output))."""
+    head = importlib.import_module("lpc-yolo_b200.nn.modules.head")
+    torch.manual_seed(5)
+    B, C1, NC, H, W = 3, 80, 80, 20, 12
+    conv = head._Plain1x1(C1, NC).cuda().eval()
+    with torch.no_grad():
+        conv.weight.normal_(0, 0.2)
+        conv.bias.normal_(0, 1.0)
+    x = Fn.new_act(B, C1, H, W, torch.bfloat16, "cuda")
+    x.normal_()
+    A, off = 2 * H * W + 7, H * W + 7                     # keys land at an offset inside a larger per-image key array
+    ws = torch.zeros((B * A * 4 + 256,), dtype=torch.uint8, device="cuda")
+    out = Fn.new_act(B, 64 + NC, H, W, torch.bfloat16, "cuda")
+    rm = {"ws": ws, "A": A, "off": off}
+    with torch.no_grad():
+        conv(x, out=out[:, 64:], rowmax=rm)
+    assert rm.get("ok") is True
+    torch.cuda.synchronize()
+    keys = ws[: B * A * 4].view(torch.int32).view(B, A)[:, off: off + H * W].cpu()
+    m = out[:, 64:].float().amax(1).reshape(B, H * W).cpu()                      # max over classes of the stored bf16 logits
+    u = m.view(torch.int32)
+    want = torch.where(u < 0, ~u, u ^ torch.tensor(-2 ** 31, dtype=torch.int32))    # fkey(): order-preserving uint32 of the float
+    assert torch.equal(keys, want)
+    assert int(ws[: B * A * 4].view(torch.int32).view(B, A)[:, :off].abs().sum()) == 0   # nothing written outside the slot
