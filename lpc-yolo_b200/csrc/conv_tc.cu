@@ -741,7 +741,7 @@ extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W
   { const char* e = getenv("LPC_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
 
   // ---- choose the kernel -------------------------------------------------------------------------------
-  bool halo = false, pair = false;
+  bool halo = false, pair = false, tpair = false;   // pair: CTA-pair halo kernel, tpair: CTA-pair per-tap kernel
   if (k == 3 && stride == 1 && g_force_mode != 1 && (Cin == 16 || Cin == 32 || Cin % 64 == 0) && Cin <= 256) {
     const long long tiles = (long long)((Wo + HALO_TW - 1) / HALO_TW) * ((Ho + HALO_TH - 1) / HALO_TH);
     const double eff = (double)Ho * Wo / (double)(tiles * 128);
@@ -852,7 +852,18 @@ extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W
         }
       }
     }
-    const int stage_bytes = A_STAGE_BYTES + p.n_tile * 128;
+    {
+      // The CTA-pair variant of this kernel (conv_tc_taps2_kernel) is correct (the parity tests pass with LPC_TC_TPAIR=2)
+      // but OFF by default: its full/empty handshake crosses the cluster once per 64-wide K step (4 MMAs), and that
+      // round trip costs more than the doubled MMA rate returns - measured B=64 (us, single / pair): 192->64 k3 40x40
+      // 46 / 102, 128->256 k3 40x40 63 / 124, 512->256 1x1 20x20 15 / 23, 256->64 1x1 80x80 44 / 67.  The halo pair
+      // kernel hands over once per TILE (>= 36 MMAs) and wins.  Next step: several K steps per barrier round.
+      static const int tp_env = [] { const char* e = getenv("LPC_TC_TPAIR"); return e ? atoi(e) : 0; }();
+      const long long m_est = (long long)p.tiles_x * p.tiles_y * p.B;
+      const bool wanted = tp_env == 2 || p.ksteps >= 8 || (p.n_tile >= 128 && p.ksteps >= 2);
+      tpair = tp_env && wanted && p.n_tile % 16 == 0 && m_est >= 4;
+    }
+    const int stage_bytes = A_STAGE_BYTES + (tpair ? ((p.n_tile / 2 * 128 + 1023) & ~1023) : p.n_tile * 128);
     // two CTAs per SM when the double-buffered accumulators leave TMEM room, else one CTA with a deeper ring
     const size_t budget = (p.tmem_cols <= 256) ? 100 * 1024 : SMEM_LIMIT;
     int stages = (int)(budget / stage_bytes);
@@ -869,7 +880,7 @@ extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W
   {
     cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)Cout};
     cuuint64_t strides[1] = {(cuuint64_t)kpad * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)(pair ? p.n_tile / 2 : p.n_tile)};   // a CTA of a pair loads its half of the rows
+    cuuint32_t box[2] = {64, (cuuint32_t)((pair || tpair) ? p.n_tile / 2 : p.n_tile)};   // a CTA of a pair loads its half of the rows
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&maps.b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -879,6 +890,7 @@ extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e1 = cudaFuncSetAttribute(conv_tc_taps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT + 16 * 1024);
+    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(conv_tc_taps2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT + 16 * 1024);
     cudaError_t e2 = cudaSuccess;
     const int lim = (int)SMEM_LIMIT + 16 * 1024;
 #define HALO_ATTR(C_) if (cudaFuncSetAttribute(conv_tc_halo_kernel<C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess) e2 = cudaErrorUnknown;
@@ -904,19 +916,19 @@ extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W
   int per_n = (num_sms() * ctas_per_sm) / p.n_tiles;
   if (per_n < 1) per_n = 1;
   if (per_n > p.m_tiles) per_n = p.m_tiles;
-  if (pair) {                                   // per_n counts CTA PAIRS here; each pair walks two M tiles at a time
+  if (pair || tpair) {                          // per_n counts CTA PAIRS here; each pair walks two M tiles at a time
     per_n = (num_sms() * ctas_per_sm / 2) / p.n_tiles;
     if (per_n < 1) per_n = 1;
     if (per_n > (p.m_tiles + 1) / 2) per_n = (p.m_tiles + 1) / 2;
   }
-  const unsigned grid = (unsigned)(per_n * p.n_tiles) * (pair ? 2u : 1u);
+  const unsigned grid = (unsigned)(per_n * p.n_tiles) * ((pair || tpair) ? 2u : 1u);
   const unsigned threads = 64 + 128 * p.epi_split;
   // Each role is latency-bound per tile (~1.5-2k cycles: barrier round trips, tcgen05.ld, MUFU chains), so with enough
   // tiles per CTA the two epilogue warp groups take alternate tiles (two epilogues in flight) instead of splitting the
   // columns of one; LPC_TC_EPI_ALT=0/1 overrides (profiling).
   {
     static const int force = [] { const char* e = getenv("LPC_TC_EPI_ALT"); return e ? atoi(e) : -1; }();
-    p.epi_alt = (p.epi_split == 2 && p.m_tiles / (per_n * (pair ? 2 : 1)) >= 4) ? 1 : 0;
+    p.epi_alt = (p.epi_split == 2 && p.m_tiles / (per_n * ((pair || tpair) ? 2 : 1)) >= 4) ? 1 : 0;
     if (force >= 0 && p.epi_split == 2) p.epi_alt = force;
   }
   static unsigned long long* trace_buf = nullptr;
@@ -941,6 +953,8 @@ extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W
     if (pair) { HALO_LAUNCH(conv_tc_halo2_kernel) } else { HALO_LAUNCH(conv_tc_halo_kernel) }
 #undef HALO_LAUNCH
   }
+  else if (tpair)
+    lpc_launch_pdl(conv_tc_taps2_kernel, grid, threads, smem, (cudaStream_t)stream, maps, p);
   else
     lpc_launch_pdl(conv_tc_taps_kernel, grid, threads, smem, (cudaStream_t)stream, maps, p);
   LPC_CHECK_LAUNCH("conv2d_tc");

@@ -164,3 +164,143 @@ conv_tc_halo2_kernel(const __grid_constant__ TmapPack maps, const __grid_constan
   cluster_sync_all();             // the peer's shared memory / barriers stay alive until both CTAs are done
   if (warp == 1) tmem_dealloc2(tmem_base, (uint32_t)p.tmem_cols);
 }
+
+// ---- the per-tap TMA kernel on CTA pairs -------------------------------------------------------------------------
+// Same division of labour as conv_tc_halo2_kernel for the layers conv_tc_taps_kernel serves (1x1 on the flat view, 3x3
+// stride 2, the s2d fold, 3x3 on small maps): each CTA of the pair streams ITS M tile's activation boxes and ITS half of
+// the weight rows of every 64-wide K step through its own stage ring (both report expect_tx + complete_tx to the
+// leader's full[s], count 2); the leader's thread issues M = 256 MMAs; tcgen05.commit.multicast frees stage s in both
+// CTAs.  Pays off where a tile has many MMAs (K >= 512) or wide N: the MMA instruction rate per SM doubles.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 2)
+conv_tc_taps2_kernel(const __grid_constant__ TmapPack maps, const __grid_constant__ ConvTcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long bars[2 * MAX_STAGES + 8];
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t rank = cluster_ctarank();
+  const int half = p.n_tile >> 1;
+  const uint32_t ones_addr = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bias_addr = ones_addr + ONES_BYTES;
+  const uint32_t smem_base = (bias_addr + (uint32_t)half * 32u + 1023u) & ~1023u;
+  const int b_stage_bytes = half * 128;
+  const int stage_bytes = A_STAGE_BYTES + ((b_stage_bytes + 1023) & ~1023);      // the B half keeps its 1024-byte alignment
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(&bars[0]);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };                          // leader only
+  auto empty_bar = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * MAX_STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * MAX_STAGES + 4 + b); };   // leader only
+
+  const int pair = blockIdx.x >> 1, pairs = gridDim.x >> 1;
+  const int n_idx = pair % p.n_tiles;
+  const int mp_first = pair / p.n_tiles, mp_step = pairs / p.n_tiles;
+  const int n0 = n_idx * p.n_tile;
+  const int epi_warps_per_tile = p.epi_alt ? 4 : 4 * p.epi_split;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&maps.a[0]);
+    prefetch_tmap(&maps.b);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 2);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 4; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 2 * epi_warps_per_tile);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc2(smem_u32(&tmem_base_slot), (uint32_t)p.tmem_cols);
+  write_bias_tiles(ones_addr, bias_addr, p.bias, n0 + (int)rank * half, half);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  pdl_trigger();
+  pdl_wait();
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      const uint32_t tx_bytes = (uint32_t)(p.TW * p.TH * 128 + b_stage_bytes);
+      const int sub_bytes = 256 * p.kc;
+      int it = 0;
+      for (int mp = mp_first; 2 * mp < p.m_tiles; mp += mp_step) {
+        const int m = 2 * mp + (int)rank;
+        const TileCoord t = tile_coord(p, m < p.m_tiles ? m : p.m_tiles - 1);    // odd tile count: the idle half re-loads the last tile
+        for (int ks = 0; ks < p.ksteps; ++ks, ++it) {
+          const int s = it % p.stages;
+          mbar_wait(empty_bar(s), (uint32_t)(((it / p.stages) & 1) ^ 1));
+          const uint32_t a_dst = smem_base + (uint32_t)(s * stage_bytes);
+          const uint32_t lead_bar = mapa_rank(full_bar(s), 0);
+          mbar_expect_tx_cluster(lead_bar, tx_bytes);
+          for (int j = 0; j < p.nsub; ++j) {
+            int q = ks * p.nsub + j;
+            if (q >= p.real_slots) q = p.real_slots - 1;
+            const int tap = q / p.chunks_per_tap;
+            const int c0 = (q - tap * p.chunks_per_tap) * p.kc;
+            tma_load_4d_pair(a_dst + (uint32_t)(j * sub_bytes), &maps.a[p.tap_map[tap]], lead_bar, c0, t.x0 + p.tap_dx[tap],
+                             t.y0 + p.tap_dy[tap], t.img);
+          }
+          tma_load_2d_pair(a_dst + A_STAGE_BYTES, &maps.b, lead_bar, ks * 64, n0 + (int)rank * half);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && elect_one_sync()) {
+      const uint32_t idesc = make_idesc_m(p.n_tile, 256);
+      const uint32_t a_layout = p.kc == 64 ? 2u : (p.kc == 32 ? 4u : 6u);
+      const uint32_t a_hi = desc_hi((uint32_t)(16 * p.kc), a_layout), b_hi = desc_hi(1024u, 2u);
+      const int sub_bytes = 256 * p.kc;
+      uint32_t a_off[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int e = k * 16, j = e / p.kc;
+        a_off[k] = (uint32_t)((j * sub_bytes + (e - j * p.kc) * 2) >> 4);
+      }
+      const int last_real = (min(p.real_slots * p.kc, p.Cin * (p.real_slots / p.chunks_per_tap)) - (p.ksteps - 1) * 64 + 15) / 16;
+      const uint64_t ones_desc = smem_desc(ones_addr, 16u, 256u, 6u), bias_desc = smem_desc(bias_addr, 16u, 256u, 6u);
+      int it = 0, tcount = 0;
+      for (int mp = mp_first; 2 * mp < p.m_tiles; mp += mp_step, ++tcount) {
+        const int buf = tcount & (p.n_acc - 1);
+        mbar_wait_cluster(tempty_bar(buf), (uint32_t)(((tcount >> p.acc_shift) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)(buf * p.acc_cols);
+        umma2_bf16(acc, ones_desc, bias_desc, idesc, 0u);
+        for (int ks = 0; ks < p.ksteps; ++ks, ++it) {
+          const int s = it % p.stages;
+          mbar_wait_cluster(full_bar(s), (uint32_t)((it / p.stages) & 1));
+          tc_fence_after();
+          const uint32_t a_lo = desc_lo(smem_base + (uint32_t)(s * stage_bytes), 16u);
+          const uint32_t b_lo = desc_lo(smem_base + (uint32_t)(s * stage_bytes) + A_STAGE_BYTES, 16u);
+          const int nk = (ks == p.ksteps - 1) ? last_real : 4;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k < nk) umma2_acc(acc, desc64(a_lo + a_off[k], a_hi), desc64(b_lo + 2u * k, b_hi), idesc);
+          umma2_commit_both(empty_bar(s));
+        }
+        umma2_commit_both(tfull_bar(buf));
+      }
+    }
+  } else {
+    const EpiCtx ectx = make_epi_ctx(p, warp, lane);
+    int tcount = 0;
+    for (int mp = mp_first; 2 * mp < p.m_tiles; mp += mp_step, ++tcount) {
+      if (p.epi_alt && (tcount & 1) != ectx.group) continue;
+      const int m = 2 * mp + (int)rank;
+      const bool live = m < p.m_tiles;
+      const TileCoord t = tile_coord(p, live ? m : 0);
+      const int buf = tcount & (p.n_acc - 1);
+      ResPre rp;
+      if (live) res_prefetch(p, ectx, t.img, t.x0, t.y0, n0, rp);
+      mbar_wait(tfull_bar(buf), (uint32_t)((tcount >> p.acc_shift) & 1));
+      tc_fence_after();
+      if (live) epilogue_tile(p, ectx, tmem_base + (uint32_t)(buf * p.acc_cols), t.img, t.x0, t.y0, n0, &rp);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_rank(tempty_bar(buf), 0);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc2(tmem_base, (uint32_t)p.tmem_cols);
+}
