@@ -2,26 +2,29 @@
 //
 //   D[M = output pixels, N = Cout] = A[M, K = taps*Cin] * W[N, K]^T,  bf16 operands, fp32 accumulate in TMEM.
 //
-// Two persistent, warp-specialised kernels share the PTX helpers and the epilogue:
+// Four persistent, warp-specialised kernels share the PTX helpers (tc_ptx.cuh) and the epilogue:
 //
-//  conv_tc_taps_kernel  (1x1 as a flat GEMM, 3x3 stride 2, the k=2/s=2 space_to_depth fold, small 3x3 maps)
+//  conv_tc_taps_kernel  (1x1 as a flat GEMM, 3x3 stride 2, the k=2/s=2 space_to_depth fold, 3x3 on small maps)
 //     Per 64-wide K step the TMA engine loads, for the current filter tap, a box [kc channels, TW, TH, 1 image] of
-//     the NHWC activation into 128B/64B/32B-swizzled shared memory (zero padding = TMA out-of-bounds fill; stride-2
-//     convs read through four "parity" tensor maps with doubled W/H strides) plus the [n_tile x 64] weight block.
-//  conv_tc_halo_kernel  (3x3 stride 1 - 72 % of LPC-YOLO's FLOPs)
-//     Per M tile (8 x 16 output pixels) ONE halo patch (10 x 18 pixels, all Cin) is loaded, pixel-major with
-//     min(Cin,64) channels per row in the 32B/64B/128B-swizzled K-major layout; the nine taps are nine shifted UMMA
-//     descriptors into that patch (8-row group = one 8-pixel tile row, SBO = patch row pitch of 16 pixels so that
-//     every group starts on a swizzle-atom boundary), so the activation crosses L2->SM 1.4x instead of 9x.
-//     (An un-swizzled "planar" patch also works but the tensor core reads un-swizzled operands ~8x slower:
-//     measured 230 cycles per 128x32x16 MMA, profiles/r01_d_halo_trace.txt.)
-//     The weights stay resident in shared memory for the CTA's lifetime when they fit, else stream through a ring.
+//     the NHWC activation into 128B/64B/32B-swizzled shared memory (zero padding and the channel tail of Cin % 64 != 0
+//     = TMA out-of-bounds fill; stride-2 convs read through four "parity" tensor maps with doubled W/H strides) plus
+//     the [n_tile x 64] weight block.
+//  conv_tc_halo_kernel  (3x3 stride 1 - 72 % of LPC-YOLO's FLOPs - for Cin 16 / 32)
+//     Per M tile (8 x 16 output pixels) ONE halo patch (18 rows x 16 pixels, all Cin) arrives as one TMA box per
+//     64-channel slab, pixel-major with min(Cin,64) channels per row in the 32B/64B/128B-swizzled K-major layout; the
+//     nine taps are nine shifted UMMA descriptors into that patch (8-row group = one 8-pixel tile row, SBO = patch row
+//     pitch of 16 pixels so that every group starts on a swizzle-atom boundary), so the activation crosses L2->SM 1.6x
+//     instead of 9x and no CUDA thread touches an operand byte.  The weights stay resident in shared memory.
+//     (An un-swizzled "planar" patch also works but the tensor core reads un-swizzled operands ~8x slower.)
+//  conv_tc_halo2_kernel / conv_tc_taps2_kernel  (conv_tc_pair.cuh)
+//     The same two on CTA PAIRS (tcgen05 cta_group::2, M = 256 over two SMs): used for every Cin >= 64 halo layer;
+//     the per-tap pair kernel is experimental and off by default.
 //
-// Common structure (one CTA per SM, or two when TMEM/smem allow): warp 0 = TMA producer, warp 1 = TMEM allocator
-// + single-thread tcgen05.mma issuer, warps 2.. = epilogue.  The accumulator is double-buffered in TMEM
-// (tmem_full / tmem_empty mbarriers), so tile i's epilogue (tcgen05.ld -> bias + SiLU/Mish (+gate, +residual) ->
-// bf16 -> 16-byte stores into the NHWC output slice) overlaps tile i+1's main loop.  All mbarrier waits are
-// bounded: a protocol bug traps instead of hanging the GPU.
+// Common structure (two CTAs per SM when TMEM/smem allow): warp 0 = TMA producer, warp 1 = TMEM allocator +
+// single-thread tcgen05.mma issuer, warps 2..9 = epilogue.  The accumulator ring in TMEM has 2 or 4 buffers (tmem_full /
+// tmem_empty mbarriers), so tile i's epilogue (tcgen05.ld -> packed SiLU/Mish (+gate, +pre-fetched residual) -> bf16 ->
+// 16-byte stores into the NHWC output slice) overlaps the main loops of the next tiles; the bias enters through one extra
+// K=16 MMA.  All mbarrier waits are bounded: a protocol bug traps instead of hanging the GPU.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -36,11 +39,9 @@ namespace {
 constexpr int MAX_STAGES = 8;
 constexpr int A_STAGE_BYTES = 128 * 64 * 2;  // taps kernel: 128 rows x 64 K-elements of bf16
 constexpr int MAX_TAPS = 9;
-constexpr int MAX_HALO_SLICES = 9 * 512 / 16;   // halo kernel handles Cin <= 512
 constexpr int HALO_TW = 8, HALO_TH = 16;
 constexpr int HALO_PW = HALO_TW + 2, HALO_PH = HALO_TH + 2;
 constexpr int HALO_SPW = 16;             // patch row pitch in pixels: a multiple of 8 so every 8-pixel row group starts on a swizzle-atom boundary
-constexpr int HALO_LOADERS = 128;        // four cp.async loader warps; thread t owns patch pixels t and t+128
 
 struct TmapPack {
   CUtensorMap a[4];
@@ -55,7 +56,7 @@ struct ConvTcParams {
   int Cout, Cin, ksteps, kc, nsub, chunks_per_tap, real_slots, stages;
   int pix_per_img;
   float inv_tiles_per_img, inv_tiles_x, inv_tw;  // reciprocals for the small integer divisions of the tile scheduler
-  int a_bufs, b_resident, b_stages;  // halo kernel
+  int a_bufs, b_resident;            // halo kernels: patch buffers in the ring; weights resident (always 1 there)
   int a_tma;                         // halo kernel: 1 = the patch arrives by TMA (one 4-D box per 64-channel slab), no loader warps
   const bf16* x;                     // halo kernel: activation base, pixel pitch, input geometry
   long long x_ld;
@@ -63,7 +64,7 @@ struct ConvTcParams {
   int pitch, slabs, slab_bytes;      // halo patch: bytes per pixel row (32/64/128), 64-channel slabs
   int epi_split;                     // epilogue warps = 4 * epi_split
   int epi_alt;                       // 1: the two epilogue warp groups take alternate tiles (full width each) instead of half the columns of every tile
-  int dbg;                           // LPC_TC_DBG bits (profiling only): 1 skip MMAs, 2 skip A loads, 4 skip stores, 8 trace
+  int dbg;                           // LPC_TC_DBG bits (profiling only): 1 skip MMAs, 4 skip the epilogue math + stores, 8 trace, 32 skip stores only
   unsigned long long* trace;         // [4 roles][64 tiles][4 stamps] of clock64, CTA 0 only
   signed char tap_map[MAX_TAPS], tap_dx[MAX_TAPS], tap_dy[MAX_TAPS];
   const float* bias;
@@ -392,10 +393,7 @@ conv_tc_taps_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
 #define TRACE(role, tile, k) do { if ((p.dbg & 8) && blockIdx.x == 0 && (tile) < 64) p.trace[((role) * 64 + (tile)) * 4 + (k)] = clock64(); } while (0)
 
 // ---- kernel 2: 3x3 stride-1 conv from one halo patch per tile ---------------------------------------------
-// Warps: 0 = weight TMA, 1 = MMA issuer, 2..(1+4*epi_split) = epilogue, last two = activation loaders.  The halo
-// patch is gathered with 16-byte cp.async (coalesced in global memory, scattered into the planar layout, zero-filled
-// outside the image): TMA would need one request per 16-byte element here, and its per-request rate (~5 cycles)
-// made it the bottleneck of every small-Cin layer (profiles/r01_c_*).
+// Warps: 0 = TMA (resident weights once, then one patch box per slab per tile), 1 = MMA issuer, 2..9 = epilogue.
 template <int CIN>   // CIN > 0: patch geometry and the MMA issue sequence are compile-time
 __global__ void __launch_bounds__(320, 2)
 conv_tc_halo_kernel(const __grid_constant__ TmapPack maps, const __grid_constant__ ConvTcParams p) {
@@ -406,17 +404,13 @@ conv_tc_halo_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
   const uint32_t ones_addr = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bias_addr = ones_addr + ONES_BYTES;
   const uint32_t smem_base = (bias_addr + (uint32_t)p.n_tile * 32u + 1023u) & ~1023u;
-  constexpr bool b_res = true;                  // weights stay resident (the host routes everything else to the taps kernel)
   const int b_block = p.n_tile * 128;
-  const int b_blocks = b_res ? p.ksteps : p.b_stages;
+  const int b_blocks = p.ksteps;                // the weights stay resident (the host routes everything else to the per-tap kernel)
   const int halo_bytes = p.slabs * p.slab_bytes;
-  const int chunks_px = p.Cin / 8;              // 16-byte channel groups per pixel
-  const int chunks_row = p.pitch / 16;          // ... per swizzled row (one 64-channel slab)
   const uint32_t a_region = smem_base + (uint32_t)(b_blocks * b_block);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(&bars[0]);
   auto bfull_bar = [&](int s) { return bar0 + 8u * s; };
-  auto bempty_bar = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
   auto afull_bar = [&](int s) { return bar0 + 8u * (2 * MAX_STAGES + s); };
   auto aempty_bar = [&](int s) { return bar0 + 8u * (3 * MAX_STAGES + s); };
   auto tfull_bar = [&](int b) { return bar0 + 8u * (4 * MAX_STAGES + b); };
@@ -431,7 +425,6 @@ conv_tc_halo_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
     prefetch_tmap(&maps.b);
     for (int s = 0; s < MAX_STAGES; ++s) {
       mbar_init(bfull_bar(s), 1);
-      mbar_init(bempty_bar(s), 1);
     }
     for (int s = 0; s < MAX_STAGES; ++s) {
       mbar_init(afull_bar(s), 1);
@@ -454,10 +447,8 @@ conv_tc_halo_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
 
   if (warp == 0) {
     if (elect_one_sync()) {
-      if (b_res) {
-        mbar_expect_tx(bfull_bar(0), (uint32_t)(p.ksteps * b_block));
-        for (int ks = 0; ks < p.ksteps; ++ks) tma_load_2d(smem_base + (uint32_t)(ks * b_block), &maps.b, bfull_bar(0), ks * 64, n0);
-      }
+      mbar_expect_tx(bfull_bar(0), (uint32_t)(p.ksteps * b_block));
+      for (int ks = 0; ks < p.ksteps; ++ks) tma_load_2d(smem_base + (uint32_t)(ks * b_block), &maps.b, bfull_bar(0), ks * 64, n0);
       {
         // The halo patch by TMA: per 64-channel slab ONE 4-D box [min(Cin,64) ch, 16 px, 18 rows, 1 image] at (x0-1, y0-1);
         // the box lands exactly in the pixel-major swizzled slab layout the MMA descriptors view (row pitch 16 pixels) and
@@ -489,8 +480,8 @@ conv_tc_halo_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
       const uint32_t pitch16 = (uint32_t)p.pitch >> 4, slab16 = (uint32_t)p.slab_bytes >> 4, bblk16 = (uint32_t)b_block >> 4;
       const int groups = (p.Cin < 64 ? p.Cin : 64) / 16;     // K=16 slices per slab row
       const uint32_t b_lo0 = desc_lo(smem_base, 16u);
-      if (b_res) mbar_wait(bfull_bar(0), 0);
-      int tcount = 0, bit = 0;
+      mbar_wait(bfull_bar(0), 0);
+      int tcount = 0;
       for (int m = m_first; m < p.m_tiles; m += m_step, ++tcount) {
         const int buf = tcount & (p.n_acc - 1);
         const int ab = tcount % p.a_bufs;
@@ -503,8 +494,6 @@ conv_tc_halo_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
         const uint32_t acc = tmem_base + (uint32_t)(buf * p.acc_cols);
         const uint32_t a_lo0 = desc_lo(a_region + (uint32_t)(ab * halo_bytes), 16u);
         issue_bias_mma(acc, ones_addr, bias_addr, p.n_tile, idesc);      // accumulator := bias
-        int kin = 0, ks = 0;
-        uint32_t b_lo = b_lo0;
         if (CIN > 0) {
           constexpr int C_ROW = CIN < 64 ? CIN : 64, PITCH16 = C_ROW * 2 / 16, GROUPS = C_ROW / 16, SLABS = (CIN + 63) / 64;
           constexpr int SLAB16 = HALO_PH * HALO_SPW * C_ROW * 2 / 16;
@@ -512,52 +501,24 @@ conv_tc_halo_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
           for (int j = 0; j < 9 * SLABS * GROUPS; ++j) {
             const int tap = j / (SLABS * GROUPS), sl = (j / GROUPS) % SLABS, g = j % GROUPS;     // all compile-time
             const int kin_c = j & 3, ks_c = j >> 2;
-            if (kin_c == 0) {
-              if (b_res) {
-                b_lo = b_lo0 + (uint32_t)ks_c * bblk16;
-              } else {
-                const int st = bit % p.b_stages;
-                mbar_wait(bfull_bar(st), (uint32_t)((bit / p.b_stages) & 1));
-                tc_fence_after();
-                b_lo = b_lo0 + (uint32_t)st * bblk16;
-              }
-            }
             if (!(p.dbg & 1))
               umma_acc(acc, desc64(a_lo0 + (uint32_t)(((tap / 3) * HALO_SPW + tap % 3) * PITCH16 + sl * SLAB16 + 2 * g), a_hi),
-                       desc64(b_lo + 2u * (uint32_t)kin_c, b_hi), idesc);
-            if (kin_c == 3 && !b_res) { umma_commit(bempty_bar(bit % p.b_stages)); ++bit; }
+                       desc64(b_lo0 + (uint32_t)ks_c * bblk16 + 2u * (uint32_t)kin_c, b_hi), idesc);
           }
-          kin = (9 * SLABS * GROUPS) & 3;
-          ks = (9 * SLABS * GROUPS) >> 2;
         } else {
-        for (int ty = 0; ty < 3; ++ty) {
-          for (int tx = 0; tx < 3; ++tx) {
-            const uint32_t tap_lo = a_lo0 + (uint32_t)(ty * HALO_SPW + tx) * pitch16;
-            for (int sl = 0; sl < p.slabs; ++sl) {
-              for (int g = 0; g < groups; ++g) {
-                if (kin == 0) {
-                  if (b_res) {
-                    b_lo = b_lo0 + (uint32_t)ks * bblk16;
-                  } else {
-                    const int st = bit % p.b_stages;
-                    mbar_wait(bfull_bar(st), (uint32_t)((bit / p.b_stages) & 1));
-                    tc_fence_after();
-                    b_lo = b_lo0 + (uint32_t)st * bblk16;
-                  }
+          int kin = 0, ks = 0;
+          for (int ty = 0; ty < 3; ++ty)
+            for (int tx = 0; tx < 3; ++tx) {
+              const uint32_t tap_lo = a_lo0 + (uint32_t)(ty * HALO_SPW + tx) * pitch16;
+              for (int sl = 0; sl < p.slabs; ++sl)
+                for (int g = 0; g < groups; ++g) {
+                  if (!(p.dbg & 1))
+                    umma_acc(acc, desc64(tap_lo + (uint32_t)sl * slab16 + 2u * (uint32_t)g, a_hi),
+                             desc64(b_lo0 + (uint32_t)ks * bblk16 + 2u * (uint32_t)kin, b_hi), idesc);
+                  if (++kin == 4) { kin = 0; ++ks; }
                 }
-                if (!(p.dbg & 1)) umma_acc(acc, desc64(tap_lo + (uint32_t)sl * slab16 + 2u * (uint32_t)g, a_hi), desc64(b_lo + 2u * (uint32_t)kin, b_hi), idesc);
-                if (++kin == 4) {
-                  kin = 0;
-                  ++ks;
-                  if (!b_res) { umma_commit(bempty_bar(bit % p.b_stages)); ++bit; }
-                }
-              }
             }
-          }
         }
-        }
-        (void)ks;
-        if (kin != 0 && !b_res) { umma_commit(bempty_bar(bit % p.b_stages)); ++bit; }   // partial last K step
         umma_commit(aempty_bar(ab));
         umma_commit(tfull_bar(buf));
         TRACE(1, tcount, 3);
@@ -782,7 +743,6 @@ extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W
       halo = true;
       p.n_tile = nt;
       p.b_resident = resident;
-      p.b_stages = resident ? 0 : 3;
       // deep activation prefetch: small-C layers are HBM-bound and need tens of KB in flight per SM
       const size_t b_bytes = need - 2 * halo_bytes;
       const size_t budget = (nt <= 128 && b_bytes + 3 * halo_bytes <= 100 * 1024) ? 100 * 1024 : SMEM_LIMIT;  // 2 CTAs/SM when small
@@ -808,7 +768,7 @@ extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W
     p.pitch = (Cin >= 64 ? 64 : Cin) * 2;
     p.slabs = (Cin + 63) / 64;
     p.slab_bytes = HALO_PH * HALO_SPW * p.pitch;
-    smem = (size_t)(p.b_resident ? p.ksteps : p.b_stages) * (pair ? p.n_tile / 2 : p.n_tile) * 128 + (size_t)p.a_bufs * p.slabs * p.slab_bytes + 1024 + BIAS_REGION(p.n_tile);
+    smem = (size_t)p.ksteps * (pair ? p.n_tile / 2 : p.n_tile) * 128 + (size_t)p.a_bufs * p.slabs * p.slab_bytes + 1024 + BIAS_REGION(p.n_tile);
     {
       p.a_tma = 1;                                // both halo kernels receive their patches by TMA
       const int cb = Cin >= 64 ? 64 : Cin;
