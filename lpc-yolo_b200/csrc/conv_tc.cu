@@ -312,9 +312,13 @@ conv_tc_taps_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
     if (elect_one_sync()) {
       const uint32_t tx_bytes = (uint32_t)(p.TW * p.TH * 128 + b_stage_bytes);
       const int sub_bytes = 256 * p.kc;
-      int it = 0;
-      for (int m = m_first; m < p.m_tiles; m += m_step) {
+      int it = 0, tcount = 0;
+      for (int m = m_first; m < p.m_tiles; m += m_step, ++tcount) {
         const TileCoord t = tile_coord(p, m);
+        // The PRODUCER checks that the tile's accumulator buffer has been drained before it loads the tile's first
+        // operands, so "stage full" implies "accumulator free" and the MMA thread - the serial bottleneck, ~185 cycles
+        // per already-complete mbarrier wait (tools/mma_bench.cu) - waits on one barrier per K step instead of two.
+        mbar_wait(tempty_bar(tcount & (p.n_acc - 1)), (uint32_t)(((tcount >> p.acc_shift) & 1) ^ 1));
         for (int ks = 0; ks < p.ksteps; ++ks, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (uint32_t)((it / p.stages) & 1);
@@ -349,14 +353,12 @@ conv_tc_taps_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
       int it = 0, tcount = 0;
       for (int m = m_first; m < p.m_tiles; m += m_step, ++tcount) {
         const int buf = tcount & (p.n_acc - 1);
-        mbar_wait(tempty_bar(buf), (uint32_t)(((tcount >> p.acc_shift) & 1) ^ 1));
-        tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)(buf * p.acc_cols);
-        issue_bias_mma(acc, ones_addr, bias_addr, p.n_tile, idesc);      // accumulator := bias
         for (int ks = 0; ks < p.ksteps; ++ks, ++it) {
           const int s = it % p.stages;
-          mbar_wait(full_bar(s), (uint32_t)((it / p.stages) & 1));
+          mbar_wait(full_bar(s), (uint32_t)((it / p.stages) & 1));     // implies tempty(buf): see the producer
           tc_fence_after();
+          if (ks == 0) issue_bias_mma(acc, ones_addr, bias_addr, p.n_tile, idesc);      // accumulator := bias
           const uint32_t a_lo = desc_lo(smem_base + (uint32_t)(s * stage_bytes), 16u);
           const uint32_t b_lo = desc_lo(smem_base + (uint32_t)(s * stage_bytes) + A_STAGE_BYTES, 16u);
           const int nk = (ks == p.ksteps - 1) ? last_real : 4;           // zero-padded K slices are skipped
@@ -460,6 +462,8 @@ conv_tc_halo_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
           const TileCoord t = tile_coord(p, m);
           const int ab = tcount % p.a_bufs;
           mbar_wait(aempty_bar(ab), (uint32_t)(((tcount / p.a_bufs) & 1) ^ 1));
+          // "patch full" must imply "accumulator buffer drained" (the MMA thread waits on afull only)
+          mbar_wait(tempty_bar(tcount & (p.n_acc - 1)), (uint32_t)(((tcount >> p.acc_shift) & 1) ^ 1));
           mbar_expect_tx(afull_bar(ab), (uint32_t)halo_bytes);
           const uint32_t a_dst = a_region + (uint32_t)(ab * halo_bytes);
           for (int sl = 0; sl < p.slabs; ++sl)
@@ -486,9 +490,8 @@ conv_tc_halo_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
         const int buf = tcount & (p.n_acc - 1);
         const int ab = tcount % p.a_bufs;
         TRACE(1, tcount, 0);
-        mbar_wait(tempty_bar(buf), (uint32_t)(((tcount >> p.acc_shift) & 1) ^ 1));
         TRACE(1, tcount, 1);
-        mbar_wait(afull_bar(ab), (uint32_t)((tcount / p.a_bufs) & 1));
+        mbar_wait(afull_bar(ab), (uint32_t)((tcount / p.a_bufs) & 1));   // implies tempty(buf): the producer waited for it
         TRACE(1, tcount, 2);
         tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)(buf * p.acc_cols);

@@ -10,7 +10,8 @@
 //   patches: each CTA's warp 0 issues its own TMA boxes (cta_group::2 signalling): expect_tx + complete_tx land on the
 //            LEADER's afull[s] (count 2)
 //   leader MMA --commit.multicast--> aempty[s], tfull[b] in BOTH CTAs
-//   epilogue (both CTAs, per warp) --arrive.cluster--> leader tempty[b]     (count 2 x warps per tile)
+//   epilogue --arrive--> the CTA's OWN tempty[b]; each producer waits for it before loading the tile, so the leader's
+//            afull implies both accumulators are drained
 //   weights: each CTA TMA-loads its half, then its warp 0 arrives on the leader's wready barrier (count 2)
 template <int CIN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 2)
@@ -51,7 +52,7 @@ conv_tc_halo2_kernel(const __grid_constant__ TmapPack maps, const __grid_constan
     }
     for (int b = 0; b < 4; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 2 * epi_warps_per_tile);
+      mbar_init(tempty_bar(b), epi_warps_per_tile);
     }
     mbar_init(bfull_bar, 1);
     mbar_init(wready_bar, 2);
@@ -84,6 +85,10 @@ conv_tc_halo2_kernel(const __grid_constant__ TmapPack maps, const __grid_constan
           const TileCoord t = tile_coord(p, live ? m : p.m_tiles - 1);     // odd tile count: the idle half re-loads the last tile
           const int ab = tcount % p.a_bufs;
           mbar_wait(aempty_bar(ab), (uint32_t)(((tcount / p.a_bufs) & 1) ^ 1));
+          // each CTA's producer checks ITS accumulator buffer (local tempty, arrived by its own epilogue warps) before it
+          // loads: the leader's afull (both patches landed) then implies both accumulators are drained - no remote
+          // epilogue arrivals and no cluster-scope tempty wait on the MMA thread
+          mbar_wait(tempty_bar(tcount & (p.n_acc - 1)), (uint32_t)(((tcount >> p.acc_shift) & 1) ^ 1));
           const uint32_t lead_bar = mapa_rank(afull_bar(ab), 0);
           mbar_expect_tx_cluster(lead_bar, (uint32_t)halo_bytes);
           const uint32_t a_dst = a_region + (uint32_t)(ab * halo_bytes);
@@ -107,7 +112,6 @@ conv_tc_halo2_kernel(const __grid_constant__ TmapPack maps, const __grid_constan
       for (int mp = mp_first; 2 * mp < p.m_tiles; mp += mp_step, ++tcount) {
         const int buf = tcount & (p.n_acc - 1);
         const int ab = tcount % p.a_bufs;
-        mbar_wait_cluster(tempty_bar(buf), (uint32_t)(((tcount >> p.acc_shift) & 1) ^ 1));
         mbar_wait_cluster(afull_bar(ab), (uint32_t)((tcount / p.a_bufs) & 1));
         tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)(buf * p.acc_cols);
@@ -157,7 +161,7 @@ conv_tc_halo2_kernel(const __grid_constant__ TmapPack maps, const __grid_constan
       if (live) epilogue_tile(p, ectx, tmem_base + (uint32_t)(buf * p.acc_cols), t.img, t.x0, t.y0, n0, &rp);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_rank(tempty_bar(buf), 0);
+      if (lane == 0) mbar_arrive(tempty_bar(buf));
     }
   }
   tc_fence_before();
@@ -206,7 +210,7 @@ conv_tc_taps2_kernel(const __grid_constant__ TmapPack maps, const __grid_constan
     }
     for (int b = 0; b < 4; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 2 * epi_warps_per_tile);
+      mbar_init(tempty_bar(b), epi_warps_per_tile);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -223,10 +227,11 @@ conv_tc_taps2_kernel(const __grid_constant__ TmapPack maps, const __grid_constan
     if (elect_one_sync()) {
       const uint32_t tx_bytes = (uint32_t)(p.TW * p.TH * 128 + b_stage_bytes);
       const int sub_bytes = 256 * p.kc;
-      int it = 0;
-      for (int mp = mp_first; 2 * mp < p.m_tiles; mp += mp_step) {
+      int it = 0, tcount = 0;
+      for (int mp = mp_first; 2 * mp < p.m_tiles; mp += mp_step, ++tcount) {
         const int m = 2 * mp + (int)rank;
         const TileCoord t = tile_coord(p, m < p.m_tiles ? m : p.m_tiles - 1);    // odd tile count: the idle half re-loads the last tile
+        mbar_wait(tempty_bar(tcount & (p.n_acc - 1)), (uint32_t)(((tcount >> p.acc_shift) & 1) ^ 1));   // local accumulator drained
         for (int ks = 0; ks < p.ksteps; ++ks, ++it) {
           const int s = it % p.stages;
           mbar_wait(empty_bar(s), (uint32_t)(((it / p.stages) & 1) ^ 1));
@@ -262,14 +267,12 @@ conv_tc_taps2_kernel(const __grid_constant__ TmapPack maps, const __grid_constan
       int it = 0, tcount = 0;
       for (int mp = mp_first; 2 * mp < p.m_tiles; mp += mp_step, ++tcount) {
         const int buf = tcount & (p.n_acc - 1);
-        mbar_wait_cluster(tempty_bar(buf), (uint32_t)(((tcount >> p.acc_shift) & 1) ^ 1));
-        tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)(buf * p.acc_cols);
-        umma2_bf16(acc, ones_desc, bias_desc, idesc, 0u);
         for (int ks = 0; ks < p.ksteps; ++ks, ++it) {
           const int s = it % p.stages;
           mbar_wait_cluster(full_bar(s), (uint32_t)((it / p.stages) & 1));
           tc_fence_after();
+          if (ks == 0) umma2_bf16(acc, ones_desc, bias_desc, idesc, 0u);
           const uint32_t a_lo = desc_lo(smem_base + (uint32_t)(s * stage_bytes), 16u);
           const uint32_t b_lo = desc_lo(smem_base + (uint32_t)(s * stage_bytes) + A_STAGE_BYTES, 16u);
           const int nk = (ks == p.ksteps - 1) ? last_real : 4;
@@ -297,7 +300,7 @@ conv_tc_taps2_kernel(const __grid_constant__ TmapPack maps, const __grid_constan
       if (live) epilogue_tile(p, ectx, tmem_base + (uint32_t)(buf * p.acc_cols), t.img, t.x0, t.y0, n0, &rp);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_rank(tempty_bar(buf), 0);
+      if (lane == 0) mbar_arrive(tempty_bar(buf));
     }
   }
   tc_fence_before();
