@@ -12,16 +12,16 @@ __global__ void upsample2x_kernel(const T* __restrict__ x, int x_ld, int B, int 
   pdl_wait();
   constexpr int V = Vec<T>::N;
   const int cvecs = C / V;
-  const long long total = (long long)B * H * W * cvecs;  // one thread per INPUT vector, writes 4 outputs
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned total = (unsigned)B * H * W * cvecs;  // one thread per INPUT vector, writes 4 outputs (host checks < 2^32)
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int cv = (int)(idx % cvecs);
-  long long p = idx / cvecs;
-  const int ix = (int)(p % W);
-  long long t = p / W;
-  const int iy = (int)(t % H);
-  const int n = (int)(t / H);
-  Vec<T> v = ldg_vec<T>(x + p * x_ld + cv * V);
+  const unsigned p = idx / (unsigned)cvecs;
+  const int cv = (int)(idx - p * (unsigned)cvecs);
+  const unsigned t = p / (unsigned)W;
+  const int ix = (int)(p - t * (unsigned)W);
+  const int n = (int)(t / (unsigned)H);
+  const int iy = (int)(t - (unsigned)n * (unsigned)H);
+  Vec<T> v = ldg_vec<T>(x + (long long)p * x_ld + cv * V);
   const int Wo = 2 * W;
   T* o = y + (((long long)n * 2 * H + 2 * iy) * Wo + 2 * ix) * y_ld + cv * V;
   st_vec<T>(o, v);
@@ -169,24 +169,38 @@ template <typename T>
 __global__ void global_avgpool_kernel(const T* __restrict__ x, int x_ld, int HW, int C, int chunk_pix, float* __restrict__ out) {
   pdl_trigger();
   pdl_wait();
-  __shared__ float part[8][33];
+  // 256 threads = PL pixel lanes x CV channel-vector lanes (16-byte loads); per channel block the pixel lanes are reduced
+  // through shared memory in a fixed order (deterministic).
+  constexpr int V = Vec<T>::N;
+  __shared__ float part[256 * V];
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int p0 = chunk * chunk_pix, p1 = min(HW, p0 + chunk_pix);
-  const int lane_c = threadIdx.x & 31, lane_p = threadIdx.x >> 5;
-  for (int cb = 0; cb < C; cb += 32) {
-    const int c = cb + lane_c;
-    float s = 0.f;
-    if (c < C) {
-      const T* base = x + (long long)b * HW * x_ld + c;
-      for (int p = p0 + lane_p; p < p1; p += 8) s += to_f(base[(long long)p * x_ld]);
-    }
-    part[lane_p][lane_c] = s;
-    __syncthreads();
-    if (threadIdx.x < 32 && c < C) {
-      float t = 0.f;
+  const int cvecs = C / V;
+  const int CV = cvecs < 32 ? cvecs : 32, PL = 256 / CV;
+  const int cvl = threadIdx.x % CV, pl = threadIdx.x / CV;
+  const T* base = x + (long long)b * HW * x_ld;
+  for (int cb = 0; cb < cvecs; cb += CV) {
+    const int cv = cb + cvl;
+    float acc[V];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x];
-      out[((long long)b * gridDim.x + chunk) * C + c] = t;
+    for (int v = 0; v < V; ++v) acc[v] = 0.f;
+    if (cv < cvecs && pl < PL)
+      for (int p = p0 + pl; p < p1; p += PL) {
+        float f[V];
+        ldg_vec<T>(base + (long long)p * x_ld + cv * V).unpack(f);
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[v] += f[v];
+      }
+#pragma unroll
+    for (int v = 0; v < V; ++v) part[threadIdx.x * V + v] = acc[v];
+    __syncthreads();
+    for (int i = threadIdx.x; i < CV * V; i += 256) {
+      const int c = cb * V + i;
+      if (c < C) {
+        float t = 0.f;
+        for (int q = 0; q < PL; ++q) t += part[(q * CV) * V + i];
+        out[((long long)b * gridDim.x + chunk) * C + c] = t;
+      }
     }
     __syncthreads();
   }
@@ -232,21 +246,26 @@ __global__ void cbam_stats_kernel(const T* __restrict__ x, int x_ld, int B, int 
   pdl_trigger();
   pdl_wait();
   constexpr int V = Vec<T>::N;
-  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long gp = gt / lpp;
-  const int sub = (int)(gt - gp * lpp);
-  const bool live = gp < (long long)B * HW;
+  const unsigned gt = blockIdx.x * blockDim.x + threadIdx.x;       // 32-bit index math (host checks the range); lpp is a power of two
+  const unsigned gp = gt / (unsigned)lpp;
+  const int sub = (int)(gt & (unsigned)(lpp - 1));
+  const bool live = gp < (unsigned)B * (unsigned)HW;
   float s = 0.f, m = -INFINITY;
   if (live) {
-    const int b = (int)(gp / HW);
-    const T* px = x + gp * x_ld;
+    const int b = (int)(gp / (unsigned)HW);
+    const T* px = x + (long long)gp * x_ld;
     const float* cab = ca + (long long)b * C;
     for (int c = sub * V; c < C; c += lpp * V) {
-      float f[V];
+      float f[V], g[V];
       ldg_vec<T>(px + c).unpack(f);
 #pragma unroll
+      for (int v = 0; v < V; v += 4) {
+        const float4 c4 = __ldg(reinterpret_cast<const float4*>(cab + c + v));
+        g[v] = c4.x; g[v + 1] = c4.y; g[v + 2] = c4.z; g[v + 3] = c4.w;
+      }
+#pragma unroll
       for (int v = 0; v < V; ++v) {
-        const float t = f[v] * __ldg(cab + c + v);
+        const float t = f[v] * g[v];
         s += t;
         m = fmaxf(m, t);
       }
@@ -256,10 +275,7 @@ __global__ void cbam_stats_kernel(const T* __restrict__ x, int x_ld, int B, int 
     s += __shfl_xor_sync(0xffffffffu, s, o);
     m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   }
-  if (live && sub == 0) {
-    stats[gp * 2] = s / (float)C;
-    stats[gp * 2 + 1] = m;
-  }
+  if (live && sub == 0) reinterpret_cast<float2*>(stats)[gp] = make_float2(s / (float)C, m);
 }
 
 // gate = sigmoid(conv_kxk([mean_c, max_c])) ; y = x * ca * gate (conv.py:300-320).  CTA = one 16 x 16 pixel tile of one
@@ -345,6 +361,7 @@ extern "C" int lpc_upsample2x(int dtype, const void* x, int x_ld, int B, int H, 
   if (int e = check_vec("upsample2x", dtype, C, x_ld, y_ld, x, y)) return e;
   cudaStream_t s = (cudaStream_t)stream;
   const int V = dtype == LPC_F32 ? 4 : 8;
+  LPC_REQUIRE((long long)B * H * W * (C / V) < (1ll << 32), "upsample2x: tensor too large for 32-bit indexing");
   const int g = cdiv((long long)B * H * W * (C / V), 256);
   DISPATCH_T(dtype, (lpc_launch_pdl(upsample2x_kernel<float>, g, 256, 0, s, (const float*)x, x_ld, B, H, W, C, (float*)y, y_ld)),
              (lpc_launch_pdl(upsample2x_kernel<bf16>, g, 256, 0, s, (const bf16*)x, x_ld, B, H, W, C, (bf16*)y, y_ld)), "upsample2x")
@@ -445,6 +462,7 @@ extern "C" int lpc_cbam_stats(int dtype, const void* x, int x_ld, int B, int HW,
   if (int e = check_vec("cbam_stats", dtype, C, x_ld, x_ld, x, x)) return e;
   cudaStream_t s = (cudaStream_t)stream;
   const int lpp = lanes_per_pixel(dtype, C);
+  LPC_REQUIRE((long long)B * HW * lpp < (1ll << 32), "cbam_stats: tensor too large for 32-bit indexing");
   const int g = cdiv((long long)B * HW * lpp, 256);
   DISPATCH_T(dtype, (lpc_launch_pdl(cbam_stats_kernel<float>, g, 256, 0, s, (const float*)x, x_ld, B, HW, C, lpp, ca, stats)),
              (lpc_launch_pdl(cbam_stats_kernel<bf16>, g, 256, 0, s, (const bf16*)x, x_ld, B, HW, C, lpp, ca, stats)), "cbam_stats")
