@@ -134,6 +134,13 @@ int lpc_pack_input(int dtype, const float* x_nchw, int B, int C, int H, int W, v
 int lpc_pack_u8(int dtype, const void* src_u8, int B, int Hs, int Ws, int top, int left, int H, int W, int pad_value,
                 int swap_rb, void* y, void* stream);
 
+/* The same with LetterBox's resize (data/augment.py:726-727, cv2.resize INTER_LINEAR) in front: the [hs,ws] images are
+ * resized to [nh,nw] with OpenCV's 8-bit fixed-point linear interpolation (bit-exact), placed at (top,left) of [H,W].
+ * xtab [nw][3] = {x0, a0, a1}, ytab [nh][4] = {y0, y1, b0, b1}: int32 device arrays (11-bit coefficients, built as
+ * imgproc/resize.cpp builds them; see engine.resize_tables). */
+int lpc_letterbox_u8(int dtype, const void* src_u8, int B, int hs, int ws, int nh, int nw, const int* xtab, const int* ytab,
+                     int top, int left, int H, int W, int pad_value, int swap_rb, void* y, void* stream);
+
 /* ---- CBAM / SPCA pooled gates (conv.py:278-320, block.py:5735-5747) */
 /* partial[b][chunk][c] = sum of x over the chunk's pixels, chunk count = lpc_global_avgpool_chunks(B, HW)
  * (a fixed-order two-stage reduction: deterministic, no atomics). */

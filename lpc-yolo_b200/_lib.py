@@ -38,6 +38,7 @@ SIGNATURES = {
     "lpc_channel_deinterleave": (_i, [_i, _p, _i, _ll, _i, _p, _i, _p]),
     "lpc_pack_input": (_i, [_i, _f32p, _i, _i, _i, _i, _p, _i, _i, _p]),
     "lpc_pack_u8": (_i, [_i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "lpc_letterbox_u8": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "lpc_global_avgpool": (_i, [_i, _p, _i, _i, _i, _i, _f32p, _p]),
     "lpc_global_avgpool_chunks": (_i, [_i, _i]),
     "lpc_channel_mlp": (_i, [_f32p, _i, _i, C.c_float, _i, _f32p, _f32p, _i, _i, _f32p, _f32p, _i, _i, _f32p, _p]),

@@ -163,6 +163,59 @@ __global__ void pack_u8_kernel(const unsigned char* __restrict__ src, int B, int
   }
 }
 
+// LetterBox with resize (data/augment.py:726-727: cv2.resize(img, new_unpad, INTER_LINEAR)) fused with the border, BGR->RGB,
+// /255 and the NHWC-4 pack.  Bit-exact to OpenCV's 8-bit linear resize (imgproc/resize.cpp, HResizeLinear / VResizeLinear with
+// 11-bit fixed-point coefficients): per output column xtab = {x0, a0, a1} (x1 = min(x0 + 1, ws - 1)), per output row
+// ytab = {y0, y1, b0, b1}; the tables are built on the host exactly as OpenCV builds them (engine.resize_tables) and
+// verified against cv2 in tests/test_preprocess.py.
+//   h_r = S[y_r][x0] * a0 + S[y_r][x1] * a1;   out = ((b0 * (h_0 >> 4) >> 16) + (b1 * (h_1 >> 4) >> 16) + 2) >> 2
+template <typename T>
+__global__ void letterbox_u8_kernel(const unsigned char* __restrict__ src, int B, int hs, int ws, int nh, int nw,
+                                    const int* __restrict__ xtab, const int* __restrict__ ytab, int top, int left, int H, int W,
+                                    float pad, int swap_rb, T* __restrict__ y) {
+  pdl_trigger();
+  pdl_wait();
+  const unsigned total = (unsigned)B * H * W;
+  const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= total) return;
+  const unsigned t = p / (unsigned)W;
+  const int w = (int)(p - t * (unsigned)W);
+  const int n = (int)(t / (unsigned)H);
+  const int h = (int)(t - (unsigned)n * (unsigned)H);
+  const int dy = h - top, dx = w - left;
+  float c0 = pad, c1 = pad, c2 = pad;
+  if ((unsigned)dy < (unsigned)nh && (unsigned)dx < (unsigned)nw) {
+    const int x0 = xtab[dx * 3], a0 = xtab[dx * 3 + 1], a1 = xtab[dx * 3 + 2];
+    const int x1 = min(x0 + 1, ws - 1);
+    const int y0 = ytab[dy * 4], y1 = ytab[dy * 4 + 1], b0 = ytab[dy * 4 + 2], b1 = ytab[dy * 4 + 3];
+    const unsigned char* r0 = src + ((long long)n * hs + y0) * ws * 3;
+    const unsigned char* r1 = src + ((long long)n * hs + y1) * ws * 3;
+    int o[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int h0 = (int)r0[x0 * 3 + c] * a0 + (int)r0[x1 * 3 + c] * a1;
+      const int h1 = (int)r1[x0 * 3 + c] * a0 + (int)r1[x1 * 3 + c] * a1;
+      const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+      o[c] = min(max(v, 0), 255);
+    }
+    c0 = (float)(swap_rb ? o[2] : o[0]);
+    c1 = (float)o[1];
+    c2 = (float)(swap_rb ? o[0] : o[2]);
+  }
+  c0 = __fdiv_rn(c0, 255.0f);
+  c1 = __fdiv_rn(c1, 255.0f);
+  c2 = __fdiv_rn(c2, 255.0f);
+  if (sizeof(T) == 2) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(c0, c1), hi = __floats2bfloat162_rn(c2, 0.f);
+    uint2 ov;
+    ov.x = *reinterpret_cast<const uint32_t*>(&lo);
+    ov.y = *reinterpret_cast<const uint32_t*>(&hi);
+    reinterpret_cast<uint2*>(y)[p] = ov;
+  } else {
+    reinterpret_cast<float4*>(y)[p] = make_float4(c0, c1, c2, 0.f);
+  }
+}
+
 // partial[b, chunk, c] = sum over the chunk's pixels (fixed order: deterministic, no atomics).  grid (chunks, B);
 // 256 threads = 8 pixel lanes x 32 channel lanes looping over channel blocks.
 template <typename T>
@@ -421,6 +474,18 @@ extern "C" int lpc_pack_u8(int dtype, const void* src, int B, int Hs, int Ws, in
   const int g = cdiv((long long)B * H * W, 256);
   DISPATCH_T(dtype, (lpc_launch_pdl(pack_u8_kernel<float>, g, 256, 0, s, (const unsigned char*)src, B, Hs, Ws, top, left, H, W, (float)pad_value, swap_rb, (float*)y)),
              (lpc_launch_pdl(pack_u8_kernel<bf16>, g, 256, 0, s, (const unsigned char*)src, B, Hs, Ws, top, left, H, W, (float)pad_value, swap_rb, (bf16*)y)), "pack_u8")
+}
+
+extern "C" int lpc_letterbox_u8(int dtype, const void* src, int B, int hs, int ws, int nh, int nw, const int* xtab, const int* ytab,
+                                int top, int left, int H, int W, int pad_value, int swap_rb, void* y, void* stream) {
+  LPC_REQUIRE(src && y && xtab && ytab && B > 0 && hs > 0 && ws > 0 && nh > 0 && nw > 0, "letterbox_u8: bad argument");
+  LPC_REQUIRE(top >= 0 && left >= 0 && top + nh <= H && left + nw <= W, "letterbox_u8: the resized image does not fit at (%d, %d)", top, left);
+  LPC_REQUIRE(pad_value >= 0 && pad_value <= 255, "letterbox_u8: pad value must be a byte");
+  LPC_REQUIRE(aligned16(y) && (long long)B * H * W < (1ll << 32), "letterbox_u8: output alignment / size");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int g = cdiv((long long)B * H * W, 256);
+  DISPATCH_T(dtype, (lpc_launch_pdl(letterbox_u8_kernel<float>, g, 256, 0, s, (const unsigned char*)src, B, hs, ws, nh, nw, xtab, ytab, top, left, H, W, (float)pad_value, swap_rb, (float*)y)),
+             (lpc_launch_pdl(letterbox_u8_kernel<bf16>, g, 256, 0, s, (const unsigned char*)src, B, hs, ws, nh, nw, xtab, ytab, top, left, H, W, (float)pad_value, swap_rb, (bf16*)y)), "letterbox_u8")
 }
 
 extern "C" int lpc_global_avgpool_chunks(int B, int HW) {

@@ -234,32 +234,35 @@ class YOLOv10DetectionPredictor:
     # ---- array sources: uint8 HWC (cv2 / BGR) images, SURVEY.md section 8(f) row 1 ------------------------------
     @staticmethod
     def letterbox_geometry(shape, imgsz, stride=32, auto=True):
-        """data/augment.py:700-731 LetterBox for one image shape (h, w): -> (H, W, top, left) of the network input.
-        Only ratio 1 (no resize) is implemented; the resize path is listed under "next" in DESIGN.md."""
+        """data/augment.py:700-731 LetterBox for one image shape (h, w) (scaleFill=False, scaleup=True, center=True):
+        -> (H, W, top, left, nh, nw): network input size, where the (nh, nw)-resized image lands in it."""
         new_shape = (imgsz, imgsz) if isinstance(imgsz, int) else tuple(imgsz)
         r = min(new_shape[0] / shape[0], new_shape[1] / shape[1])
-        if r != 1.0:
-            raise NotImplementedError(f"LetterBox resize (ratio {r:.4f}) is not implemented: pass images whose longer side is imgsz")
-        new_unpad = int(round(shape[1] * r)), int(round(shape[0] * r))
+        new_unpad = int(round(shape[1] * r)), int(round(shape[0] * r))         # (w, h)
         dw, dh = new_shape[1] - new_unpad[0], new_shape[0] - new_unpad[1]
         if auto:                                    # minimum rectangle (:716-717)
             dw, dh = dw % stride, dh % stride
         dw, dh = dw / 2, dh / 2                     # center=True (:723-725)
         top, bottom = int(round(dh - 0.1)), int(round(dh + 0.1))
         left, right = int(round(dw - 0.1)), int(round(dw + 0.1))
-        return shape[0] + top + bottom, shape[1] + left + right, top, left
+        nh, nw = new_unpad[1], new_unpad[0]
+        return nh + top + bottom, nw + left + right, top, left, nh, nw
 
     class _GraphedU8:
         """Two CUDA graphs of pack_u8 + ``model.detect`` on two static uint8 input buffers."""
 
         def __init__(self, model, cb, hs, ws, geom, max_det):
             dev = next(model.parameters()).device
-            H, W, top, left = geom
+            H, W, top, left, nh, nw = geom
             self.inp = [torch.full((cb, hs, ws, 3), 114, dtype=torch.uint8, device=dev) for _ in range(2)]
             self.net = [torch.empty((cb, H, W, 4), dtype=model.compute_dtype, device=dev) for _ in range(2)]
+            tables = F.resize_tables(hs, ws, nh, nw, dev) if (nh, nw) != (hs, ws) else None
 
             def run(i):
-                x = F.pack_u8(self.inp[i], model.compute_dtype, top, left, H, W, 114, True, out=self.net[i])
+                if tables is None:                  # LetterBox ratio 1: border + pack only
+                    x = F.pack_u8(self.inp[i], model.compute_dtype, top, left, H, W, 114, True, out=self.net[i])
+                else:                               # cv2.resize(INTER_LINEAR) fused in front
+                    x = F.letterbox_u8(self.inp[i], model.compute_dtype, nh, nw, tables, top, left, H, W, 114, True, out=self.net[i])
                 return model.detect(x, max_det, clip=True)
 
             side = torch.cuda.Stream(device=dev)
@@ -314,7 +317,7 @@ class YOLOv10DetectionPredictor:
             d.record(cur)
             done[(id(gd), b)] = d
             lo += cb
-        self._pad = (geom[2], geom[3], hs, ws)
+        self._pad = (geom[2], geom[3], hs, ws, geom[0], geom[1])
         return preds
 
     @staticmethod
@@ -333,13 +336,19 @@ class YOLOv10DetectionPredictor:
         return source.contiguous()
 
     def scale_back(self, preds):
-        """utils/ops.py:89-124 scale_boxes / :305-324 clip_boxes for gain 1: subtract the LetterBox pad, clip to the image."""
-        top, left, hs, ws = self._pad
-        if top == 0 and left == 0:
+        """utils/ops.py:89-124 scale_boxes (+ clip_boxes :305-324): network-input coordinates -> original image."""
+        top, left, hs, ws, H, W = self._pad
+        gain = min(H / hs, W / ws)                                        # :110
+        pad_w = round((W - ws * gain) / 2 - 0.1)                          # :111-114
+        pad_h = round((H - hs * gain) / 2 - 0.1)
+        if gain == 1.0 and pad_w == 0 and pad_h == 0:
             return preds
         preds = preds.clone()
-        preds[..., [0, 2]] = (preds[..., [0, 2]] - left).clamp_(0, ws)
-        preds[..., [1, 3]] = (preds[..., [1, 3]] - top).clamp_(0, hs)
+        preds[..., [0, 2]] -= pad_w
+        preds[..., [1, 3]] -= pad_h
+        preds[..., :4] /= gain
+        preds[..., [0, 2]] = preds[..., [0, 2]].clamp_(0, ws)
+        preds[..., [1, 3]] = preds[..., [1, 3]].clamp_(0, hs)
         return preds
 
     def postprocess(self, preds, img, orig_imgs):

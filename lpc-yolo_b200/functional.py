@@ -140,6 +140,51 @@ def pack_u8(src, dtype, top=0, left=0, H=None, W=None, pad_value=114, swap_rb=Tr
     return buf.permute(0, 3, 1, 2)[:, :3]
 
 
+def resize_tables(hs, ws, nh, nw, device):
+    """Coefficient tables of OpenCV's 8-bit INTER_LINEAR resize (imgproc/resize.cpp: fx = (float)((dx+0.5)*scale-0.5),
+    cvFloor, border handling, saturate_cast<short>(w * 2048)), as int32 device tensors: xtab [nw,3], ytab [nh,4]."""
+    import numpy as np
+
+    def sat(v):
+        return int(max(-32768, min(32767, np.rint(v))))
+
+    xt = np.empty((nw, 3), np.int32)
+    sx = ws / nw
+    for d in range(nw):
+        f = np.float32((d + 0.5) * sx - 0.5)
+        s0 = int(np.floor(f))
+        f = np.float32(f - np.float32(s0))
+        if s0 < 0:
+            f, s0 = np.float32(0), 0
+        if s0 >= ws - 1:
+            f, s0 = np.float32(0), ws - 1
+        xt[d] = (s0, sat(np.float32(np.float32(1) - f) * np.float32(2048)), sat(f * np.float32(2048)))
+    yt = np.empty((nh, 4), np.int32)
+    sy = hs / nh
+    for d in range(nh):
+        f = np.float32((d + 0.5) * sy - 0.5)
+        s0 = int(np.floor(f))
+        f = np.float32(f - np.float32(s0))        # rows are clamped, the weights are not (unlike x)
+        yt[d] = (min(max(s0, 0), hs - 1), min(max(s0 + 1, 0), hs - 1), sat(np.float32(np.float32(1) - f) * np.float32(2048)), sat(f * np.float32(2048)))
+    return torch.from_numpy(xt).to(device), torch.from_numpy(yt).to(device)
+
+
+@_profiled
+def letterbox_u8(src, dtype, nh, nw, tables, top, left, H, W, pad_value=114, swap_rb=True, out=None):
+    """uint8 HWC images [B,hs,ws,3] -> resized to [nh,nw] (cv2 INTER_LINEAR, bit-exact), bordered to [H,W], /255, BGR->RGB."""
+    if not src.is_cuda:
+        raise LpcError("lpc-yolo_b200 ops run on CUDA tensors only (there is no CPU fallback)")
+    assert src.dtype == torch.uint8 and src.dim() == 4 and src.shape[3] == 3 and src.is_contiguous()
+    B, hs, ws, _ = src.shape
+    xt, yt = tables
+    assert tuple(xt.shape) == (nw, 3) and tuple(yt.shape) == (nh, 4) and xt.dtype == torch.int32 and yt.dtype == torch.int32
+    buf = out if out is not None else torch.empty((B, H, W, 4), dtype=dtype, device=src.device)
+    assert buf.shape == (B, H, W, 4) and buf.dtype == dtype and buf.is_contiguous()
+    check(_lib.lib().lpc_letterbox_u8(dt_code(dtype), _fp(src), B, hs, ws, nh, nw, _fp(xt), _fp(yt), top, left, H, W, pad_value,
+                                      int(swap_rb), _fp(buf), _stream()), "letterbox_u8")
+    return buf.permute(0, 3, 1, 2)[:, :3]
+
+
 def conv2d(x, pc, out=None, res=None, chan_scale=None, rowmax=None):
     """Dense conv through a PackedConv ``pc`` (see pack.py). Chooses tcgen05 when the shape allows."""
     B, Cin, H, W = x.shape

@@ -141,8 +141,12 @@ class v10Detect(Detect):
         if self.training:
             return {"one2many": one2many, "one2one": one2one}
         if self.export:
-            # head.py:521-523: [B, max_det, 6] = boxes(xyxy), score, label  -- one fused kernel pair
-            return F.v10_decode_topk(one2one, [float(s) for s in self.stride], self.nc, self.max_det)
+            # head.py:519-523: cat(boxes, scores, labels) of ops.v10postprocess on y.  The boxes there are gathered from
+            # y as they are, i.e. (cx, cy, w, h) in pixels (decode_bboxes uses dist2bbox(xywh=True), head.py:97-101),
+            # unclipped: the fused tail yields xyxy, converted back here.
+            d = F.v10_decode_topk(one2one, [float(s) for s in self.stride], self.nc, self.max_det)
+            xy1, xy2 = d[..., 0:2], d[..., 2:4]
+            return torch.cat(((xy1 + xy2) / 2, xy2 - xy1, d[..., 4:]), -1)
         return {"one2many": one2many, "one2one": self.inference(one2one)}
 
     def detections(self, x, max_det=None, img_hw=None):

@@ -642,6 +642,13 @@ def synth_input(batch: int, size: int, seed: int = 1) -> torch.Tensor:
     return torch.rand(batch, 3, size, size, generator=g)
 
 
+def export_output(y: torch.Tensor, max_det: int = 300, nc: int = 80) -> torch.Tensor:
+    """v10Detect.forward with export=True (nn/modules/head.py:519-523; engine/exporter.py:227-235 sets the flag): y is
+    Detect.inference's [B,4+nc,A]; -> [B,max_det,6] = (cx, cy, w, h, score, label)."""
+    boxes, scores, labels, _ = v10postprocess(y.permute(0, 2, 1), max_det, nc)
+    return torch.cat([boxes, scores.unsqueeze(-1), labels.unsqueeze(-1).to(boxes.dtype)], dim=-1)
+
+
 # ---- array-source preprocessing (SURVEY.md section 8(f) row 1) ---------------------------------------------------
 def letterbox(img, new_shape=(640, 640), auto=False, stride=32):
     """data/augment.py:684-742 LetterBox.__call__ for one HWC uint8 image (scaleFill=False, scaleup=True, center=True).
@@ -687,4 +694,19 @@ def scale_boxes_unit_gain(boxes, pad_top_left, orig_hw):
     b[..., [1, 3]] -= top
     b[..., [0, 2]] = b[..., [0, 2]].clamp(0, orig_hw[1])
     b[..., [1, 3]] = b[..., [1, 3]].clamp(0, orig_hw[0])
+    return b
+
+
+def scale_boxes(img1_shape, boxes, img0_shape):
+    """utils/ops.py:89-124 scale_boxes (ratio_pad=None, padding=True, xyxy) followed by clip_boxes (:305-324)."""
+    gain = min(img1_shape[0] / img0_shape[0], img1_shape[1] / img0_shape[1])
+    pad = (round((img1_shape[1] - img0_shape[1] * gain) / 2 - 0.1), round((img1_shape[0] - img0_shape[0] * gain) / 2 - 0.1))
+    b = boxes.clone()
+    b[..., 0] -= pad[0]
+    b[..., 1] -= pad[1]
+    b[..., 2] -= pad[0]
+    b[..., 3] -= pad[1]
+    b[..., :4] /= gain
+    b[..., [0, 2]] = b[..., [0, 2]].clamp(0, img0_shape[1])
+    b[..., [1, 3]] = b[..., [1, 3]].clamp(0, img0_shape[0])
     return b

@@ -164,6 +164,31 @@ def test_detections_vs_reference_predict_640(pkg, oracle, name):
     assert all(o <= 1.25 * r + 1e-6 for o, r in zip(ours, ref))
 
 
+@pytest.mark.parametrize("name", ["yolov10n", "lpc"])
+def test_export_mode_head_contract(pkg, oracle, name):
+    """v10Detect.forward with export=True returns [B,max_det,6] = (cx,cy,w,h,score,label)
+    (head.py:519-523) - the fused tail behind the exported-graph contract."""
+    om, pm = _pair(pkg, oracle, name)
+    pm.compute_dtype = torch.float32
+    x = oracle.synth_input(2, 320)
+    head = pm.model[-1]
+    head.export = True
+    try:
+        with torch.no_grad():
+            got = pm(x.cuda()).cpu()
+    finally:
+        head.export = False
+    y, _ = om.forward(x)
+    want = oracle.export_output(y, 300, om.nc)
+    assert got.shape == want.shape == (2, 300, 6)
+
+    def to_xyxy(t):
+        return torch.cat((t[..., :2] - t[..., 2:4] / 2, t[..., :2] + t[..., 2:4] / 2, t[..., 4:]), -1)
+    rate = _match_rate(to_xyxy(got), to_xyxy(want), 1e-2, 2e-4)
+    print(f"{name}: export-mode match rate {rate:.4f}")
+    assert rate >= 0.99
+
+
 def test_predict_api(pkg, oracle):
     om, _ = _pair(pkg, oracle, "yolov10n")
     yolo = pkg.YOLO("yolov10n.yaml")
