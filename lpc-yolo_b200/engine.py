@@ -18,6 +18,7 @@ import numpy as np
 import torch
 
 from . import functional as F
+from .nn import checkpoint
 from .nn.tasks import YOLOv10DetectionModel
 
 DEFAULTS = dict(conf=0.25, max_det=300, classes=None, half=True, device=None, verbose=False, imgsz=640, batch=1,
@@ -409,18 +410,36 @@ class YOLOv10DetectionPredictor:
 class YOLO:
     """models/yolo/model.py:11 YOLO / models/yolov10/model.py:10 YOLOv10 facade, predict side."""
 
-    def __init__(self, model="yolov10n.yaml", task=None, verbose=False):
+    def __init__(self, model="yolov10n.yaml", task=None, verbose=False, names=None):
         self.task = task or "detect"
         self.overrides = {}
         self.callbacks = defaultdict(list)
         self.predictor = None
+        self.ckpt = self.ckpt_path = None
         if isinstance(model, torch.nn.Module):
             self.model = model
-        else:
-            if not str(model).endswith((".yaml", ".yml")):
-                raise NotImplementedError("only model YAMLs are loadable in this round (weights come via load_state_dict)")
+        elif str(model).endswith((".yaml", ".yml")):                       # engine/model.py:195 _new
             self.model = YOLOv10DetectionModel(model, verbose=verbose)
+        elif str(model).endswith(".pt"):                                     # engine/model.py:217 _load
+            self.model, self.ckpt = checkpoint.attempt_load_one_weight(model)
+            self.ckpt_path = self.model.pt_path
+        else:
+            raise NotImplementedError(f"'{model}': a model YAML, a reference .pt checkpoint or (from_pretrained) a local "
+                                      "Hugging Face folder is expected; exported formats are out of scope")
+        if names is not None:                                                # models/yolov10/model.py:15-16
+            self.model.names = names
         self.names = self.model.names
+
+    @classmethod
+    def from_pretrained(cls, folder, **kwargs):
+        """models/yolov10/model.py:10 (PyTorchModelHubMixin.from_pretrained), local folders only - no network."""
+        model, names, task = checkpoint.from_pretrained_dir(folder)
+        return cls(model, task=task, names=names, **kwargs)
+
+    def load(self, weights):
+        """engine/model.py:278-298: transfer matching tensors from a checkpoint / state_dict."""
+        checkpoint.load_into(self.model, weights)
+        return self
 
     def add_callback(self, event, func):
         self.callbacks[event].append(func)
