@@ -2,6 +2,12 @@
 //
 // Channel vectors (16 bytes: 8 bf16 / 4 fp32) are the fastest-varying index across threads -> coalesced 128-bit accesses.
 #include "common.cuh"
+#include "tc_ptx.cuh"
+
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
 
 namespace {
 
@@ -200,6 +206,312 @@ sppf_pool_kernel(const T* __restrict__ x, int x_ld, int H, int W, int C, T* __re
   }
 }
 
+
+// ---- bf16 depthwise conv, TMA-staged (production path) ---------------------------------------------------------------
+// The register-window kernel above spends ~45 % of its ~1060 instructions per thread on addressing and bounds
+// predicates of its 18 global loads and hides their latency only through occupancy (ncu: issue-active 52 %, warps
+// active 22 %, profiles/r01_h_ncu_dwconv.md).  Here a persistent CTA receives the whole input tile - TH x TW outputs
+// plus the filter halo, CB channels - as ONE 4-D TMA box per tile (zero fill outside the map = the conv padding, so no
+// predicates), double buffered on two mbarriers; every thread owns one 16-byte channel vector of PX adjacent outputs
+// and reads its (K rows) x (NV columns) window with LDS.128 at tile-constant offsets.  Outputs go straight from
+// registers to global memory (16-byte stores, a 64/128-byte run per pixel).
+
+// acc0 += lo(x) * lo(w), acc1 += hi(x) * hi(w): bf16 operands taken straight from the packed words, fp32 accumulate
+__device__ __forceinline__ void fhfma2(float& a0, float& a1, uint32_t x, uint32_t w) {
+  asm("{\n\t.reg .b16 xl, xh, wl, wh;\n\t"
+      "mov.b32 {xl, xh}, %2;\n\t"
+      "mov.b32 {wl, wh}, %3;\n\t"
+      "fma.rn.f32.bf16 %0, xl, wl, %0;\n\t"
+      "fma.rn.f32.bf16 %1, xh, wh, %1;\n\t}"
+      : "+f"(a0), "+f"(a1)
+      : "r"(x), "r"(w));
+}
+
+struct DwTmaParams {
+  int C, Ho, Wo, B;
+  int CB, CV, XG, TH;          // tile = TH rows x (XG * PX) columns x CB channels; CV = CB / 8 channel vectors
+  int IW, IH;                  // input tile extent (with halo)
+  int tiles_x, tiles_y, cblks, ntiles;
+  int pad, act;
+  float inv_tiles_x, inv_tiles_y;   // fast_div reciprocals (ntiles < 2^24 checked on the host)
+  unsigned stage_bytes, tx_bytes;   // ring slot pitch (128-byte multiple) / bytes one box delivers
+  const float* w;
+  const float* bias;
+  bf16* y;
+  int y_ld;
+  const bf16* res;
+  int res_ld;
+};
+
+template <int K, int S, int D, int PX>
+__global__ void __launch_bounds__(256, 2)
+dwconv_tma_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ DwTmaParams p) {
+  extern __shared__ __align__(128) unsigned char dw_smem[];
+  __shared__ __align__(8) unsigned long long dw_bars[2];
+  constexpr int NV = (PX - 1) * S + (K - 1) * D + 1;
+  constexpr bool WREG = (K == 3);            // 9 taps x 4 packed words = 36 registers; larger filters read shared memory
+  const uint32_t base = (smem_u32(dw_smem) + 127u) & ~127u;
+  const uint32_t wsm = base + 2u * p.stage_bytes;          // [K*K][CB] bf16: this CTA's filter taps
+  const uint32_t bar0 = smem_u32(&dw_bars[0]);
+  const int tid = threadIdx.x;
+  const int cb = blockIdx.y;                 // the channel block is fixed per CTA: its taps are staged ONCE
+  if (tid == 0) {
+    prefetch_tmap(&map);
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // fp32 taps -> bf16 in shared memory (weights are not produced by the previous kernel: this runs before pdl_wait)
+  for (int i = tid; i < K * K * (p.CB / 2); i += 256) {
+    const int tap = i / (p.CB / 2), c = (i - tap * (p.CB / 2)) * 2;
+    const float2 wf = __ldg(reinterpret_cast<const float2*>(p.w + (long long)tap * p.C + cb * p.CB + c));
+    const __nv_bfloat162 h = __floats2bfloat162_rn(wf.x, wf.y);
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(wsm + (uint32_t)(tap * p.CB + c) * 2u), "r"(*reinterpret_cast<const uint32_t*>(&h)));
+  }
+  __syncthreads();
+  pdl_trigger();
+  pdl_wait();
+
+  auto issue = [&](int t, int stage) {       // one elected thread: arm the barrier, fetch spatial tile t of this channel block
+    const int r1 = fast_div(t, p.tiles_x, p.inv_tiles_x), tx = t - r1 * p.tiles_x;
+    const int n = fast_div(r1, p.tiles_y, p.inv_tiles_y), ty = r1 - n * p.tiles_y;
+    mbar_expect_tx(bar0 + 8u * stage, p.tx_bytes);
+    tma_load_4d(base + stage * p.stage_bytes, &map, bar0 + 8u * stage, cb * p.CB, tx * (p.XG * PX) * S - p.pad,
+                ty * p.TH * S - p.pad, n);
+  };
+
+  // this thread's work item inside every tile
+  const int items = p.TH * p.XG * p.CV;
+  const bool worker = tid < items;
+  const int cv = tid % p.CV;
+  const int xg = (tid / p.CV) % p.XG;
+  const int ry = tid / (p.CV * p.XG);
+  const uint32_t pix_b = (uint32_t)p.CB * 2u, row_b = (uint32_t)p.IW * pix_b;
+  const uint32_t my_off = (uint32_t)(ry * S) * row_b + (uint32_t)(xg * PX * S) * pix_b + (uint32_t)cv * 16u;
+  const int c0 = cb * p.CB + cv * 8;
+  const uint32_t wsrc = wsm + (uint32_t)cv * 16u;
+
+  uint4 wreg[WREG ? K * K : 1];
+  if (WREG) {
+#pragma unroll
+    for (int tap = 0; tap < K * K; ++tap)
+      asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(wreg[tap].x), "=r"(wreg[tap].y), "=r"(wreg[tap].z), "=r"(wreg[tap].w)
+                   : "r"(wsrc + (uint32_t)tap * pix_b));
+  }
+  float bv[8];
+  {
+    const float4 b0 = (p.bias && worker) ? __ldg(reinterpret_cast<const float4*>(p.bias + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 b1 = (p.bias && worker) ? __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+  }
+
+  int t = blockIdx.x;
+  if (tid == 0 && t < p.ntiles) issue(t, 0);
+  int it = 0;
+  for (; t < p.ntiles; t += gridDim.x, ++it) {
+    const int stage = it & 1;
+    const int tn = t + gridDim.x;
+    if (tid == 0 && tn < p.ntiles) issue(tn, stage ^ 1);    // the other buffer was released by the barrier below
+    const int r1 = fast_div(t, p.tiles_x, p.inv_tiles_x), tx = t - r1 * p.tiles_x;
+    const int n = fast_div(r1, p.tiles_y, p.inv_tiles_y), ty = r1 - n * p.tiles_y;
+    const int oy = ty * p.TH + ry, ox0 = (tx * p.XG + xg) * PX;
+
+    mbar_wait(bar0 + 8u * stage, (uint32_t)((it >> 1) & 1));
+    if (worker) {
+      const uint32_t src = base + stage * p.stage_bytes + my_off;
+      // bf16 x bf16 -> fp32 mixed-precision FMA (fma.rn.f32.bf16 = one FHFMA.BF16 with .H0/.H1 operand selectors): the
+      // packed input words are consumed as they are, so there is no bf16 -> fp32 unpack at all (it was ~45 % of the
+      // ALU-pipe work of the fp32 FFMA2 formulation); the BN-folded filter taps are rounded to bf16 like the weights of
+      // every dense conv of this mode, products are exact and the accumulation stays fp32.
+      float acc[PX][8];
+#pragma unroll
+      for (int q = 0; q < PX; ++q)
+#pragma unroll
+        for (int v = 0; v < 8; ++v) acc[q][v] = bv[v];
+#pragma unroll
+      for (int ky = 0; ky < K; ++ky) {
+        uint4 in[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j)
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(in[j].x), "=r"(in[j].y), "=r"(in[j].z), "=r"(in[j].w)
+                       : "r"(src + (uint32_t)(ky * D) * row_b + (uint32_t)j * pix_b));
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+          uint4 wq;
+          if (WREG) {
+            wq = wreg[ky * K + kx];
+          } else {
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(wq.x), "=r"(wq.y), "=r"(wq.z), "=r"(wq.w)
+                         : "r"(wsrc + (uint32_t)(ky * K + kx) * pix_b));
+          }
+#pragma unroll
+          for (int q = 0; q < PX; ++q) {
+            const uint4 xv = in[q * S + kx * D];
+            fhfma2(acc[q][0], acc[q][1], xv.x, wq.x);
+            fhfma2(acc[q][2], acc[q][3], xv.y, wq.y);
+            fhfma2(acc[q][4], acc[q][5], xv.z, wq.z);
+            fhfma2(acc[q][6], acc[q][7], xv.w, wq.w);
+          }
+        }
+      }
+      float2 acc2[PX][4];
+#pragma unroll
+      for (int q = 0; q < PX; ++q)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc2[q][v] = make_float2(acc[q][2 * v], acc[q][2 * v + 1]);
+      switch (p.act) {
+        case LPC_ACT_NONE: break;
+        case LPC_ACT_SILU:
+#pragma unroll
+          for (int q = 0; q < PX; ++q)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc2[q][v] = silu2_(acc2[q][v]);
+          break;
+        case LPC_ACT_MISH:
+#pragma unroll
+          for (int q = 0; q < PX; ++q)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc2[q][v] = mish2_(acc2[q][v]);
+          break;
+        default:
+#pragma unroll
+          for (int q = 0; q < PX; ++q)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              acc2[q][v].x = apply_act<false>(acc2[q][v].x, p.act);
+              acc2[q][v].y = apply_act<false>(acc2[q][v].y, p.act);
+            }
+          break;
+      }
+      if (oy < p.Ho) {
+#pragma unroll
+        for (int q = 0; q < PX; ++q) {
+          const int ox = ox0 + q;
+          if (ox >= p.Wo) break;
+          const long long opix = (long long)(n * p.Ho + oy) * p.Wo + ox;
+          if (p.res) {
+            float rr[8];
+            ld_vec<bf16>(p.res + opix * p.res_ld + c0).unpack(rr);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) { acc2[q][v].x += rr[2 * v]; acc2[q][v].y += rr[2 * v + 1]; }
+          }
+          uint4 o;
+          __nv_bfloat162 h;
+          h = __floats2bfloat162_rn(acc2[q][0].x, acc2[q][0].y); o.x = *reinterpret_cast<uint32_t*>(&h);
+          h = __floats2bfloat162_rn(acc2[q][1].x, acc2[q][1].y); o.y = *reinterpret_cast<uint32_t*>(&h);
+          h = __floats2bfloat162_rn(acc2[q][2].x, acc2[q][2].y); o.z = *reinterpret_cast<uint32_t*>(&h);
+          h = __floats2bfloat162_rn(acc2[q][3].x, acc2[q][3].y); o.w = *reinterpret_cast<uint32_t*>(&h);
+          *reinterpret_cast<uint4*>(p.y + opix * p.y_ld + c0) = o;
+        }
+      }
+    }
+    __syncthreads();          // every read of this stage is done: the next iteration may refill it
+  }
+}
+
+typedef CUresult (*DwEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+DwEncodeFn dw_get_encode() {
+  static DwEncodeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<DwEncodeFn>(f);
+  });
+  return fn;
+}
+int dw_num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// returns LPC_OK when launched, 1 when the shape is left to the register-window kernel
+template <int K, int S, int D>
+int launch_dw_tma(const void* x, int x_ld, int B, int H, int W, int C, const float* w, const float* bias, int pad,
+                  int Ho, int Wo, void* y, int y_ld, int act, const void* res, int res_ld, cudaStream_t s) {
+  constexpr int PX = (K == 7) ? 2 : 4;
+  static const int enabled = [] { const char* e = getenv("LPC_DW_TMA"); return e ? atoi(e) : 1; }();
+  DwEncodeFn enc = dw_get_encode();
+  if (!enabled || !enc || C % 8 || H > 65535 || W > 65535) return 1;
+  // tile search: CB channels (a divisor of C, multiple of 8, <= 128), XG x-groups of PX outputs, TH rows, at most 256
+  // work items; minimise the number of tile passes, then the halo overhead
+  DwTmaParams p;
+  memset(&p, 0, sizeof(p));
+  double best = 1e30;
+  for (int cbv = 1; cbv <= 16; ++cbv) {
+    if ((C / 8) % cbv) continue;
+    if (cbv % 4 && cbv != C / 8) continue;      // 64-byte runs per pixel (or the whole pixel): full 32-byte sectors
+    for (int th = 4; th <= 16; th *= 2)
+      for (int xg = 1; xg * cbv * th <= 256; ++xg) {
+        const int tw = xg * PX;
+        const int iw = (tw - 1) * S + (K - 1) * D + 1, ih = (th - 1) * S + (K - 1) * D + 1;
+        if (iw > 256 || ih > 256) continue;
+        const size_t bytes = (size_t)iw * ih * cbv * 16;
+        if (bytes > 44 * 1024) continue;
+        const double tiles = (double)((Wo + tw - 1) / tw) * ((Ho + th - 1) / th) * (C / 8 / cbv);
+        // cost ~ per-tile pass (fixed 256-thread sweep + barrier) plus the bytes the tile moves
+        const double cost = tiles * (1.0 + (double)bytes / (24.0 * 1024));
+        if (cost < best) {
+          best = cost;
+          p.CV = cbv; p.CB = cbv * 8; p.XG = xg; p.TH = th; p.IW = iw; p.IH = ih;
+          p.stage_bytes = (unsigned)((bytes + 127) & ~(size_t)127);
+          p.tx_bytes = (unsigned)bytes;
+        }
+      }
+  }
+  if (best >= 1e30) return 1;
+  p.C = C; p.Ho = Ho; p.Wo = Wo; p.B = B;
+  p.tiles_x = (Wo + p.XG * PX - 1) / (p.XG * PX);
+  p.tiles_y = (Ho + p.TH - 1) / p.TH;
+  p.cblks = C / p.CB;
+  const long long nt = (long long)p.tiles_x * p.tiles_y * B;      // spatial tiles per channel block
+  if (nt >= (1ll << 24)) return 1;
+  p.ntiles = (int)nt;
+  p.inv_tiles_x = 1.0f / (float)p.tiles_x;
+  p.inv_tiles_y = 1.0f / (float)p.tiles_y;
+  p.pad = pad; p.act = act; p.w = w; p.bias = bias;
+  p.y = (bf16*)y; p.y_ld = y_ld; p.res = (const bf16*)res; p.res_ld = res_ld;
+  CUtensorMap map;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)x_ld * 2, (cuuint64_t)W * x_ld * 2, (cuuint64_t)H * W * x_ld * 2};
+    cuuint32_t box[4] = {(cuuint32_t)p.CB, (cuuint32_t)p.IW, (cuuint32_t)p.IH, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return 1;
+  }
+  const size_t smem = 2 * (size_t)p.stage_bytes + (size_t)K * K * p.CB * 2 + 128;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(dwconv_tma_kernel<K, S, D, PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr_done = true;
+  }
+  const int per_sm = (int)((200 * 1024) / (smem + 1024));
+  (void)per_sm;
+  long long gx = (2ll * dw_num_sms() + p.cblks - 1) / p.cblks;      // two resident CTAs per SM in total, split over the channel blocks
+  if (gx > nt) gx = nt;
+  if (gx < 1) gx = 1;
+  if (p.cblks > 65535) return 1;
+  lpc_launch_pdl(dwconv_tma_kernel<K, S, D, PX>, dim3((unsigned)gx, (unsigned)p.cblks), 256, smem, s, map, p);
+  LPC_CHECK_LAUNCH("dwconv2d(tma)");
+  return LPC_OK;
+}
+
 template <typename T, int K, int S, int D>
 int launch_dw(const void* x, int x_ld, int B, int H, int W, int C, const float* w, const float* bias, int pad,
               int Ho, int Wo, void* y, int y_ld, int act, const void* res, int res_ld, cudaStream_t s) {
@@ -218,8 +530,14 @@ template <typename T>
 int dispatch_dw(const void* x, int x_ld, int B, int H, int W, int C, const float* w, const float* bias, int k,
                 int stride, int pad, int dil, int Ho, int Wo, void* y, int y_ld, int act, const void* res,
                 int res_ld, cudaStream_t s) {
-#define DW(K_, S_, D_) \
-  if (k == K_ && stride == S_ && dil == D_) return launch_dw<T, K_, S_, D_>(x, x_ld, B, H, W, C, w, bias, pad, Ho, Wo, y, y_ld, act, res, res_ld, s);
+#define DW(K_, S_, D_)                                                                                                      \
+  if (k == K_ && stride == S_ && dil == D_) {                                                                               \
+    if (sizeof(T) == 2) {                                                                                                   \
+      const int r = launch_dw_tma<K_, S_, D_>(x, x_ld, B, H, W, C, w, bias, pad, Ho, Wo, y, y_ld, act, res, res_ld, s);      \
+      if (r != 1) return r;                                                                                                 \
+    }                                                                                                                       \
+    return launch_dw<T, K_, S_, D_>(x, x_ld, B, H, W, C, w, bias, pad, Ho, Wo, y, y_ld, act, res, res_ld, s);               \
+  }
   DW(3, 1, 1) DW(3, 2, 1) DW(3, 1, 2) DW(3, 1, 3) DW(5, 1, 1) DW(5, 2, 1) DW(7, 1, 1) DW(7, 2, 1)
 #undef DW
   LPC_FAIL(LPC_E_UNSUPPORTED, "dwconv2d: k=%d stride=%d dilation=%d not supported", k, stride, dil);

