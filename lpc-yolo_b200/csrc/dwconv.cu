@@ -144,68 +144,71 @@ dwconv_kernel(const T* __restrict__ x, int x_ld, int B, int H, int W, int C,
   }
 }
 
-// SPPF: three chained MaxPool2d(5,1,2) (-inf padding).  One CTA owns one image x 8 channels, keeps the whole map in
-// shared memory and runs each 5x5 pool as a separable row pass + column pass (10 compares instead of 25); pool i's
-// result is stored to its concat slice and is the input of pool i+1.
+// SPPF: three chained MaxPool2d(5,1,2) (-inf padding).  One CTA owns one image x VP 16-byte channel vectors per pixel
+// (2 x 8 bf16 channels), keeps the whole map in shared memory IN ITS NATIVE TYPE - max needs no arithmetic, so bf16
+// pairs are compared packed (HMNMX2.BF16) and nothing is converted - and runs each 5x5 pool as a separable row pass +
+// column pass; the three pool outputs go to channel slices [0,C), [C,2C), [2C,3C) of y with 16-byte stores.  The first
+// version staged fp32 float4 pairs per pixel: twice the shared-memory traffic for the same channels and 2-way bank
+// conflicts in the column pass (33 us for 6.5 MB, profiles/r01_k_per_launch_lpc_b64.csv).
+template <typename T> __device__ __forceinline__ uint4 vec_max(uint4 a, uint4 b);
+template <> __device__ __forceinline__ uint4 vec_max<bf16>(uint4 a, uint4 b) {
+  uint4 r;
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+  return r;
+}
+template <> __device__ __forceinline__ uint4 vec_max<float>(uint4 a, uint4 b) {
+  uint4 r;
+  r.x = __float_as_uint(fmaxf(__uint_as_float(a.x), __uint_as_float(b.x)));
+  r.y = __float_as_uint(fmaxf(__uint_as_float(a.y), __uint_as_float(b.y)));
+  r.z = __float_as_uint(fmaxf(__uint_as_float(a.z), __uint_as_float(b.z)));
+  r.w = __float_as_uint(fmaxf(__uint_as_float(a.w), __uint_as_float(b.w)));
+  return r;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
-sppf_pool_kernel(const T* __restrict__ x, int x_ld, int H, int W, int C, T* __restrict__ y, int y_ld) {
+sppf_pool_kernel(const T* __restrict__ x, int x_ld, int H, int W, int C, T* __restrict__ y, int y_ld, int VP) {
   pdl_trigger();
   pdl_wait();
   constexpr int V = Vec<T>::N;
-  extern __shared__ float4 sp4[];
-  const int HW = H * W;
-  float4* a = sp4;               // [HW][2] float4 = 8 channels per pixel
-  float4* b = sp4 + HW * 2;
-  const int n = blockIdx.y, c0 = blockIdx.x * 8;
+  extern __shared__ uint4 sp4[];
+  const int HW = H * W, items = HW * VP;
+  uint4* a = sp4;                 // [HW][VP]
+  uint4* b = sp4 + items;
+  const int n = blockIdx.y, c0 = blockIdx.x * VP * V;
   const T* xin = x + (long long)n * HW * x_ld + c0;
   T* yo = y + (long long)n * HW * y_ld + c0;
-  for (int p = threadIdx.x; p < HW; p += blockDim.x) {          // thread = pixel: 16-byte loads
-    float f[8];
-#pragma unroll
-    for (int v = 0; v < 8; v += V) ldg_vec<T>(xin + (long long)p * x_ld + v).unpack(f + v);
-    a[p * 2] = make_float4(f[0], f[1], f[2], f[3]);
-    a[p * 2 + 1] = make_float4(f[4], f[5], f[6], f[7]);
+  for (int e = threadIdx.x; e < items; e += blockDim.x) {
+    const int p = e / VP, j = e - p * VP;
+    a[e] = __ldg(reinterpret_cast<const uint4*>(xin + (long long)p * x_ld + j * V));
   }
   __syncthreads();
-  auto max4 = [](float4 u, float4 v) { return make_float4(fmaxf(u.x, v.x), fmaxf(u.y, v.y), fmaxf(u.z, v.z), fmaxf(u.w, v.w)); };
   for (int pool = 0; pool < 3; ++pool) {
-    for (int e = threadIdx.x; e < HW * 2; e += blockDim.x) {     // row pass a -> b (thread = pixel x 4 channels)
-      const int p = e >> 1, py = p / W, px = p - py * W;
-      float4 m = a[e];
+    for (int e = threadIdx.x; e < items; e += blockDim.x) {     // row pass a -> b: consecutive lanes, consecutive 16-byte words
+      const int p = e / VP, px = p % W;
+      uint4 m = a[e];
 #pragma unroll
-      for (int d = -2; d <= 2; ++d) {
-        const int xx = px + d;
-        if (d != 0 && xx >= 0 && xx < W) m = max4(m, a[e + 2 * d]);
-      }
+      for (int d = -2; d <= 2; ++d)
+        if (d != 0 && px + d >= 0 && px + d < W) m = vec_max<T>(m, a[e + d * VP]);
       b[e] = m;
     }
     __syncthreads();
-    for (int p = threadIdx.x; p < HW; p += blockDim.x) {         // column pass b -> a (+ 16-byte stores)
-      const int py = p / W;
-      float4 m0 = b[p * 2], m1 = b[p * 2 + 1];
+    for (int e = threadIdx.x; e < items; e += blockDim.x) {     // column pass b -> a (+ 16-byte stores)
+      const int p = e / VP, j = e - p * VP, py = p / W;
+      uint4 m = b[e];
 #pragma unroll
-      for (int d = -2; d <= 2; ++d) {
-        const int yy = py + d;
-        if (d != 0 && yy >= 0 && yy < H) {
-          m0 = max4(m0, b[(p + d * W) * 2]);
-          m1 = max4(m1, b[(p + d * W) * 2 + 1]);
-        }
-      }
-      a[p * 2] = m0;
-      a[p * 2 + 1] = m1;
-      const float f[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-#pragma unroll
-      for (int v = 0; v < 8; v += V) {
-        Vec<T> o;
-        o.pack(f + v);
-        st_vec<T>(yo + (long long)p * y_ld + pool * C + v, o);
-      }
+      for (int d = -2; d <= 2; ++d)
+        if (d != 0 && py + d >= 0 && py + d < H) m = vec_max<T>(m, b[e + d * W * VP]);
+      a[e] = m;
+      *reinterpret_cast<uint4*>(yo + (long long)p * y_ld + pool * C + j * V) = m;
     }
     __syncthreads();
   }
 }
-
 
 // ---- bf16 depthwise conv, TMA-staged (production path) ---------------------------------------------------------------
 // The register-window kernel above spends ~45 % of its ~1060 instructions per thread on addressing and bounds
@@ -569,17 +572,19 @@ extern "C" int lpc_sppf_pool(int dtype, const void* x, int x_ld, int B, int H, i
   const int V = dtype == LPC_F32 ? 4 : 8;
   LPC_REQUIRE(C % V == 0 && x_ld % V == 0 && y_ld % V == 0 && y_ld >= 3 * C, "sppf_pool: C / pitch constraints");
   LPC_REQUIRE(aligned16(x) && aligned16(y), "sppf_pool: pointers must be 16-byte aligned");
-  LPC_REQUIRE(C % 8 == 0, "sppf_pool: C must be a multiple of 8");
-  const size_t smem = (size_t)H * W * 8 * 2 * sizeof(float);
+  // two 16-byte channel vectors per pixel per CTA when the channel count and the shared-memory budget allow
+  int VP = (C % (2 * V) == 0 && (size_t)H * W * 2 * 16 * 2 <= 100 * 1024) ? 2 : 1;
+  const size_t smem = (size_t)H * W * VP * 16 * 2;
   LPC_REQUIRE(smem <= 200 * 1024, "sppf_pool: map too large for the shared-memory pooling kernel (%d x %d)", H, W);
+  LPC_REQUIRE(B <= 65535, "sppf_pool: batch too large");
   cudaStream_t s = (cudaStream_t)stream;
-  dim3 grid(C / 8, B);
+  dim3 grid(C / (VP * V), B);
   if (dtype == LPC_F32) {
     cudaFuncSetAttribute(sppf_pool_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    lpc_launch_pdl(sppf_pool_kernel<float>, grid, 256, smem, s, (const float*)x, x_ld, H, W, C, (float*)y, y_ld);
+    lpc_launch_pdl(sppf_pool_kernel<float>, grid, 256, smem, s, (const float*)x, x_ld, H, W, C, (float*)y, y_ld, VP);
   } else if (dtype == LPC_BF16) {
     cudaFuncSetAttribute(sppf_pool_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    lpc_launch_pdl(sppf_pool_kernel<bf16>, grid, 256, smem, s, (const bf16*)x, x_ld, H, W, C, (bf16*)y, y_ld);
+    lpc_launch_pdl(sppf_pool_kernel<bf16>, grid, 256, smem, s, (const bf16*)x, x_ld, H, W, C, (bf16*)y, y_ld, VP);
   } else
     LPC_FAIL(LPC_E_ARG, "sppf_pool: unknown dtype %d", dtype);
   LPC_CHECK_LAUNCH("sppf_pool");

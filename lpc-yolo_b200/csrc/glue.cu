@@ -237,13 +237,25 @@ __global__ void global_avgpool_kernel(const T* __restrict__ x, int x_ld, int HW,
     float acc[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) acc[v] = 0.f;
-    if (cv < cvecs && pl < PL)
-      for (int p = p0 + pl; p < p1; p += PL) {
+    if (cv < cvecs && pl < PL) {
+      int p = p0 + pl;
+      for (; p + 3 * PL < p1; p += 4 * PL) {          // four independent 16-byte loads in flight, summed in pixel order
+        Vec<T> t0 = ldg_vec<T>(base + (long long)p * x_ld + cv * V);
+        Vec<T> t1 = ldg_vec<T>(base + (long long)(p + PL) * x_ld + cv * V);
+        Vec<T> t2 = ldg_vec<T>(base + (long long)(p + 2 * PL) * x_ld + cv * V);
+        Vec<T> t3 = ldg_vec<T>(base + (long long)(p + 3 * PL) * x_ld + cv * V);
+        float f0[V], f1[V], f2[V], f3[V];
+        t0.unpack(f0); t1.unpack(f1); t2.unpack(f2); t3.unpack(f3);
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[v] = (((acc[v] + f0[v]) + f1[v]) + f2[v]) + f3[v];
+      }
+      for (; p < p1; p += PL) {
         float f[V];
         ldg_vec<T>(base + (long long)p * x_ld + cv * V).unpack(f);
 #pragma unroll
         for (int v = 0; v < V; ++v) acc[v] += f[v];
       }
+    }
 #pragma unroll
     for (int v = 0; v < V; ++v) part[threadIdx.x * V + v] = acc[v];
     __syncthreads();
@@ -259,7 +271,9 @@ __global__ void global_avgpool_kernel(const T* __restrict__ x, int x_ld, int HW,
   }
 }
 
-// tiny per-image MLP on pooled vectors; one block per image.
+// tiny per-image MLP on pooled vectors; one block per image.  A warp owns an output: its lanes stride over the weight row
+// (coalesced) and reduce with shuffles - the per-thread serial dot product it replaces walked the rows with a stride of C0
+// floats between threads and was pure load latency (7-13 us for a few KFLOP, profiles/r01_k_per_launch_lpc_b64.csv).
 __global__ void channel_mlp_kernel(const float* __restrict__ in, int parts, float in_scale, int C0, const float* __restrict__ W1,
                                    const float* __restrict__ b1, int C1, int act1, const float* __restrict__ W2,
                                    const float* __restrict__ b2, int C2, int act2, float* __restrict__ out) {
@@ -269,66 +283,128 @@ __global__ void channel_mlp_kernel(const float* __restrict__ in, int parts, floa
   float* v0 = sm;
   float* v1 = sm + C0;
   const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int i = threadIdx.x; i < C0; i += blockDim.x) {
     float t = 0.f;
-    for (int q = 0; q < parts; ++q) t += in[((long long)b * parts + q) * C0 + i];
+    for (int q = 0; q < parts; ++q) t += in[((long long)b * parts + q) * C0 + i];   // fixed order: deterministic
     v0[i] = t * in_scale;
   }
   __syncthreads();
-  for (int o = threadIdx.x; o < C1; o += blockDim.x) {
-    float s = b1 ? b1[o] : 0.f;
+  for (int o = warp; o < C1; o += nwarps) {
     const float* wr = W1 + (long long)o * C0;
-    for (int i = 0; i < C0; ++i) s = fmaf(wr[i], v0[i], s);
-    s = apply_act<true>(s, act1);
-    if (W2) v1[o] = s; else out[(long long)b * C1 + o] = s;
+    float s = 0.f;
+    for (int i = lane; i < C0; i += 32) s = fmaf(__ldg(wr + i), v0[i], s);
+#pragma unroll
+    for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (lane == 0) {
+      s = apply_act<true>(s + (b1 ? b1[o] : 0.f), act1);
+      if (W2) v1[o] = s; else out[(long long)b * C1 + o] = s;
+    }
   }
   if (!W2) return;
   __syncthreads();
-  for (int o = threadIdx.x; o < C2; o += blockDim.x) {
-    float s = b2 ? b2[o] : 0.f;
-    const float* wr = W2 + (long long)o * C1;
-    for (int i = 0; i < C1; ++i) s = fmaf(wr[i], v1[i], s);
-    out[(long long)b * C2 + o] = apply_act<true>(s, act2);
+  if (C1 <= 32) {        // short hidden vector (C/16): a thread per output, the row is a handful of floats
+    for (int o = threadIdx.x; o < C2; o += blockDim.x) {
+      float s = b2 ? b2[o] : 0.f;
+      const float* wr = W2 + (long long)o * C1;
+      for (int i = 0; i < C1; ++i) s = fmaf(__ldg(wr + i), v1[i], s);
+      out[(long long)b * C2 + o] = apply_act<true>(s, act2);
+    }
+  } else {
+    for (int o = warp; o < C2; o += nwarps) {
+      const float* wr = W2 + (long long)o * C1;
+      float s = 0.f;
+      for (int i = lane; i < C1; i += 32) s = fmaf(__ldg(wr + i), v1[i], s);
+#pragma unroll
+      for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+      if (lane == 0) out[(long long)b * C2 + o] = apply_act<true>(s + (b2 ? b2[o] : 0.f), act2);
+    }
   }
 }
 
-// LPP lanes (a power of two <= 32) share one pixel, each owning 16-byte channel vectors: mean_c and max_c of x*ca
+// LPP lanes (a power of two <= 32) share one pixel, each owning 16-byte channel vectors: mean_c and max_c of x*ca.
+// grid (chunks, B): a CTA stays inside one image, so a lane's channel-attention weights ca[b][c] are loaded ONCE into
+// registers (the first version re-loaded 2 x 16 bytes of ca for every 16 bytes of x: the LSU, not HBM, set its speed);
+// 4 pixels are in flight per lane group.
 template <typename T>
-__global__ void cbam_stats_kernel(const T* __restrict__ x, int x_ld, int B, int HW, int C, int lpp, const float* __restrict__ ca,
-                                  float* __restrict__ stats) {
+__global__ void __launch_bounds__(256)
+cbam_stats_kernel(const T* __restrict__ x, int x_ld, int B, int HW, int C, int lpp, const float* __restrict__ ca,
+                  float* __restrict__ stats) {
   pdl_trigger();
   pdl_wait();
   constexpr int V = Vec<T>::N;
-  const unsigned gt = blockIdx.x * blockDim.x + threadIdx.x;       // 32-bit index math (host checks the range); lpp is a power of two
-  const unsigned gp = gt / (unsigned)lpp;
-  const int sub = (int)(gt & (unsigned)(lpp - 1));
-  const bool live = gp < (unsigned)B * (unsigned)HW;
-  float s = 0.f, m = -INFINITY;
-  if (live) {
-    const int b = (int)(gp / (unsigned)HW);
-    const T* px = x + (long long)gp * x_ld;
-    const float* cab = ca + (long long)b * C;
-    for (int c = sub * V; c < C; c += lpp * V) {
-      float f[V], g[V];
-      ldg_vec<T>(px + c).unpack(f);
+  const int b = blockIdx.y;
+  const int sub = threadIdx.x & (lpp - 1);
+  const int grp = threadIdx.x / lpp, ngrp = 256 / lpp;
+  const int chunk_pix = (HW + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * chunk_pix, p1 = min(HW, p0 + chunk_pix);
+  const T* img = x + (long long)b * HW * x_ld;
+  const float* cab = ca + (long long)b * C;
+  float2* so = reinterpret_cast<float2*>(stats) + (long long)b * HW;
+  const bool single = C <= lpp * V;          // one vector per lane (C <= 256 in bf16): ca lives in registers
+  float g0[V];
+  if (single) {
 #pragma unroll
-      for (int v = 0; v < V; v += 4) {
-        const float4 c4 = __ldg(reinterpret_cast<const float4*>(cab + c + v));
-        g[v] = c4.x; g[v + 1] = c4.y; g[v + 2] = c4.z; g[v + 3] = c4.w;
-      }
-#pragma unroll
-      for (int v = 0; v < V; ++v) {
-        const float t = f[v] * g[v];
-        s += t;
-        m = fmaxf(m, t);
-      }
+    for (int v = 0; v < V; v += 4) {
+      const float4 c4 = sub * V < C ? __ldg(reinterpret_cast<const float4*>(cab + sub * V + v)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      g0[v] = c4.x; g0[v + 1] = c4.y; g0[v + 2] = c4.z; g0[v + 3] = c4.w;
     }
   }
-  for (int o = lpp >> 1; o; o >>= 1) {
-    s += __shfl_xor_sync(0xffffffffu, s, o);
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  constexpr int U = 4;
+  for (int pb = p0 + grp; pb < p1; pb += ngrp * U) {
+    float s[U], m[U];
+    if (single) {
+      Vec<T> xv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int p = pb + u * ngrp;
+        xv[u].raw = make_uint4(0, 0, 0, 0);
+        if (p < p1 && sub * V < C) xv[u] = ldg_vec<T>(img + (long long)p * x_ld + sub * V);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float f[V];
+        xv[u].unpack(f);
+        s[u] = 0.f;
+        m[u] = -INFINITY;
+        if (sub * V < C) {
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            const float t = f[v] * g0[v];
+            s[u] += t;
+            m[u] = fmaxf(m[u], t);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int p = pb + u * ngrp;
+        s[u] = 0.f;
+        m[u] = -INFINITY;
+        if (p < p1)
+          for (int c = sub * V; c < C; c += lpp * V) {
+            float f[V];
+            ldg_vec<T>(img + (long long)p * x_ld + c).unpack(f);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              const float t = f[v] * __ldg(cab + c + v);
+              s[u] += t;
+              m[u] = fmaxf(m[u], t);
+            }
+          }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      for (int o = lpp >> 1; o; o >>= 1) {
+        s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+        m[u] = fmaxf(m[u], __shfl_xor_sync(0xffffffffu, m[u], o));
+      }
+      const int p = pb + u * ngrp;
+      if (p < p1 && sub == 0) so[p] = make_float2(s[u] / (float)C, m[u]);
+    }
   }
-  if (live && sub == 0) reinterpret_cast<float2*>(stats)[gp] = make_float2(s / (float)C, m);
 }
 
 // gate = sigmoid(conv_kxk([mean_c, max_c])) ; y = x * ca * gate (conv.py:300-320).  CTA = one 16 x 16 pixel tile of one
@@ -374,6 +450,29 @@ cbam_apply_kernel(const T* __restrict__ x, int x_ld, int H, int W, int C, const 
   }
   __syncthreads();
   const int cvecs = C / V;
+  if ((CB_T * CB_T) % cvecs == 0) {
+    // the lane's channel vector is the same in every round: its ca weights stay in registers, and the pixel index
+    // advances by a constant (no division in the loop)
+    const int cv = tid % cvecs, ppr = CB_T * CB_T / cvecs;
+    float cg[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) cg[v] = casm[cv * V + v];
+    for (int pix = tid / cvecs; pix < CB_T * CB_T; pix += ppr) {
+      const int ty = pix / CB_T, tx = pix % CB_T;
+      const int oy = y0 + ty, ox = x0 + tx;
+      if (oy >= H || ox >= W) continue;
+      const long long gp = ((long long)b * H + oy) * W + ox;
+      float f[V];
+      ldg_vec<T>(x + gp * x_ld + cv * V).unpack(f);
+      const float g = gate[pix];
+#pragma unroll
+      for (int v = 0; v < V; ++v) f[v] *= cg[v] * g;
+      Vec<T> o;
+      o.pack(f);
+      st_vec<T>(y + gp * y_ld + cv * V, o);
+    }
+    return;
+  }
   for (int i = tid; i < CB_T * CB_T * cvecs; i += CB_T * CB_T) {
     const int pix = i / cvecs, cv = i - pix * cvecs;
     const int ty = pix / CB_T, tx = pix - ty * CB_T;
@@ -527,8 +626,13 @@ extern "C" int lpc_cbam_stats(int dtype, const void* x, int x_ld, int B, int HW,
   if (int e = check_vec("cbam_stats", dtype, C, x_ld, x_ld, x, x)) return e;
   cudaStream_t s = (cudaStream_t)stream;
   const int lpp = lanes_per_pixel(dtype, C);
-  LPC_REQUIRE((long long)B * HW * lpp < (1ll << 32), "cbam_stats: tensor too large for 32-bit indexing");
-  const int g = cdiv((long long)B * HW * lpp, 256);
+  LPC_REQUIRE(B <= 65535, "cbam_stats: batch too large");
+  // ~8 CTAs per SM in total, at least 128 pixels (4 rounds of the 4-pixel unroll for 8 lane groups) per CTA
+  int chunks = (8 * 148 + B - 1) / B;
+  const int max_chunks = (HW + 127) / 128;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  dim3 g(chunks, B);
   DISPATCH_T(dtype, (lpc_launch_pdl(cbam_stats_kernel<float>, g, 256, 0, s, (const float*)x, x_ld, B, HW, C, lpp, ca, stats)),
              (lpc_launch_pdl(cbam_stats_kernel<bf16>, g, 256, 0, s, (const bf16*)x, x_ld, B, HW, C, lpp, ca, stats)), "cbam_stats")
 }
