@@ -32,6 +32,11 @@ def _chunk_plan(B):
     compute early, one large second chunk keeps the kernels efficient (measured on B200, LPC @640 B=64, uint8 source:
     1 chunk 4.7 ms, 2 x 32 4.5 ms, 4 x 16 5.3 ms, 8 x 8 7.6 ms per step; H2D 55 GB/s).  LPC_E2E_CHUNKS=n forces n equal chunks."""
     import os
+    plan = os.environ.get("LPC_E2E_PLAN")          # explicit chunk sizes, e.g. "8,24,32" (measurement)
+    if plan:
+        sizes = [int(v) for v in plan.split(",")]
+        if sum(sizes) == B and all(v > 0 for v in sizes):
+            return sizes
     env = os.environ.get("LPC_E2E_CHUNKS")
     if env and B % int(env) == 0:
         return [B // int(env)] * int(env)

@@ -1,6 +1,7 @@
 """Drop-in counterparts of ``Detect`` (reference nn/modules/head.py:21-101) and ``v10Detect`` (:497-535)."""
 import copy
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -111,27 +112,63 @@ class v10Detect(Detect):
         self.one2one_cv2 = copy.deepcopy(self.cv2)
         self.one2one_cv3 = copy.deepcopy(self.cv3)
 
+    # The six branch chains of the head (3 levels x {box, class}) are independent and, on the 40x40 / 20x20 levels, too
+    # small to fill 148 SMs on their own: they are issued on side streams (forked / joined with events, so a CUDA-graph
+    # capture records them as parallel branches).  LPC_HEAD_STREAMS=0 serialises them again.
+    branch_streams = os.environ.get("LPC_HEAD_STREAMS", "1") != "0"
+
+    def _side_streams(self, device, n):
+        pool = self.__dict__.setdefault("_streams", {})
+        key = (device.type, device.index)
+        if len(pool.get(key, ())) < n:
+            pool[key] = [torch.cuda.Stream(device=device) for _ in range(n)]
+        return pool[key][:n]
+
     def forward_feat(self, x, cv2, cv3, keys=None):
         """keys: optional {"ws": tail workspace, "A": anchors per image}: the last class-branch conv of every level also
         writes the per-anchor max-logit keys there (stage 1 of v10postprocess fused into the conv epilogue)."""
-        y = []
+        xs = [self._in(t) for t in x]
+        raws, offs, rms = [], [], []
         off = 0
-        for i in range(self.nl):
-            xi = self._in(x[i])
+        for xi in xs:
             B, _, H, W = xi.shape
-            raw = F.new_act(B, self.no, H, W, xi.dtype, xi.device)
-            cv2[i][2](cv2[i][1](cv2[i][0](xi)), out=raw[:, : 4 * self.reg_max])
-            t = cv3[i][0][1](cv3[i][0][0](xi))
-            t = cv3[i][1][1](cv3[i][1][0](t))
-            if keys is not None:
-                rm = {"ws": keys["ws"], "A": keys["A"], "off": off}
-                cv3[i][2](t, out=raw[:, 4 * self.reg_max:], rowmax=rm)
-                keys["ok"] = keys.get("ok", True) and rm.get("ok", False)
-            else:
-                cv3[i][2](t, out=raw[:, 4 * self.reg_max:])
+            raws.append(F.new_act(B, self.no, H, W, xi.dtype, xi.device))
+            offs.append(off)
+            rms.append({"ws": keys["ws"], "A": keys["A"], "off": off} if keys is not None else None)
             off += H * W
-            y.append(raw)
-        return y
+        nb = 4 * self.reg_max
+
+        def box(i):
+            cv2[i][2](cv2[i][1](cv2[i][0](xs[i])), out=raws[i][:, :nb])
+
+        def cls(i):
+            t = cv3[i][0][1](cv3[i][0][0](xs[i]))
+            t = cv3[i][1][1](cv3[i][1][0](t))
+            if rms[i] is not None:
+                cv3[i][2](t, out=raws[i][:, nb:], rowmax=rms[i])
+            else:
+                cv3[i][2](t, out=raws[i][:, nb:])
+
+        jobs = [(fn, i) for i in range(self.nl) for fn in (cls, box)]      # class branches first: they are the longer chains
+        if self.branch_streams and xs[0].is_cuda and len(jobs) > 1:
+            dev = xs[0].device
+            main = torch.cuda.current_stream(dev)
+            sides = self._side_streams(dev, len(jobs) - 1)
+            fork = torch.cuda.Event()
+            fork.record(main)
+            for (fn, i), st in zip(jobs[1:], sides):
+                st.wait_event(fork)
+                with torch.cuda.stream(st):
+                    fn(i)
+            jobs[0][0](jobs[0][1])
+            for st in sides:
+                main.wait_stream(st)
+        else:
+            for fn, i in jobs:
+                fn(i)
+        if keys is not None:
+            keys["ok"] = all(rm.get("ok", False) for rm in rms)
+        return raws
 
     def forward(self, x):
         one2one = self.forward_feat(x, self.one2one_cv2, self.one2one_cv3)
