@@ -6,6 +6,8 @@ logical shape NCHW keeps every reference module signature (SURVEY.md section 8(b
 """
 import ctypes as C
 
+import os
+
 import torch
 
 from . import _lib
@@ -64,6 +66,38 @@ def dt_code(dtype):
 
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ---- independent op chains on side streams -------------------------------------------------------------------------
+_SIDE_STREAMS = {}
+BRANCH_STREAMS = os.environ.get("LPC_BRANCH_STREAMS", os.environ.get("LPC_HEAD_STREAMS", "1")) != "0"
+
+
+def fork_join(jobs, device):
+    """Run independent callables concurrently: jobs[0] on the current stream, the others on cached side streams that
+    first wait for everything issued so far; the current stream then waits for all of them.  Under CUDA-graph capture
+    this records parallel branches.  Every tensor a job READS must have been produced on the current stream before the
+    call, every tensor it WRITES must outlive the call (the callers pre-allocate outputs on the current stream);
+    temporaries a job allocates belong to its side stream in the caching allocator, so they are never handed to another
+    stream while in use.  LPC_BRANCH_STREAMS=0 serialises."""
+    if not BRANCH_STREAMS or len(jobs) < 2 or device.type != "cuda":
+        for j in jobs:
+            j()
+        return
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    pool = _SIDE_STREAMS.setdefault(key, [])
+    while len(pool) < len(jobs) - 1:
+        pool.append(torch.cuda.Stream(device=device))
+    main = torch.cuda.current_stream(device)
+    fork = torch.cuda.Event()
+    fork.record(main)
+    for j, st in zip(jobs[1:], pool):
+        st.wait_event(fork)
+        with torch.cuda.stream(st):
+            j()
+    jobs[0]()
+    for st in pool[:len(jobs) - 1]:
+        main.wait_stream(st)
 
 
 def new_act(B, Cc, H, W, dtype, device):

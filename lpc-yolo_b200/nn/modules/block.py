@@ -298,10 +298,12 @@ class SPCA(LpcModule):
         dws, pw, w1, w2 = self._packed(x, self._build)
         B, c, H, W = x.shape
         feats = F.new_act(B, 3 * c, H, W, x.dtype, x.device)
-        for j, pd in enumerate(dws):
-            F.dwconv2d(x, pd, out=feats[:, j * c:(j + 1) * c])
-        gate = F.pooled_gate(x, w1, None, ACT_RELU, w2, None, ACT_SIGMOID)
-        return F.conv2d(feats, pw, out=out, res=x, chan_scale=gate)
+        # the three dilated depthwise convs and the pooled channel gate only read x: four independent small chains
+        got = {}
+        jobs = [(lambda j=j, pd=pd: F.dwconv2d(x, pd, out=feats[:, j * c:(j + 1) * c])) for j, pd in enumerate(dws)]
+        jobs.append(lambda: got.__setitem__("gate", F.pooled_gate(x, w1, None, ACT_RELU, w2, None, ACT_SIGMOID)))
+        F.fork_join(jobs, x.device)
+        return F.conv2d(feats, pw, out=out, res=x, chan_scale=got["gate"])
 
 
 class LPC(LpcModule):

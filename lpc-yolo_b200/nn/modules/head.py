@@ -1,7 +1,6 @@
 """Drop-in counterparts of ``Detect`` (reference nn/modules/head.py:21-101) and ``v10Detect`` (:497-535)."""
 import copy
 import math
-import os
 
 import torch
 import torch.nn as nn
@@ -113,17 +112,8 @@ class v10Detect(Detect):
         self.one2one_cv3 = copy.deepcopy(self.cv3)
 
     # The six branch chains of the head (3 levels x {box, class}) are independent and, on the 40x40 / 20x20 levels, too
-    # small to fill 148 SMs on their own: they are issued on side streams (forked / joined with events, so a CUDA-graph
-    # capture records them as parallel branches).  LPC_HEAD_STREAMS=0 serialises them again.
-    branch_streams = os.environ.get("LPC_HEAD_STREAMS", "1") != "0"
-
-    def _side_streams(self, device, n):
-        pool = self.__dict__.setdefault("_streams", {})
-        key = (device.type, device.index)
-        if len(pool.get(key, ())) < n:
-            pool[key] = [torch.cuda.Stream(device=device) for _ in range(n)]
-        return pool[key][:n]
-
+    # small to fill 148 SMs on their own: F.fork_join issues them on side streams (parallel branches of the captured
+    # graph).
     def forward_feat(self, x, cv2, cv3, keys=None):
         """keys: optional {"ws": tail workspace, "A": anchors per image}: the last class-branch conv of every level also
         writes the per-anchor max-logit keys there (stage 1 of v10postprocess fused into the conv epilogue)."""
@@ -149,23 +139,8 @@ class v10Detect(Detect):
             else:
                 cv3[i][2](t, out=raws[i][:, nb:])
 
-        jobs = [(fn, i) for i in range(self.nl) for fn in (cls, box)]      # class branches first: they are the longer chains
-        if self.branch_streams and xs[0].is_cuda and len(jobs) > 1:
-            dev = xs[0].device
-            main = torch.cuda.current_stream(dev)
-            sides = self._side_streams(dev, len(jobs) - 1)
-            fork = torch.cuda.Event()
-            fork.record(main)
-            for (fn, i), st in zip(jobs[1:], sides):
-                st.wait_event(fork)
-                with torch.cuda.stream(st):
-                    fn(i)
-            jobs[0][0](jobs[0][1])
-            for st in sides:
-                main.wait_stream(st)
-        else:
-            for fn, i in jobs:
-                fn(i)
+        # class branches first: they are the longer chains
+        F.fork_join([(lambda fn=fn, i=i: fn(i)) for i in range(self.nl) for fn in (cls, box)], xs[0].device)
         if keys is not None:
             keys["ok"] = all(rm.get("ok", False) for rm in rms)
         return raws
