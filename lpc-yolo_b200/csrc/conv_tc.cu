@@ -164,6 +164,15 @@ __device__ __forceinline__ void store16(const uint32_t* v, bf16* yrow, const bf1
     if ((o.raw.x ^ o2.raw.y) == 0x7fc17fc1u) st_vec<bf16>(yrow, o);
     return;
   }
+  // One 32-byte store per lane (STG.E.ENL2.256, sm_100) when the row slice is 32-byte aligned: the lanes of a warp
+  // own different pixels, so every store instruction touches 32 separate sectors whatever its width - halving the
+  // instruction count halves the L1 wavefronts the epilogue queues (l1tex data-pipe was 60 % busy on the HBM-side layers).
+  if ((reinterpret_cast<uintptr_t>(yrow) & 31u) == 0) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(yrow), "r"(o.raw.x), "r"(o.raw.y), "r"(o.raw.z),
+                 "r"(o.raw.w), "r"(o2.raw.x), "r"(o2.raw.y), "r"(o2.raw.z), "r"(o2.raw.w)
+                 : "memory");
+    return;
+  }
   st_vec<bf16>(yrow, o);
   st_vec<bf16>(yrow + 8, o2);
 }

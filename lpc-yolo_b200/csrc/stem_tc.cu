@@ -54,11 +54,17 @@ __device__ __forceinline__ void stem_epilogue_row(uint32_t trow, int Cout, bf16*
         const float t = __uint_as_float(v[i]);
         f[i] = ACT == LPC_ACT_SILU ? silu_<false>(t) : ACT == LPC_ACT_MISH ? mish_<false>(t) : ACT == LPC_ACT_NONE ? t : apply_act<false>(t, ACT);
       }
-      Vec<bf16> o;
+      Vec<bf16> o, o2;
       o.pack(f);
-      st_vec<bf16>(yrow + c, o);
-      o.pack(f + 8);
-      st_vec<bf16>(yrow + c + 8, o);
+      o2.pack(f + 8);
+      if ((reinterpret_cast<uintptr_t>(yrow + c) & 31u) == 0) {      // one 32-byte store per lane (see conv_tc.cu store16)
+        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(yrow + c), "r"(o.raw.x), "r"(o.raw.y),
+                     "r"(o.raw.z), "r"(o.raw.w), "r"(o2.raw.x), "r"(o2.raw.y), "r"(o2.raw.z), "r"(o2.raw.w)
+                     : "memory");
+      } else {
+        st_vec<bf16>(yrow + c, o);
+        st_vec<bf16>(yrow + c + 8, o2);
+      }
     }
   }
 }
