@@ -9,6 +9,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "liblpcyolo.so")
+if os.environ.get("LPC_LIB"):            # A/B measurements of two builds in one process tree (tools only)
+    LIB_PATH = os.environ["LPC_LIB"]
 
 BF16, F32 = 0, 1
 E_ARG, E_UNSUPPORTED, E_CUDA, E_WORKSPACE = -1, -2, -3, -4
