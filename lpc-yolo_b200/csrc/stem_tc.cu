@@ -14,6 +14,7 @@
 // Per image at 640x640: 1.64 MB in + 3.28 MB out (Cout = 16): HBM-bound (the CUDA-core version was FMA-bound at
 // 5x the HBM floor, profiles/r01_f_*).
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -26,6 +27,13 @@ constexpr int SB_TW = 16, SB_TH = 8;          // output tile
 constexpr int SB_THREADS = 288;
 constexpr int SB_A_BYTES = 128 * 128;         // 128 rows x 128 B (K = 64 slots, 48 used), 128B swizzle
 constexpr int SB_DEPTH = 3, SB_SLOT = 80;     // input ring: tiles in flight per CTA, bytes per thread slot
+// TMA input box of one 8 x 16 output tile: input rows 2*oy0-1 .. 2*oy0+15, pixels 2*ox0-2 .. 2*ox0+33 (36 pixels of 8 bytes;
+// 33 are read; the box starts on an EVEN pixel because every box row must start on a 16-byte boundary in global memory -
+// a box starting at pixel 2*ox0-1 raised 'illegal instruction'), zero fill outside the image = the conv padding.  The image is described as [B][H][W*4 bf16] so that the
+// box's inner extent (144 elements = 288 bytes) is a multiple of 16 bytes.
+constexpr int SB_BOX_PX = 36, SB_BOX_ROWS = 2 * SB_TH + 1, SB_BOX_ROW_B = SB_BOX_PX * 8;
+constexpr int SB_BOX_BYTES = SB_BOX_ROWS * SB_BOX_ROW_B, SB_BOX_SLOT = (SB_BOX_BYTES + 127) & ~127;
+static_assert(SB_DEPTH * SB_BOX_SLOT <= SB_DEPTH * 128 * SB_SLOT, "the TMA ring reuses the cp.async ring's shared memory");
 
 
 struct StemTcParams {
@@ -38,6 +46,7 @@ struct StemTcParams {
   int tiles_x, tiles_y, m_tiles;
   int acc_cols, tmem_cols;
   float inv_per_img, inv_tiles_x;
+  int tma_in;          // the 3x3 stride-2 input windows of a tile arrive as ONE TMA box (else: per-thread cp.async ring)
   unsigned long long* trace;   // LPC_STEM_DBG=1: [3 roles][64 tiles][4 stamps] clock64 of CTA 0
 };
 
@@ -71,9 +80,9 @@ __device__ __forceinline__ void stem_epilogue_row(uint32_t trow, int Cout, bf16*
 
 template <int ACT>
 __global__ void __launch_bounds__(SB_THREADS, 4)
-stem_tc_kernel(const __grid_constant__ StemTcParams p) {
+stem_tc_kernel(const __grid_constant__ StemTcParams p, const __grid_constant__ CUtensorMap in_map) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  __shared__ __align__(8) unsigned long long bars[8];
+  __shared__ __align__(8) unsigned long long bars[8 + SB_DEPTH];
   __shared__ uint32_t tmem_base_slot;
 
   const uint32_t a_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // two A stages
@@ -85,6 +94,7 @@ stem_tc_kernel(const __grid_constant__ StemTcParams p) {
   auto aempty = [&](int s) { return bar0 + 8u * (2 + s); };
   auto tfull = [&](int s) { return bar0 + 8u * (4 + s); };
   auto tempty = [&](int s) { return bar0 + 8u * (6 + s); };
+  auto ifull = [&](int s) { return bar0 + 8u * (8 + s); };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
@@ -93,6 +103,8 @@ stem_tc_kernel(const __grid_constant__ StemTcParams p) {
       mbar_init(tfull(s), 1);
       mbar_init(tempty(s), 4);
     }
+    for (int s = 0; s < SB_DEPTH; ++s) mbar_init(ifull(s), 1);
+    if (p.tma_in) prefetch_tmap(&in_map);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) tmem_alloc(smem_u32(&tmem_base_slot), (uint32_t)p.tmem_cols);
@@ -129,6 +141,60 @@ stem_tc_kernel(const __grid_constant__ StemTcParams p) {
     const int ty = r >> 4, tx = r & 15;
     const uint32_t row_addr = (uint32_t)(r * 128);
     const uint32_t sw = (uint32_t)(r & 7);
+    if (p.tma_in) {
+      // One elected builder thread fetches the whole input window of tile it + SB_DEPTH - 1 with a single TMA box; every
+      // builder then reads its own 3 x (16 + 8) bytes from shared memory.  The per-thread cp.async ring below needed
+      // six LSU instructions per output pixel on the global side alone and made the L1 data pipe the stem's limiter.
+      const uint32_t ring0 = b_base + (uint32_t)(p.Cout * 128);
+      auto issue_box = [&](int m, int slot) {
+        if (m < p.m_tiles) {
+          const int img = fast_div(m, per_img, p.inv_per_img), rem = m - img * per_img;
+          const int tyi = fast_div(rem, p.tiles_x, p.inv_tiles_x), txi = rem - tyi * p.tiles_x;
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_expect_tx(ifull(slot), (uint32_t)SB_BOX_BYTES);
+          asm volatile(
+              "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+              ::"r"(ring0 + (uint32_t)(slot * SB_BOX_SLOT)), "l"(&in_map), "r"(ifull(slot)),
+                "r"((2 * txi * SB_TW - 2) * 4), "r"(2 * tyi * SB_TH - 1), "r"(img)
+              : "memory");
+        }
+      };
+      int m = blockIdx.x;
+      if (r == 0)
+        for (int d = 0; d < SB_DEPTH - 1; ++d) issue_box(m + d * (int)gridDim.x, d);
+      const uint32_t my_off = (uint32_t)(2 * ty * SB_BOX_ROW_B + tx * 16);
+      int it = 0;
+      for (; m < p.m_tiles; m += gridDim.x, ++it) {
+        if (r == 0) STRACE(0, it, 0);
+        // the slot refilled now was read in iteration it - 1: all 128 builders have passed their loads of it
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (r == 0) issue_box(m + (SB_DEPTH - 1) * (int)gridDim.x, (it + SB_DEPTH - 1) % SB_DEPTH);
+        const int slot = it % SB_DEPTH;
+        mbar_wait(ifull(slot), (uint32_t)((it / SB_DEPTH) & 1));
+        const uint32_t src = ring0 + (uint32_t)(slot * SB_BOX_SLOT) + my_off;
+        uint4 e12[3];     // pixels 2ox, 2ox+1 of input row k (box pixels 2tx+2, 2tx+3)
+        uint2 e0[3];      // pixel 2ox-1 (box pixel 2tx+1)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(e0[k].x), "=r"(e0[k].y) : "r"(src + (uint32_t)(k * SB_BOX_ROW_B + 8)));
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(e12[k].x), "=r"(e12[k].y), "=r"(e12[k].z), "=r"(e12[k].w) : "r"(src + (uint32_t)(k * SB_BOX_ROW_B + 16)));
+        }
+        const int s = it & 1;
+        if (r == 0) STRACE(0, it, 1);
+        mbar_wait(aempty(s), (uint32_t)(((it >> 1) & 1) ^ 1));
+        if (r == 0) STRACE(0, it, 2);
+        unsigned char* rowp = gen_base + s * SB_A_BYTES + row_addr;
+        // K chunks of 8 elements = two taps, exactly as in the cp.async path below
+        *reinterpret_cast<uint4*>(rowp + ((0u ^ sw) << 4)) = make_uint4(e0[0].x, e0[0].y, e12[0].x, e12[0].y);
+        *reinterpret_cast<uint4*>(rowp + ((1u ^ sw) << 4)) = make_uint4(e12[0].z, e12[0].w, e0[1].x, e0[1].y);
+        *reinterpret_cast<uint4*>(rowp + ((2u ^ sw) << 4)) = e12[1];
+        *reinterpret_cast<uint4*>(rowp + ((3u ^ sw) << 4)) = make_uint4(e0[2].x, e0[2].y, e12[2].x, e12[2].y);
+        *reinterpret_cast<uint4*>(rowp + ((4u ^ sw) << 4)) = make_uint4(e12[2].z, e12[2].w, 0x3F803F80u, 0u);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(afull(s));
+        if (r == 0) STRACE(0, it, 3);
+      }
+    } else {
     // Input ring: every thread stages the 72 bytes of its own 3 x 3-pixel window (3 x [16 B: pixels 2ox, 2ox+1] then
     // 3 x [8 B: pixel 2ox-1]) for tile it + SB_DEPTH - 1 with cp.async (zero-fill outside the image) into a
     // thread-private 80-byte slot, so SB_DEPTH - 1 tiles of loads are in flight per CTA without holding registers.
@@ -191,6 +257,7 @@ stem_tc_kernel(const __grid_constant__ StemTcParams p) {
       if (r == 0) STRACE(0, it, 3);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
   } else if (warp == 4) {
     // ===== MMA issuer =====
     if (elect_one_sync()) {
@@ -271,7 +338,7 @@ int lpc_stem_conv_tc(const void* x, int B, int H, int W, const float* w, const f
   while (p.acc_cols < Cout) p.acc_cols <<= 1;
   p.tmem_cols = 2 * p.acc_cols;
   const size_t smem = 2 * SB_A_BYTES + (size_t)Cout * 128 + (size_t)SB_DEPTH * 128 * SB_SLOT + 1024;
-  void (*kern)(StemTcParams) = act == LPC_ACT_SILU ? stem_tc_kernel<LPC_ACT_SILU> : act == LPC_ACT_MISH ? stem_tc_kernel<LPC_ACT_MISH>
+  void (*kern)(StemTcParams, CUtensorMap) = act == LPC_ACT_SILU ? stem_tc_kernel<LPC_ACT_SILU> : act == LPC_ACT_MISH ? stem_tc_kernel<LPC_ACT_MISH>
                               : act == LPC_ACT_NONE ? stem_tc_kernel<LPC_ACT_NONE> : stem_tc_kernel<LPC_ACT_RELU>;
   static bool attr = false;
   if (!attr) {
@@ -299,7 +366,33 @@ int lpc_stem_conv_tc(const void* x, int B, int H, int W, const float* w, const f
     cudaMemset(trace_buf, 0, 3 * 64 * 4 * 8);
     p.trace = trace_buf;
   }
-  lpc_launch_pdl(kern, (unsigned)grid, SB_THREADS, smem, stream, p);
+  // input tensor map: [B][H][W*4 bf16], box = 144 elements x 17 rows (see SB_BOX_*)
+  CUtensorMap in_map;
+  memset(&in_map, 0, sizeof(in_map));
+  p.tma_in = 0;
+  {
+    static const int tma_env = [] { const char* e = getenv("LPC_STEM_TMA"); return e ? atoi(e) : 1; }();
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn enc = [] {
+      void* f = nullptr;
+      cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+      return reinterpret_cast<EncodeFn>(f);
+    }();
+    if (tma_env && enc && W % 2 == 0 && W * 4 >= SB_BOX_PX * 4 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0) {
+      cuuint64_t dims[3] = {(cuuint64_t)W * 4, (cuuint64_t)H, (cuuint64_t)B};
+      cuuint64_t strides[2] = {(cuuint64_t)W * 8, (cuuint64_t)H * W * 8};
+      cuuint32_t box[3] = {(cuuint32_t)SB_BOX_PX * 4, (cuuint32_t)SB_BOX_ROWS, 1};
+      cuuint32_t es[3] = {1, 1, 1};
+      if (enc(&in_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<uint2*>(p.x), dims, strides, box, es,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+        p.tma_in = 1;
+    }
+  }
+  lpc_launch_pdl(kern, (unsigned)grid, SB_THREADS, smem, stream, p, in_map);
   LPC_CHECK_LAUNCH("stem_conv_tc");
   if (dbg) {
     static int calls = 0;
