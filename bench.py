@@ -100,7 +100,7 @@ def cpu_reference_leg(model_key, size, batch, reps, warm=1):
     return batch / t, torch.get_num_threads(), f"{model_key} @{size} batch {batch}, fp32, median of {reps} predict() passes after {warm} warm-up", t
 
 
-def run_reference(args):
+def run_reference(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -112,7 +112,7 @@ def run_reference(args):
             "config": {"workload": f"{args.model} YAML predict, {args.size}x{args.size}, batch {b} per step (bounded CPU sample of the batch-{args.batch} workload)"},
             "cpu_baseline": {"value": round(ips, 3), "unit": "img/s", "cores": threads, "kind": "port", "sample": desc},
             "e2e": {"value": round(ips, 3), "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -127,8 +127,17 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON record: everything else any library writes to fd 1 (NCCL prints its version
+    # banner there) goes to stderr for the rest of the process; emit() writes the record to the real stdout.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(rec):
+        os.write(real_stdout, (json.dumps(rec) + "\n").encode())
+
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, emit)
 
     import torch
     import torch.distributed as dist
@@ -140,8 +149,6 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"       # NCCL prints its version banner on stdout: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     pkg = importlib.import_module("lpc-yolo_b200")
     Fn = importlib.import_module("lpc-yolo_b200.functional")
@@ -309,7 +316,7 @@ def main():
                         "source": "YOLO.predict(uint8 HWC BGR arrays in pinned host memory): H2D, /255 + BGR->RGB + NHWC pack, network, fused tail, D2H"},
                 "gpu_launches": int(launches_per_step * args.steps),
                 "roofline": roof, "roofline_tail": roof_tail, "cpu_baseline": cpu}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
