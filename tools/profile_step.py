@@ -1,6 +1,7 @@
 """Per-launch profile of one step of the bench workload (CUDA events around every op, eager mode).
 usage: python tools/profile_step.py [model] [batch] [size]   -> table sorted by time, written to stdout."""
 import importlib, os, sys
+os.environ.setdefault("LPC_BRANCH_STREAMS", "0")    # per-op attribution needs one stream (side streams overlap ops inside the event brackets)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
