@@ -894,15 +894,20 @@ extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W
     if (per_n > (p.m_tiles + 1) / 2) per_n = (p.m_tiles + 1) / 2;
   }
   const unsigned grid = (unsigned)(per_n * p.n_tiles) * ((pair || tpair) ? 2u : 1u);
-  const unsigned threads = 64 + 128 * p.epi_split;
   // Each role is latency-bound per tile (~1.5-2k cycles: barrier round trips, tcgen05.ld, MUFU chains), so with enough
   // tiles per CTA the two epilogue warp groups take alternate tiles (two epilogues in flight) instead of splitting the
   // columns of one; LPC_TC_EPI_ALT=0/1 overrides (profiling).
   {
     static const int force = [] { const char* e = getenv("LPC_TC_EPI_ALT"); return e ? atoi(e) : -1; }();
-    p.epi_alt = (p.epi_split == 2 && p.m_tiles / (per_n * ((pair || tpair) ? 2 : 1)) >= 4) ? 1 : 0;
+    const bool many_tiles = p.m_tiles / (per_n * ((pair || tpair) ? 2 : 1)) >= 4;
+    p.epi_alt = (p.epi_split == 2 && many_tiles) ? 1 : 0;
     if (force >= 0 && p.epi_split == 2) p.epi_alt = force;
+    // N tiles that cannot be split between two warp groups (Cout = 16, 48, 80 ...: half a tile is not a multiple of 16
+    // columns) ran with ONE epilogue group - 6 warps per CTA, one epilogue latency chain per CTA (16->16 @160x160 B64:
+    // 18 % warps active, 53 / 75 us against a 16 / 24 us floor).  Alternating whole tiles needs no column split.
+    if (p.epi_split == 1 && many_tiles && force != 0) { p.epi_split = 2; p.epi_alt = 1; }
   }
+  const unsigned threads = 64 + 128 * p.epi_split;
   static unsigned long long* trace_buf = nullptr;
   if (p.dbg & 8) {
     if (!trace_buf) cudaMalloc(&trace_buf, 4 * 64 * 4 * 8);
