@@ -212,6 +212,7 @@ __device__ void rank_emit(const unsigned long long* __restrict__ in, int n, unsi
   __syncthreads();
   for (int t0 = 0; t0 < G * P; t0 += SEL_NT) {
     const int t = t0 + threadIdx.x, part = t & (P - 1), gq = t / P, g = min(gq, G - 1);
+    if ((t & ~31) / P >= G) continue;              // the whole warp is past the last entry group (warp-uniform)
     const int j0 = min(npad, part * chunk), j1 = min(npad, j0 + chunk);
     const ulonglong2 ea = *reinterpret_cast<const ulonglong2*>(in + 4 * g), eb = *reinterpret_cast<const ulonglong2*>(in + 4 * g + 2);
     uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0;
@@ -488,6 +489,7 @@ select_decode_kernel(const __grid_constant__ TailSrc s, int K, int sortn, const 
 #pragma unroll 1
     for (int r0 = 0; r0 < K; r0 += SEL_NT / 4) {
       const int r = r0 + (tid >> 2);
+      if (r0 + ((tid & ~31) >> 2) >= K) continue;  // none of this warp's eight winners exists (warp-uniform)
       const unsigned long long e = sorted[r < K ? r : 0];
       const uint32_t flat = 0xFFFFFFFFu - (uint32_t)(e & 0xFFFFFFFFull);
       const int a = (int)(flat / (uint32_t)nc), c = (int)(flat - (uint32_t)a * nc);
