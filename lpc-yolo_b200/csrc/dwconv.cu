@@ -457,6 +457,10 @@ int launch_dw_tma(const void* x, int x_ld, int B, int H, int W, int C, const flo
   for (int cbv = 1; cbv <= 16; ++cbv) {
     if ((C / 8) % cbv) continue;
     if (cbv % 4 && cbv != C / 8) continue;      // 64-byte runs per pixel (or the whole pixel): full 32-byte sectors
+    // Two outputs per thread (7x7) and 64-byte pixels put consecutive x-groups 128 bytes apart: every quarter-warp of a
+    // 16-byte shared-memory load hits the same banks twice.  Measured 512ch 20x20 B256: cbv 4 -> 522 us, cbv 8 / 16 ->
+    // 207 / 201 us (gpurun_out/dw7_tiles.txt); 128-byte pixels are conflict-free.
+    if (PX == 2 && cbv < 8 && (C / 8) % 8 == 0) continue;
     for (int th = 4; th <= 16; th *= 2)
       for (int xg = 1; xg * cbv * th <= 256; ++xg) {
         const int tw = xg * PX;
@@ -475,6 +479,20 @@ int launch_dw_tma(const void* x, int x_ld, int B, int H, int W, int C, const flo
         }
       }
   }
+  if (const char* e = getenv("LPC_DW_TILE")) {           // "cbv,xg,th": force a tile (tuning runs only)
+    int cbv = 0, xg = 0, th = 0;
+    if (sscanf(e, "%d,%d,%d", &cbv, &xg, &th) == 3 && cbv > 0 && (C / 8) % cbv == 0 && xg * cbv * th <= 256) {
+      const int tw = xg * PX, iw = (tw - 1) * S + (K - 1) * D + 1, ih = (th - 1) * S + (K - 1) * D + 1;
+      const size_t bytes = (size_t)iw * ih * cbv * 16;
+      if (iw <= 256 && ih <= 256 && bytes <= 44 * 1024) {
+        best = 0;
+        p.CV = cbv; p.CB = cbv * 8; p.XG = xg; p.TH = th; p.IW = iw; p.IH = ih;
+        p.stage_bytes = (unsigned)((bytes + 127) & ~(size_t)127);
+        p.tx_bytes = (unsigned)bytes;
+      }
+    }
+  }
+  if (getenv("LPC_DW_TILE_PRINT")) fprintf(stderr, "dw tile K=%d S=%d C=%d %dx%d: cbv=%d xg=%d th=%d iw=%d ih=%d\n", K, S, C, Ho, Wo, p.CV, p.XG, p.TH, p.IW, p.IH);
   if (best >= 1e30) return 1;
   p.C = C; p.Ho = Ho; p.Wo = Wo; p.B = B;
   p.tiles_x = (Wo + p.XG * PX - 1) / (p.XG * PX);
