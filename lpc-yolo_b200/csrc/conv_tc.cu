@@ -715,10 +715,14 @@ extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W
 
   // ---- choose the kernel -------------------------------------------------------------------------------
   bool halo = false, pair = false, tpair = false;   // pair: CTA-pair halo kernel, tpair: CTA-pair per-tap kernel
-  if (k == 3 && stride == 1 && g_force_mode != 1 && (Cin == 16 || Cin == 32 || Cin % 64 == 0) && Cin <= 256) {
+  // Cin = 48 (yolov10m) takes the halo kernel with 64-channel patch rows: the TMA box runs past the tensor's channel
+  // extent and is zero-filled, the MMA loop walks only the three real 16-channel groups of every tap (the per-tap kernel
+  // needs 27 boxes of 16 channels in the slow 32-byte-swizzled layout per tile: 48->48 @160x160 B256 took 920 us).
+  static const int halo48 = [] { const char* e = getenv("LPC_TC_HALO48"); return e ? atoi(e) : 1; }();
+  if (k == 3 && stride == 1 && g_force_mode != 1 && (Cin == 16 || Cin == 32 || (Cin == 48 && halo48) || Cin % 64 == 0) && Cin <= 256) {
     const long long tiles = (long long)((Wo + HALO_TW - 1) / HALO_TW) * ((Ho + HALO_TH - 1) / HALO_TH);
     const double eff = (double)Ho * Wo / (double)(tiles * 128);
-    const int pitch = (Cin >= 64 ? 64 : Cin) * 2;
+    const int pitch = (Cin > 32 ? 64 : Cin) * 2;
     const size_t halo_bytes = (size_t)((Cin + 63) / 64) * HALO_PH * HALO_SPW * pitch;
     // weights resident if they fit next to two halo buffers (halving the N tile once if that makes them fit: the
     // activation patch is then loaded twice, still far cheaper than re-streaming the weights for every tile),
@@ -741,7 +745,7 @@ extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W
       // bound by per-tile role latency and lose to the cluster-scope hops.  Measured with TMA patches in both kernels
       // (us, single vs pair): 16->32 169 / 265, 32->64 104 / 124, 32->32 17.5 / 21.2, 64->64@80 49.3 / 44.1,
       // 64->64@40 17.9 / 16.2, 64->128 (N = 64 twice) 121 / 66.  LPC_TC_PAIR=2 forces pairs wherever they fit (tests).
-      const bool wanted = pair_env == 2 || Cin >= 64;
+      const bool wanted = (pair_env == 2 && Cin != 48) || Cin >= 64;
       if (pair_env && wanted && (eff >= 0.7 || g_force_mode == 2) && bp + 2 * halo_bytes <= SMEM_LIMIT && tot_tiles >= 4) {
         halo = pair = true;
         p.n_tile = ntp;
@@ -777,13 +781,13 @@ extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W
     p.tiles_x = (Wo + HALO_TW - 1) / HALO_TW;
     p.tiles_y = (Ho + HALO_TH - 1) / HALO_TH;
     p.x = xb; p.x_ld = x_ld; p.H = H; p.W = W;
-    p.pitch = (Cin >= 64 ? 64 : Cin) * 2;
+    p.pitch = (Cin > 32 ? 64 : Cin) * 2;
     p.slabs = (Cin + 63) / 64;
     p.slab_bytes = HALO_PH * HALO_SPW * p.pitch;
     smem = (size_t)p.ksteps * (pair ? p.n_tile / 2 : p.n_tile) * 128 + (size_t)p.a_bufs * p.slabs * p.slab_bytes + 1024 + BIAS_REGION(p.n_tile);
     {
       p.a_tma = 1;                                // both halo kernels receive their patches by TMA
-      const int cb = Cin >= 64 ? 64 : Cin;
+      const int cb = Cin > 32 ? 64 : Cin;
       if (int e = encode_act_map(&maps.a[0], xb, Cin, W, H, B, x_ld, (long long)W * x_ld, (long long)H * W * x_ld, cb, HALO_SPW, HALO_PH, swizzle_of(cb))) return e;
     }
   } else {

@@ -141,6 +141,7 @@ def test_conv_tc_is_used_and_slices(M, Fn, oracle, pkg):
 
 @pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("case", [(16, 32, 32, 32, 2), (64, 64, 40, 40, 2), (128, 128, 20, 20, 2), (80, 80, 24, 24, 2),
+                                  (48, 48, 40, 40, 2), (48, 96, 72, 88, 5), (16, 16, 80, 80, 6), (48, 80, 24, 20, 3),
                                   (16, 32, 160, 160, 8), (32, 64, 72, 88, 6), (128, 256, 40, 40, 4), (256, 64, 16, 24, 3)])
 def test_conv3x3_both_tc_kernels(M, oracle, pkg, mode, case):
     """3x3 stride-1 convs through BOTH tensor-core kernels (1 = per-tap TMA boxes, 2 = halo patch with resident or
