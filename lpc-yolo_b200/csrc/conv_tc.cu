@@ -507,7 +507,9 @@ conv_tc_halo_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
         const uint32_t a_lo0 = desc_lo(a_region + (uint32_t)(ab * halo_bytes), 16u);
         issue_bias_mma(acc, ones_addr, bias_addr, p.n_tile, idesc);      // accumulator := bias
         if (CIN > 0) {
-          constexpr int C_ROW = CIN < 64 ? CIN : 64, PITCH16 = C_ROW * 2 / 16, GROUPS = C_ROW / 16, SLABS = (CIN + 63) / 64;
+          // C_ROW: channels per patch row in shared memory (Cin = 48 rows are zero-filled to 64: 128-byte swizzle);
+          // GROUPS: the K=16 slices of a row that carry real channels
+          constexpr int C_ROW = CIN <= 32 ? CIN : 64, PITCH16 = C_ROW * 2 / 16, GROUPS = (CIN < 64 ? CIN : 64) / 16, SLABS = (CIN + 63) / 64;
           constexpr int SLAB16 = HALO_PH * HALO_SPW * C_ROW * 2 / 16;
 #pragma unroll
           for (int j = 0; j < 9 * SLABS * GROUPS; ++j) {
@@ -873,7 +875,7 @@ extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W
 #define PAIR_ATTR(C_) if (cudaFuncSetAttribute(conv_tc_halo2_kernel<C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess) e2 = cudaErrorUnknown;
     PAIR_ATTR(0) PAIR_ATTR(16) PAIR_ATTR(32) PAIR_ATTR(64) PAIR_ATTR(128)
 #undef PAIR_ATTR
-    HALO_ATTR(0) HALO_ATTR(16) HALO_ATTR(32) HALO_ATTR(64) HALO_ATTR(128)
+    HALO_ATTR(0) HALO_ATTR(16) HALO_ATTR(32) HALO_ATTR(48) HALO_ATTR(64) HALO_ATTR(128)
 #undef HALO_ATTR
     if (e1 != cudaSuccess || e2 != cudaSuccess) LPC_FAIL(LPC_E_CUDA, "conv2d_tc: smem attribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
     attr_set = true;
@@ -931,7 +933,8 @@ extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W
       case 128: lpc_launch_pdl(K_<128>, grid, th, smem, st, maps, p); break;            \
       default: lpc_launch_pdl(K_<0>, grid, th, smem, st, maps, p); break;               \
     }
-    if (pair) { HALO_LAUNCH(conv_tc_halo2_kernel) } else { HALO_LAUNCH(conv_tc_halo_kernel) }
+    if (!pair && Cin == 48) lpc_launch_pdl(conv_tc_halo_kernel<48>, grid, th, smem, st, maps, p);
+    else if (pair) { HALO_LAUNCH(conv_tc_halo2_kernel) } else { HALO_LAUNCH(conv_tc_halo_kernel) }
 #undef HALO_LAUNCH
   }
   else if (tpair)
