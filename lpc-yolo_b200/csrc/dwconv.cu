@@ -469,8 +469,10 @@ int launch_dw_tma(const void* x, int x_ld, int B, int H, int W, int C, const flo
         const size_t bytes = (size_t)iw * ih * cbv * 16;
         if (bytes > 44 * 1024) continue;
         const double tiles = (double)((Wo + tw - 1) / tw) * ((Ho + th - 1) / th) * (C / 8 / cbv);
-        // cost ~ per-tile pass (fixed 256-thread sweep + barrier) plus the bytes the tile moves
-        const double cost = tiles * (1.0 + (double)bytes / (24.0 * 1024));
+        // cost ~ per-tile pass (fixed 256-thread sweep + barrier) plus the bytes the tile moves, weighted against short
+        // per-pixel runs: a TMA box row of 64 bytes costs about as much as one of 192 (measured 192ch 80x80 B256, us:
+        // cbv 4 -> 434, cbv 8 -> 399, cbv 12 -> 276; 64ch 80x80 B64: cbv 4 -> 27.7, cbv 8 -> 26.8)
+        const double cost = tiles * (1.0 + (double)bytes / (24.0 * 1024)) * (1.0 + 4.0 / cbv);
         if (cost < best) {
           best = cost;
           p.CV = cbv; p.CB = cbv * 8; p.XG = xg; p.TH = th; p.IW = iw; p.IH = ih;
