@@ -747,7 +747,10 @@ extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W
       // bound by per-tile role latency and lose to the cluster-scope hops.  Measured with TMA patches in both kernels
       // (us, single vs pair): 16->32 169 / 265, 32->64 104 / 124, 32->32 17.5 / 21.2, 64->64@80 49.3 / 44.1,
       // 64->64@40 17.9 / 16.2, 64->128 (N = 64 twice) 121 / 66.  LPC_TC_PAIR=2 forces pairs wherever they fit (tests).
-      const bool wanted = (pair_env == 2 && Cin != 48) || Cin >= 64;
+      // Cin = 48 on CTA pairs: measured 48->48 @160x160 B256 (us, single / pair): 460 / 575 plain, 700 / 675 with the residual
+      // add -> off by default (LPC_TC_PAIR48=1 switches it on; gpurun_out/prof_m256_p48.txt)
+      static const int pair48 = [] { const char* e = getenv("LPC_TC_PAIR48"); return e ? atoi(e) : 0; }();
+      const bool wanted = (pair_env == 2 && Cin != 48) || Cin >= 64 || (Cin == 48 && pair48);
       if (pair_env && wanted && (eff >= 0.7 || g_force_mode == 2) && bp + 2 * halo_bytes <= SMEM_LIMIT && tot_tiles >= 4) {
         halo = pair = true;
         p.n_tile = ntp;
@@ -873,7 +876,7 @@ extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W
     const int lim = (int)SMEM_LIMIT + 16 * 1024;
 #define HALO_ATTR(C_) if (cudaFuncSetAttribute(conv_tc_halo_kernel<C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess) e2 = cudaErrorUnknown;
 #define PAIR_ATTR(C_) if (cudaFuncSetAttribute(conv_tc_halo2_kernel<C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess) e2 = cudaErrorUnknown;
-    PAIR_ATTR(0) PAIR_ATTR(16) PAIR_ATTR(32) PAIR_ATTR(64) PAIR_ATTR(128)
+    PAIR_ATTR(0) PAIR_ATTR(16) PAIR_ATTR(32) PAIR_ATTR(48) PAIR_ATTR(64) PAIR_ATTR(128)
 #undef PAIR_ATTR
     HALO_ATTR(0) HALO_ATTR(16) HALO_ATTR(32) HALO_ATTR(48) HALO_ATTR(64) HALO_ATTR(128)
 #undef HALO_ATTR
@@ -934,6 +937,7 @@ extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W
       default: lpc_launch_pdl(K_<0>, grid, th, smem, st, maps, p); break;               \
     }
     if (!pair && Cin == 48) lpc_launch_pdl(conv_tc_halo_kernel<48>, grid, th, smem, st, maps, p);
+    else if (pair && Cin == 48) lpc_launch_pdl(conv_tc_halo2_kernel<48>, grid, th, smem, st, maps, p);
     else if (pair) { HALO_LAUNCH(conv_tc_halo2_kernel) } else { HALO_LAUNCH(conv_tc_halo_kernel) }
 #undef HALO_LAUNCH
   }

@@ -118,7 +118,7 @@ conv_tc_halo2_kernel(const __grid_constant__ TmapPack maps, const __grid_constan
         const uint32_t a_lo0 = desc_lo(a_region + (uint32_t)(ab * halo_bytes), 16u);
         umma2_bf16(acc, ones_desc, bias_desc, idesc, 0u);                  // accumulator := bias
         if (CIN > 0) {
-          constexpr int C_ROW = CIN < 64 ? CIN : 64, PITCH16 = C_ROW * 2 / 16, GROUPS = C_ROW / 16, SLABS = (CIN + 63) / 64;
+          constexpr int C_ROW = CIN <= 32 ? CIN : 64, PITCH16 = C_ROW * 2 / 16, GROUPS = (CIN < 64 ? CIN : 64) / 16, SLABS = (CIN + 63) / 64;
           constexpr int SLAB16 = HALO_PH * HALO_SPW * C_ROW * 2 / 16;
 #pragma unroll
           for (int j = 0; j < 9 * SLABS * GROUPS; ++j) {
