@@ -6,9 +6,10 @@
 // ranking logits == ranking scores; scores are produced only for the K winners), with a deterministic
 // tie rule: equal keys are ordered by ascending flat index anchor*nc + class.
 //
-//   kernel 1  amax_keys      one pass over the class logits (HBM-bound): key of max_c logit per anchor
-//   kernel 2  select_decode  one CTA per image: radix-select K anchors, radix-select K pairs, bitonic sort,
-//                            box decode of the winners only, write [K,6]
+//   kernel 1  amax_keys      one pass over the class logits (HBM-bound): key of max_c logit per anchor; on the engine
+//                            path the class-branch conv epilogue writes these keys and this kernel is not launched
+//   kernel 2  select_decode  one CTA per image: radix-select K anchors, keep the pairs of those anchors that reach the
+//                            stage-1 threshold, rank them (all-pairs comparison), box decode of the K winners, write [K,6]
 //
 // Box decode follows Detect.inference (head.py:45-71): DFL softmax expectation over 16 bins per side
 // (block.py:57-60), anchors at cell centre (tal.py:294-306), dist2bbox xywh (tal.py:309-319), * stride,
