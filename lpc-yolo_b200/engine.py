@@ -373,17 +373,37 @@ class YOLOv10DetectionPredictor:
         preds[..., [1, 3]] = preds[..., [1, 3]].clamp_(0, hs)
         return preds
 
-    def postprocess(self, preds, img, orig_imgs):
+    def _host_copy(self, preds):
+        """Queue ONE device->host copy of the batched detections into a reused pinned buffer (stream order: behind the last
+        graph replay).  The copy gives the host path everything it needs - the per-image prefix lengths are counted from
+        it instead of by a device reduction plus a second, synchronous read - and it is what ``last_preds_host`` exposes
+        (valid until the next call)."""
+        buf = self.__dict__.get("_host_preds")
+        if buf is None or buf.shape != preds.shape or buf.dtype != preds.dtype:
+            buf = torch.empty(preds.shape, dtype=preds.dtype, pin_memory=True)
+            self._host_preds = buf
+        buf.copy_(preds, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(preds.device))
+        return buf, ev
+
+    def postprocess(self, preds, img, orig_imgs, host=None):
         """models/yolov10/predict.py:22-38: confidence / class filter, wrap in Results.  preds are already
         [B,K,6] xyxy (the export-mode contract, head.py:521-523), clipped to the image (scale_boxes is the
         identity + clip when source and network sizes agree)."""
         B = preds.shape[0]
         self.last_preds = preds          # batched [B,K,6] on the device (one D2H gives every detection)
+        self.last_preds_host = None
+        if host is not None:
+            host[1].synchronize()
+            self.last_preds_host = host[0]
         K = preds.shape[1]
         if self.args.classes is None:
-            # scores are sorted, so a prefix of every image survives: ONE device reduction + one small D2H gives the B
-            # prefix lengths, ONE split call cuts the flattened [B*K,6] tensor into (kept, dropped) pairs of views
-            counts = (preds[..., 4] > self.args.conf).sum(1).tolist()
+            # scores are sorted, so a prefix of every image survives: the B prefix lengths come from the host copy of the
+            # detections when there is one (else ONE device reduction + one small D2H), ONE split call cuts the flattened
+            # [B*K,6] tensor into (kept, dropped) pairs of views
+            src = self.last_preds_host if self.last_preds_host is not None else preds
+            counts = (src[..., 4] > self.args.conf).sum(1).tolist()
             sizes = [v for n in counts for v in (n, K - n)]
             per_img = preds.reshape(B * K, 6).split(sizes)[0::2]
         else:
@@ -409,9 +429,10 @@ class YOLOv10DetectionPredictor:
                     im = self.as_u8_batch(source)
                 with profilers[1]:
                     preds = self.scale_back(self.inference_from_host_u8(im))
+                    host = self._host_copy(preds)
                 orig = list(source) if isinstance(source, (list, tuple)) else [a for a in (source if not torch.is_tensor(source) else source.numpy())]
                 with profilers[2]:
-                    self.results = self.postprocess(preds, im, orig)
+                    self.results = self.postprocess(preds, im, orig, host=host)
             elif torch.is_tensor(source) and not source.is_cuda and source.dtype == torch.float32 and source.dim() == 4:
                 with profilers[0]:
                     im = check_tensor_source(source)
