@@ -51,7 +51,31 @@ class ClockSampler:
         self.idx, self.rows, self.stop_flag = gpu_index, [], False
         self.th = threading.Thread(target=self._run, daemon=True)
 
+    def _run_nvml(self):
+        """NVML in-process (a few microseconds per query): tens of samples inside a sub-second timed region, where one
+        nvidia-smi process start-up is longer than the region.  Returns False when NVML is unavailable."""
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.idx)
+            mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+            reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+        except Exception:
+            return False
+        bits = [0x8, 0x40, 0x20, 0x4]          # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
+        while not self.stop_flag:
+            try:
+                sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+                r = int(reasons(h))
+                self.rows.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for b in bits])
+            except Exception:
+                pass
+            time.sleep(0.005)
+        return True
+
     def _run(self):
+        if self._run_nvml():
+            return
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
@@ -118,8 +142,8 @@ def run_reference(args, emit):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="lpc", choices=sorted(FILES))
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
