@@ -115,3 +115,15 @@ def test_product_never_imports_oracle():
                 if re.search(r"^\s*(import|from)\s+(oracle|lpc_oracle)", s, re.M):
                     bad.append(f)
     assert not bad
+
+
+def test_chunk_plan_covers_the_batch():
+    """engine._chunk_plan: chunk sizes of a host batch always add up to the batch; the first chunk is the small one."""
+    import importlib
+    eng = importlib.import_module("lpc-yolo_b200.engine")
+    for B in (1, 2, 3, 8, 12, 16, 30, 32, 36, 40, 64, 100, 128, 256):
+        plan = eng._chunk_plan(B)
+        assert sum(plan) == B and all(v > 0 for v in plan)
+        if len(plan) == 2:
+            assert plan[0] <= plan[1]
+    assert eng._chunk_plan(64) == [20, 44]
