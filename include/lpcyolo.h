@@ -93,9 +93,12 @@ int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W, int Cin, 
 /* 1 if lpc_conv2d_tc accepts this shape, else 0. */
 int lpc_conv2d_tc_supported(int Cin, int Cout, int k, int stride, int pad, int x_ld, int y_ld);
 
-/* Stem: Conv(3, Cout, 3, stride, pad 1) on an NHWC input whose pixel pitch is exactly 4 (lpc_pack_input's Cpad=4):
- * a register-tiled CUDA-core kernel (K=27 is too small for the tensor-core path).  w: [27][Cout] fp32 with row index
- * (ky*3+kx)*3+cin; Cout % 8 == 0, Cout <= 96.  Replaces layer 0 of every v10 / LPC YAML (conv.py:36-54). */
+/* Stem: Conv(3, Cout, 3, stride, pad 1) on an NHWC input whose pixel pitch is exactly 4 (lpc_pack_input's Cpad=4).
+ * bf16, stride 2, even W: tcgen05 (stem_tc.cu - the 3x3 windows of an 8x16 output tile arrive as one 3-D TMA box, builder
+ * warps turn them into swizzled K-major im2col rows, K = 36 + 2 bias slots -> 48, three UMMAs per 128 pixels); other
+ * shapes: a register-tiled CUDA-core kernel (stem.cu).  The fp32 validation mode does not call this entry (the host
+ * routes it to lpc_conv2d_direct, which accumulates in fp64).  w: [27][Cout] fp32 with row index (ky*3+kx)*3+cin;
+ * Cout % 8 == 0, Cout <= 96.  Replaces layer 0 of every v10 / LPC YAML (conv.py:36-54). */
 int lpc_stem_conv(int dtype, const void* x, int B, int H, int W, const float* w, const float* bias, int stride,
                   int Cout, void* y, int y_ld, int act, void* stream);
 
@@ -183,6 +186,26 @@ int lpc_v10_decode_topk_keys(int dtype, const void* raw0, const void* raw1, cons
                              int B, int H0, int W0, int nc, const float* strides3_host, int K,
                              int img_h, int img_w, void* workspace, size_t ws_bytes, int keys_ready,
                              float* dets, int* anchor_idx, void* stream);
+/* lpc_v10_decode_topk_keys followed, inside the same kernel, by the predictor's rescale to the ORIGINAL image
+ * (ops.scale_boxes utils/ops.py:89-124 + clip_boxes :305-324, called from models/yolov10/predict.py:35):
+ * scale_back = device array [B][5] of (pad_x, pad_y, gain, orig_w, orig_h) per image, or NULL for none. */
+int lpc_v10_decode_topk_scaled(int dtype, const void* raw0, const void* raw1, const void* raw2, int ld,
+                               int B, int H0, int W0, int nc, const float* strides3_host, int K,
+                               int img_h, int img_w, void* workspace, size_t ws_bytes, int keys_ready,
+                               const float* scale_back, float* dets, int* anchor_idx, void* stream);
+/* The reference's small box helpers as kernels (function-level API parity; the fused tail above does not call them):
+ * lpc_make_anchors  utils/tal.py:294-306: anchors[A][2] = (x+offset, y+offset), stride_out[A]; levels in the given
+ *                   order, row-major cells; hw_host = {h0,w0,h1,w1,...} (1..4 levels).
+ * lpc_dist2bbox     utils/tal.py:309-319 on rows: dist[n][4] = (l,t,r,b), anchors[n_anchors][2] re-used every
+ *                   n_anchors rows (n % n_anchors == 0) -> out[n][4] = (cx,cy,w,h) if xywh else (x1,y1,x2,y2).
+ * lpc_scale_boxes   in place on n rows of row_stride floats whose first four are a box: xywh2xyxy (utils/ops.py:402-421)
+ *                   when xywh_in, then scale_boxes (ops.py:89-124: minus padding, / gain) and clip_boxes (:305-324)
+ *                   when clip_w > 0. */
+int lpc_make_anchors(int n_levels, const int* hw_host, const float* strides_host, float offset, float* anchors,
+                     float* stride_out, void* stream);
+int lpc_dist2bbox(const float* dist, const float* anchors, long long n, long long n_anchors, int xywh, float* out, void* stream);
+int lpc_scale_boxes(float* boxes, long long n, int row_stride, int xywh_in, float pad_x, float pad_y, float gain,
+                    float clip_w, float clip_h, void* stream);
 int lpc_v10_postprocess(const float* preds, long long stride_b, long long stride_a, long long stride_c,
                         int B, int A, int nc, int K, void* workspace, size_t ws_bytes,
                         float* boxes, float* scores, long long* labels, void* stream);

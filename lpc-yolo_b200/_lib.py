@@ -18,7 +18,7 @@ ACT_NONE, ACT_SILU, ACT_MISH, ACT_SIGMOID, ACT_RELU = 0, 1, 2, 3, 4
 
 _p, _i, _ll, _f32p, _sz = C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_size_t
 
-# name -> (restype, argtypes); mirrors include/lpcyolo.h one to one (tests/test_abi.py checks this)
+# name -> (restype, argtypes); mirrors include/lpcyolo.h one to one (tests/test_host_cpu.py::test_abi_exports_every_declared_symbol checks this)
 SIGNATURES = {
     "lpc_abi_version": (_i, []),
     "lpc_last_error": (C.c_char_p, []),
@@ -52,6 +52,11 @@ SIGNATURES = {
                                  _f32p, _p, _p]),
     "lpc_v10_decode_topk_keys": (_i, [_i, _p, _p, _p, _i, _i, _i, _i, _i, C.POINTER(C.c_float), _i, _i, _i, _p, _sz, _i,
                                       _f32p, _p, _p]),
+    "lpc_v10_decode_topk_scaled": (_i, [_i, _p, _p, _p, _i, _i, _i, _i, _i, C.POINTER(C.c_float), _i, _i, _i, _p, _sz, _i,
+                                        _f32p, _f32p, _p, _p]),
+    "lpc_make_anchors": (_i, [_i, C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_float, _f32p, _f32p, _p]),
+    "lpc_dist2bbox": (_i, [_f32p, _f32p, _ll, _ll, _i, _f32p, _p]),
+    "lpc_scale_boxes": (_i, [_f32p, _ll, _i, _i, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _p]),
     "lpc_v10_postprocess": (_i, [_f32p, _ll, _ll, _ll, _i, _i, _i, _i, _p, _sz, _f32p, _f32p, _p, _p]),
 }
 

@@ -4,6 +4,8 @@
 //
 // CTA = 64 queries of one (image, head); 256 threads as a 16x16 grid of 4x4 score tiles.
 // Loop over 64-key tiles: S = scale * Q K^T, running row max / sum, P -> smem, O += P V.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -123,6 +125,48 @@ psa_attention_kernel(const T* __restrict__ qkv, int ld, int N, int heads, int kd
       const int col = tx + 16 * d;
       if (col < hd) out[((long long)b * N + q) * out_ld + h * hd + col] = from_f<T>(o[i][d] * inv);
     }
+  }
+}
+
+// ---- fp32 validation mode --------------------------------------------------------------------------------
+// One warp per (image, head, query); scores, softmax and the PV sum are carried in fp64 and the output is rounded to
+// fp32 once (same contract as conv_direct_kernel<float>: a layer adds only the storage rounding of its output).
+constexpr int VAL_WARPS = 4;
+__global__ void __launch_bounds__(VAL_WARPS * 32)
+psa_attention_f32_validate_kernel(const float* __restrict__ qkv, int ld, int N, int heads, int kd, int hd, float* __restrict__ out, int out_ld) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ double val_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * VAL_WARPS + warp, h = blockIdx.y, b = blockIdx.z;
+  if (q >= N) return;
+  double* sc = val_smem + (size_t)warp * N;
+  const float* base = qkv + (long long)b * N * ld;
+  const int q_off = h * kd, k_off = heads * kd + h * kd, v_off = 2 * heads * kd + h * hd;
+  const double scale = 1.0 / sqrt((double)kd);
+  const float* qrow = base + (long long)q * ld + q_off;
+  double mx = -INFINITY;
+  for (int j = lane; j < N; j += 32) {
+    const float* krow = base + (long long)j * ld + k_off;
+    double a = 0.0;
+    for (int c = 0; c < kd; ++c) a = fma((double)qrow[c], (double)krow[c], a);
+    a *= scale;
+    sc[j] = a;
+    mx = fmax(mx, a);
+  }
+  for (int off = 16; off; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  double sum = 0.0;
+  for (int j = lane; j < N; j += 32) {
+    const double p = exp(sc[j] - mx);
+    sc[j] = p;
+    sum += p;
+  }
+  for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+  __syncwarp();
+  for (int d = lane; d < hd; d += 32) {
+    double o = 0.0;
+    for (int j = 0; j < N; ++j) o = fma(sc[j], (double)base[(long long)j * ld + v_off + d], o);
+    out[((long long)b * N + q) * out_ld + h * hd + d] = (float)(o / sum);
   }
 }
 
@@ -338,9 +382,15 @@ extern "C" int lpc_psa_attention(int dtype, const void* qkv, int qkv_ld, int B, 
   LPC_REQUIRE(qkv_ld >= heads * (2 * kd + hd) && out_ld >= heads * hd, "psa_attention: pitch too small");
   dim3 grid(cdiv(N, BQ), heads, B);
   cudaStream_t s = (cudaStream_t)stream;
-  static bool attr_done[2] = {false, false};
-  if (dtype == LPC_F32) {
-    if (!attr_done[0]) { cudaFuncSetAttribute(psa_attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM); attr_done[0] = true; }
+  static unsigned long long attr_done[2] = {0, 0};     // per device
+  if (dtype == LPC_F32 && !getenv("LPC_ATT_F32_FAST")) {
+    const size_t sm = (size_t)VAL_WARPS * N * sizeof(double);
+    LPC_REQUIRE(sm <= 200 * 1024, "psa_attention (fp32 validation): N = %d too large", N);
+    cudaFuncSetAttribute(psa_attention_f32_validate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    lpc_launch_pdl(psa_attention_f32_validate_kernel, dim3(cdiv(N, VAL_WARPS), heads, B), dim3(VAL_WARPS * 32), sm, s, (const float*)qkv, qkv_ld, N, heads, kd,
+                   hd, (float*)out, out_ld);
+  } else if (dtype == LPC_F32) {
+    if (lpc_first_on_device(&attr_done[0])) cudaFuncSetAttribute(psa_attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM);
     lpc_launch_pdl(psa_attention_kernel<float>, grid, ATT_NT, ATT_SMEM, s, (const float*)qkv, qkv_ld, N, heads, kd, hd, (float*)out, out_ld);
   } else if (dtype == LPC_BF16 && ((kd == 32 && hd == 64) || (kd == 36 && hd == 72)) && qkv_ld % 8 == 0 && out_ld % 2 == 0 &&
              aligned16(qkv) && (reinterpret_cast<uintptr_t>(out) & 3) == 0) {
@@ -349,7 +399,7 @@ extern "C" int lpc_psa_attention(int dtype, const void* qkv, int qkv_ld, int B, 
     if (kd == 32) lpc_launch_pdl(psa_attention_mma_kernel<32, 64>, g2, MMA_NT, 0, s, (const bf16*)qkv, qkv_ld, N, heads, (bf16*)out, out_ld);
     else lpc_launch_pdl(psa_attention_mma_kernel<36, 72>, g2, MMA_NT, 0, s, (const bf16*)qkv, qkv_ld, N, heads, (bf16*)out, out_ld);
   } else if (dtype == LPC_BF16) {
-    if (!attr_done[1]) { cudaFuncSetAttribute(psa_attention_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM); attr_done[1] = true; }
+    if (lpc_first_on_device(&attr_done[1])) cudaFuncSetAttribute(psa_attention_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM);
     lpc_launch_pdl(psa_attention_kernel<bf16>, grid, ATT_NT, ATT_SMEM, s, (const bf16*)qkv, qkv_ld, N, heads, kd, hd, (bf16*)out, out_ld);
   } else {
     LPC_FAIL(LPC_E_ARG, "psa_attention: unknown dtype %d", dtype);

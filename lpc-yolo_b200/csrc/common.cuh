@@ -55,6 +55,28 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif
 
+// One-time per-DEVICE work (cudaFuncSetAttribute is a per-context setting: a process that predicts on cuda:0 and later on
+// cuda:1 must raise the shared-memory limit of every kernel on both).  ``mask`` is a function-local static bit set.
+static inline bool lpc_first_on_device(unsigned long long* mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (*mask & bit) return false;
+  *mask |= bit;
+  return true;
+}
+static inline int lpc_num_sms() {
+  static int n[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& v = n[dev & 63];
+  if (!v) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
+  }
+  return v;
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
@@ -206,6 +228,21 @@ template <bool PRECISE> __device__ __forceinline__ float apply_act(float v, int 
     case LPC_ACT_MISH: return mish_<PRECISE>(v);
     case LPC_ACT_SIGMOID: return sigmoid_<PRECISE>(v);
     case LPC_ACT_RELU: return fmaxf(v, 0.0f);
+    default: return v;
+  }
+}
+// fp64 activations of the fp32 validation mode (one rounding per layer output, see conv_direct.cu)
+__device__ __forceinline__ double apply_act_f64(double v, int act) {
+  switch (act) {
+    case LPC_ACT_SILU: return v / (1.0 + exp(-v));
+    case LPC_ACT_MISH: {
+      if (v > 40.0) return v;
+      const double e = exp(v);
+      const double n = e * (e + 2.0);
+      return v * (n / (n + 2.0));
+    }
+    case LPC_ACT_SIGMOID: return 1.0 / (1.0 + exp(-v));
+    case LPC_ACT_RELU: return v > 0.0 ? v : 0.0;
     default: return v;
   }
 }

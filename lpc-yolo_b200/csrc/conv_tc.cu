@@ -584,16 +584,7 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+int num_sms() { return lpc_num_sms(); }
 
 int pick_kc(int Cin) { return Cin % 64 == 0 ? 64 : (Cin % 32 == 0 ? 32 : 16); }
 
@@ -868,8 +859,8 @@ extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) LPC_FAIL(LPC_E_CUDA, "conv2d_tc: weight tensor map encode failed (CUresult %d)", (int)r);
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_set = 0;     // per device
+  if (lpc_first_on_device(&attr_set)) {
     cudaError_t e1 = cudaFuncSetAttribute(conv_tc_taps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT + 16 * 1024);
     if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(conv_tc_taps2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT + 16 * 1024);
     cudaError_t e2 = cudaSuccess;
@@ -880,8 +871,7 @@ extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W
 #undef PAIR_ATTR
     HALO_ATTR(0) HALO_ATTR(16) HALO_ATTR(32) HALO_ATTR(48) HALO_ATTR(64) HALO_ATTR(128)
 #undef HALO_ATTR
-    if (e1 != cudaSuccess || e2 != cudaSuccess) LPC_FAIL(LPC_E_CUDA, "conv2d_tc: smem attribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
-    attr_set = true;
+    if (e1 != cudaSuccess || e2 != cudaSuccess) { attr_set = 0; LPC_FAIL(LPC_E_CUDA, "conv2d_tc: smem attribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)); }
   }
   // Four accumulator buffers when TMEM allows without costing a resident CTA: with two, the per-buffer chain
   // MMA(t) -> epilogue(t) -> MMA(t+2) makes the tile period (M + E) / 2 instead of max(M, E / groups).

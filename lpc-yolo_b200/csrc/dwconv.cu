@@ -430,16 +430,7 @@ DwEncodeFn dw_get_encode() {
   });
   return fn;
 }
-int dw_num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+int dw_num_sms() { return lpc_num_sms(); }
 
 // returns LPC_OK when launched, 1 when the shape is left to the register-window kernel
 template <int K, int S, int D>
@@ -519,11 +510,8 @@ int launch_dw_tma(const void* x, int x_ld, int B, int H, int W, int C, const flo
     if (r != CUDA_SUCCESS) return 1;
   }
   const size_t smem = 2 * (size_t)p.stage_bytes + (size_t)K * K * p.CB * 2 + 128;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(dwconv_tma_kernel<K, S, D, PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    attr_done = true;
-  }
+  static unsigned long long attr_done = 0;     // per device
+  if (lpc_first_on_device(&attr_done)) cudaFuncSetAttribute(dwconv_tma_kernel<K, S, D, PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   const int per_sm = (int)((200 * 1024) / (smem + 1024));
   (void)per_sm;
   long long gx = (2ll * dw_num_sms() + p.cblks - 1) / p.cblks;      // two resident CTAs per SM in total, split over the channel blocks
@@ -568,6 +556,37 @@ int dispatch_dw(const void* x, int x_ld, int B, int H, int W, int C, const float
 
 }  // namespace
 
+// fp32 validation mode: one thread per (output pixel, channel), products and sums in fp64, bias / activation / residual
+// in fp64, ONE rounding to fp32 per output (same contract as conv_direct_kernel<float>; speed is irrelevant here).
+__global__ void __launch_bounds__(256)
+dwconv_f32_validate_kernel(const float* __restrict__ x, int x_ld, int B, int H, int W, int C, const float* __restrict__ w,
+                           const float* __restrict__ bias, int K, int S, int pad, int D, int Ho, int Wo,
+                           float* __restrict__ y, int y_ld, int act, const float* __restrict__ res, int res_ld) {
+  pdl_trigger();
+  pdl_wait();
+  const long long total = (long long)B * Ho * Wo * C;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % C);
+  const long long pix = idx / C;
+  const int ox = (int)(pix % Wo);
+  const int oy = (int)((pix / Wo) % Ho);
+  const int n = (int)(pix / ((long long)Wo * Ho));
+  double acc = bias ? (double)bias[c] : 0.0;
+  for (int ky = 0; ky < K; ++ky) {
+    const int iy = oy * S - pad + ky * D;
+    if (iy < 0 || iy >= H) continue;
+    for (int kx = 0; kx < K; ++kx) {
+      const int ix = ox * S - pad + kx * D;
+      if (ix < 0 || ix >= W) continue;
+      acc = fma((double)x[((long long)(n * H + iy) * W + ix) * x_ld + c], (double)w[(ky * K + kx) * C + c], acc);
+    }
+  }
+  acc = apply_act_f64(acc, act);
+  if (res) acc += (double)res[pix * res_ld + c];
+  y[pix * y_ld + c] = (float)acc;
+}
+
 extern "C" int lpc_dwconv2d(int dtype, const void* x, int x_ld, int B, int H, int W, int C, const float* w,
                             const float* bias, int k, int stride, int pad, int dil, void* y, int y_ld, int act,
                             const void* res, int res_ld, void* stream) {
@@ -581,7 +600,15 @@ extern "C" int lpc_dwconv2d(int dtype, const void* x, int x_ld, int B, int H, in
   const int Ho = (H + 2 * pad - ke) / stride + 1, Wo = (W + 2 * pad - ke) / stride + 1;
   LPC_REQUIRE(Ho > 0 && Wo > 0, "dwconv2d: empty output");
   cudaStream_t s = (cudaStream_t)stream;
-  if (dtype == LPC_F32) return dispatch_dw<float>(x, x_ld, B, H, W, C, w, bias, k, stride, pad, dil, Ho, Wo, y, y_ld, act, res, res_ld, s);
+  if (dtype == LPC_F32) {
+    static const int fast32 = [] { const char* e = getenv("LPC_DW_F32_FAST"); return e ? atoi(e) : 0; }();
+    if (fast32) return dispatch_dw<float>(x, x_ld, B, H, W, C, w, bias, k, stride, pad, dil, Ho, Wo, y, y_ld, act, res, res_ld, s);
+    const long long total = (long long)B * Ho * Wo * C;
+    lpc_launch_pdl(dwconv_f32_validate_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, (const float*)x, x_ld, B, H, W, C, w, bias,
+                   k, stride, pad, dil, Ho, Wo, (float*)y, y_ld, act, (const float*)res, res_ld);
+    LPC_CHECK_LAUNCH("dwconv2d (fp32 validation)");
+    return LPC_OK;
+  }
   if (dtype == LPC_BF16) return dispatch_dw<bf16>(x, x_ld, B, H, W, C, w, bias, k, stride, pad, dil, Ho, Wo, y, y_ld, act, res, res_ld, s);
   LPC_FAIL(LPC_E_ARG, "dwconv2d: unknown dtype %d", dtype);
 }

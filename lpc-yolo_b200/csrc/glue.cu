@@ -700,3 +700,98 @@ extern "C" int lpc_cbam_apply(int dtype, const void* x, int x_ld, int B, int H, 
   DISPATCH_T(dtype, (lpc_launch_pdl(cbam_apply_kernel<float>, g, CB_T * CB_T, smem, s, (const float*)x, x_ld, H, W, C, ca, stats, w, k, (float*)y, y_ld)),
              (lpc_launch_pdl(cbam_apply_kernel<bf16>, g, CB_T * CB_T, smem, s, (const bf16*)x, x_ld, H, W, C, ca, stats, w, k, (bf16*)y, y_ld)), "cbam_apply")
 }
+
+// ---- small box utilities behind the reference's utils/tal.py / utils/ops.py function API -----------------------------
+// (the engine never calls these: the fused tail computes anchors, dist2bbox, xywh2xyxy, scale_boxes and clip_boxes itself)
+namespace {
+
+// anchors[a] = (x + offset, y + offset), stride_out[a] = stride of a's level; a = level offset + y * W_l + x
+__global__ void make_anchors_kernel(int n_levels, int4 starts, int4 widths, float4 strides, float offset, int A,
+                                    float* __restrict__ anchors, float* __restrict__ stride_out) {
+  pdl_trigger();
+  pdl_wait();
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= A) return;
+  const int st[4] = {starts.x, starts.y, starts.z, starts.w};
+  const int wd[4] = {widths.x, widths.y, widths.z, widths.w};
+  const float sv[4] = {strides.x, strides.y, strides.z, strides.w};
+  int l = 0;
+  for (int i = 1; i < n_levels; ++i)
+    if (a >= st[i]) l = i;
+  const int cell = a - st[l];
+  const int y = cell / wd[l], x = cell - y * wd[l];
+  anchors[2 * a] = (float)x + offset;
+  anchors[2 * a + 1] = (float)y + offset;
+  stride_out[a] = sv[l];
+}
+
+// rows of (l, t, r, b) distances + (ax, ay) anchor points -> (cx, cy, w, h) or (x1, y1, x2, y2)
+__global__ void dist2bbox_kernel(const float4* __restrict__ dist, const float2* __restrict__ anchors, long long n, long long anchor_mod, int xywh,
+                                 float4* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 d = dist[i];
+  const float2 a = anchors[i % anchor_mod];
+  const float x1 = a.x - d.x, y1 = a.y - d.y, x2 = a.x + d.z, y2 = a.y + d.w;
+  out[i] = xywh ? make_float4((x1 + x2) / 2, (y1 + y2) / 2, x2 - x1, y2 - y1) : make_float4(x1, y1, x2, y2);
+}
+
+// in place on rows whose first four floats are a box: optional xywh -> xyxy, minus padding, / gain, optional clip
+__global__ void scale_boxes_kernel(float* __restrict__ boxes, long long n, int row_stride, int xywh_in, float pad_x, float pad_y, float gain,
+                                   float clip_w, float clip_h) {
+  pdl_trigger();
+  pdl_wait();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float* b = boxes + i * row_stride;
+  float x1 = b[0], y1 = b[1], x2 = b[2], y2 = b[3];
+  if (xywh_in) {
+    const float dw = x2 / 2, dh = y2 / 2, cx = x1, cy = y1;
+    x1 = cx - dw; y1 = cy - dh; x2 = cx + dw; y2 = cy + dh;
+  }
+  x1 -= pad_x; x2 -= pad_x; y1 -= pad_y; y2 -= pad_y;
+  if (gain != 1.0f) { x1 /= gain; y1 /= gain; x2 /= gain; y2 /= gain; }
+  if (clip_w > 0.f) {
+    x1 = fminf(fmaxf(x1, 0.f), clip_w); x2 = fminf(fmaxf(x2, 0.f), clip_w);
+    y1 = fminf(fmaxf(y1, 0.f), clip_h); y2 = fminf(fmaxf(y2, 0.f), clip_h);
+  }
+  b[0] = x1; b[1] = y1; b[2] = x2; b[3] = y2;
+}
+
+}  // namespace
+
+extern "C" int lpc_make_anchors(int n_levels, const int* hw_host, const float* strides_host, float offset, float* anchors,
+                                float* stride_out, void* stream) {
+  LPC_REQUIRE(n_levels >= 1 && n_levels <= 4 && hw_host && strides_host && anchors && stride_out, "make_anchors: bad argument (1..4 levels)");
+  int st[4] = {0, 0, 0, 0}, wd[4] = {1, 1, 1, 1};
+  float sv[4] = {0, 0, 0, 0};
+  int A = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    LPC_REQUIRE(hw_host[2 * l] > 0 && hw_host[2 * l + 1] > 0, "make_anchors: empty level");
+    st[l] = A; wd[l] = hw_host[2 * l + 1]; sv[l] = strides_host[l];
+    A += hw_host[2 * l] * hw_host[2 * l + 1];
+  }
+  lpc_launch_pdl(make_anchors_kernel, dim3(cdiv(A, 256)), dim3(256), 0, (cudaStream_t)stream, n_levels, make_int4(st[0], st[1], st[2], st[3]),
+                 make_int4(wd[0], wd[1], wd[2], wd[3]), make_float4(sv[0], sv[1], sv[2], sv[3]), offset, A, anchors, stride_out);
+  LPC_CHECK_LAUNCH("make_anchors");
+  return LPC_OK;
+}
+
+extern "C" int lpc_dist2bbox(const float* dist, const float* anchors, long long n, long long n_anchors, int xywh, float* out, void* stream) {
+  LPC_REQUIRE(dist && anchors && out && n > 0 && n_anchors > 0 && n % n_anchors == 0, "dist2bbox: bad argument");
+  LPC_REQUIRE(aligned16(dist) && aligned16(out) && (reinterpret_cast<uintptr_t>(anchors) & 7) == 0, "dist2bbox: rows must be 16-byte aligned");
+  lpc_launch_pdl(dist2bbox_kernel, dim3(cdiv(n, 256)), dim3(256), 0, (cudaStream_t)stream, (const float4*)dist, (const float2*)anchors, n, n_anchors, xywh,
+                 (float4*)out);
+  LPC_CHECK_LAUNCH("dist2bbox");
+  return LPC_OK;
+}
+
+extern "C" int lpc_scale_boxes(float* boxes, long long n, int row_stride, int xywh_in, float pad_x, float pad_y, float gain, float clip_w,
+                               float clip_h, void* stream) {
+  LPC_REQUIRE(boxes && n > 0 && row_stride >= 4 && gain > 0.f, "scale_boxes: bad argument");
+  lpc_launch_pdl(scale_boxes_kernel, dim3(cdiv(n, 256)), dim3(256), 0, (cudaStream_t)stream, boxes, n, row_stride, xywh_in, pad_x, pad_y, gain, clip_w, clip_h);
+  LPC_CHECK_LAUNCH("scale_boxes");
+  return LPC_OK;
+}

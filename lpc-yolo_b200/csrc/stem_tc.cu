@@ -340,15 +340,14 @@ int lpc_stem_conv_tc(const void* x, int B, int H, int W, const float* w, const f
   const size_t smem = 2 * SB_A_BYTES + (size_t)Cout * 128 + (size_t)SB_DEPTH * 128 * SB_SLOT + 1024;
   void (*kern)(StemTcParams, CUtensorMap) = act == LPC_ACT_SILU ? stem_tc_kernel<LPC_ACT_SILU> : act == LPC_ACT_MISH ? stem_tc_kernel<LPC_ACT_MISH>
                               : act == LPC_ACT_NONE ? stem_tc_kernel<LPC_ACT_NONE> : stem_tc_kernel<LPC_ACT_RELU>;
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr = 0;     // per device
+  if (lpc_first_on_device(&attr)) {
     const int lim = 2 * SB_A_BYTES + 128 * 128 + SB_DEPTH * 128 * SB_SLOT + 1024;
     if (cudaFuncSetAttribute(stem_tc_kernel<LPC_ACT_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
         cudaFuncSetAttribute(stem_tc_kernel<LPC_ACT_MISH>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
         cudaFuncSetAttribute(stem_tc_kernel<LPC_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
         cudaFuncSetAttribute(stem_tc_kernel<LPC_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess)
-      LPC_FAIL(LPC_E_CUDA, "stem_conv: smem attribute");
-    attr = true;
+    { attr = 0; LPC_FAIL(LPC_E_CUDA, "stem_conv: smem attribute"); }
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

@@ -331,7 +331,7 @@ template <> struct HitTest<bf16, 16> {
 template <typename T, int PASSES, int MODE>
 __global__ void __launch_bounds__(SEL_NT)
 select_decode_kernel(const __grid_constant__ TailSrc s, int K, int sortn, const uint32_t* __restrict__ amax, int cache_cap_keys, int vec_ok,
-                     int img_h, int img_w, float* __restrict__ dets, int* __restrict__ anchor_idx,
+                     int img_h, int img_w, const float* __restrict__ scale_back, float* __restrict__ dets, int* __restrict__ anchor_idx,
                      float* __restrict__ boxes_out, float* __restrict__ scores_out, long long* __restrict__ labels_out) {
   pdl_trigger();
   extern __shared__ __align__(16) unsigned char dsm[];
@@ -511,6 +511,14 @@ select_decode_kernel(const __grid_constant__ TailSrc s, int K, int sortn, const 
           X1 = fminf(fmaxf(X1, 0.f), (float)img_w); X2 = fminf(fmaxf(X2, 0.f), (float)img_w);
           Y1 = fminf(fmaxf(Y1, 0.f), (float)img_h); Y2 = fminf(fmaxf(Y2, 0.f), (float)img_h);
         }
+        if (scale_back) {
+          // ops.scale_boxes (utils/ops.py:89-124) + clip_boxes (:305-324) of this image: subtract the LetterBox padding,
+          // divide by the resize gain (IEEE division, as torch's fp32 ``boxes /= gain``), clamp to the original image
+          const float* sp = scale_back + (long long)b * 5;
+          const float px = sp[0], py = sp[1], gain = sp[2], ow = sp[3], oh = sp[4];
+          X1 = fminf(fmaxf((X1 - px) / gain, 0.f), ow); X2 = fminf(fmaxf((X2 - px) / gain, 0.f), ow);
+          Y1 = fminf(fmaxf((Y1 - py) / gain, 0.f), oh); Y2 = fminf(fmaxf((Y2 - py) / gain, 0.f), oh);
+        }
         float2* o = reinterpret_cast<float2*>(dets + ((long long)b * K + r) * 6);   // 24-byte rows: 8-byte aligned
         o[0] = make_float2(X1, Y1);
         o[1] = make_float2(X2, Y2);
@@ -607,7 +615,7 @@ int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 constexpr int SEL_SMEM_BUDGET = 200 * 1024;
 
 template <typename T, int PASSES, int MODE>
-int launch_select(const TailSrc& s, int B, int K, const uint32_t* amax, int img_h, int img_w, float* dets, int* aidx,
+int launch_select(const TailSrc& s, int B, int K, const uint32_t* amax, int img_h, int img_w, const float* scale_back, float* dets, int* aidx,
                   float* boxes, float* scores, long long* labels, cudaStream_t st) {
   const int sortn = next_pow2(K) < 4 ? 4 : next_pow2(K);   // multiple of 4: keeps the key cache 16-byte aligned
   const size_t fixed = (size_t)(CAND_CAP + 4 + RANK_CAP + 4) * 8 + (size_t)sortn * (8 + 4);
@@ -622,7 +630,7 @@ int launch_select(const TailSrc& s, int B, int K, const uint32_t* amax, int img_
   constexpr int V = Vec<T>::N;
   const int vec_ok = MODE == 0 && s.sc == 1 && s.nc % V == 0 && s.sa % V == 0 && s.c_off % V == 0 && aligned16(s.ptr[0]) && aligned16(s.ptr[1]) &&
                      aligned16(s.ptr[2]) && s.img_stride[0] % V == 0 && s.img_stride[1] % V == 0 && s.img_stride[2] % V == 0;
-  lpc_launch_pdl(kern, B, SEL_NT, smem, st, s, K, sortn, amax, cap, vec_ok, img_h, img_w, dets, aidx, boxes, scores, labels);
+  lpc_launch_pdl(kern, B, SEL_NT, smem, st, s, K, sortn, amax, cap, vec_ok, img_h, img_w, scale_back, dets, aidx, boxes, scores, labels);
   LPC_CHECK_LAUNCH("select_decode");
   return LPC_OK;
 }
@@ -664,6 +672,14 @@ extern "C" int lpc_v10_decode_topk(int dtype, const void* raw0, const void* raw1
 extern "C" int lpc_v10_decode_topk_keys(int dtype, const void* raw0, const void* raw1, const void* raw2, int ld, int B,
                                         int H0, int W0, int nc, const float* strides, int K, int img_h, int img_w,
                                         void* workspace, size_t ws_bytes, int keys_ready, float* dets, int* anchor_idx, void* stream) {
+  return lpc_v10_decode_topk_scaled(dtype, raw0, raw1, raw2, ld, B, H0, W0, nc, strides, K, img_h, img_w, workspace, ws_bytes, keys_ready,
+                                    nullptr, dets, anchor_idx, stream);
+}
+
+extern "C" int lpc_v10_decode_topk_scaled(int dtype, const void* raw0, const void* raw1, const void* raw2, int ld, int B,
+                                          int H0, int W0, int nc, const float* strides, int K, int img_h, int img_w,
+                                          void* workspace, size_t ws_bytes, int keys_ready, const float* scale_back,
+                                          float* dets, int* anchor_idx, void* stream) {
   TailSrc s;
   if (int e = make_raw_src(s, "v10_decode_topk", dtype, raw0, raw1, raw2, ld, B, H0, W0, nc, strides)) return e;
   LPC_REQUIRE(dets && workspace, "v10_decode_topk: null pointer");
@@ -679,7 +695,7 @@ extern "C" int lpc_v10_decode_topk_keys(int dtype, const void* raw0, const void*
       else lpc_launch_pdl(amax_keys_kernel<bf16, false>, g, 256, 0, st, s, B, amax);
       LPC_CHECK_LAUNCH("amax_keys");
     }
-    return launch_select<bf16, 2, 0>(s, B, K, amax, img_h, img_w, dets, anchor_idx, nullptr, nullptr, nullptr, st);
+    return launch_select<bf16, 2, 0>(s, B, K, amax, img_h, img_w, scale_back, dets, anchor_idx, nullptr, nullptr, nullptr, st);
   } else if (dtype == LPC_F32) {
     const bool vec = (nc % 4 == 0) && (ld % 4 == 0) && aligned16(raw0) && aligned16(raw1) && aligned16(raw2);
     if (!keys_ready) {
@@ -687,7 +703,7 @@ extern "C" int lpc_v10_decode_topk_keys(int dtype, const void* raw0, const void*
       else lpc_launch_pdl(amax_keys_kernel<float, false>, g, 256, 0, st, s, B, amax);
       LPC_CHECK_LAUNCH("amax_keys");
     }
-    return launch_select<float, 4, 0>(s, B, K, amax, img_h, img_w, dets, anchor_idx, nullptr, nullptr, nullptr, st);
+    return launch_select<float, 4, 0>(s, B, K, amax, img_h, img_w, scale_back, dets, anchor_idx, nullptr, nullptr, nullptr, st);
   }
   LPC_FAIL(LPC_E_ARG, "v10_decode_topk: unknown dtype %d", dtype);
 }
@@ -708,5 +724,5 @@ extern "C" int lpc_v10_postprocess(const float* preds, long long stride_b, long 
   const int g = cdiv((long long)B * A, 256);
   lpc_launch_pdl(amax_keys_kernel<float, false>, g, 256, 0, st, s, B, amax);
   LPC_CHECK_LAUNCH("amax_keys");
-  return launch_select<float, 4, 1>(s, B, K, amax, 0, 0, nullptr, nullptr, boxes, scores, labels, st);
+  return launch_select<float, 4, 1>(s, B, K, amax, 0, 0, nullptr, nullptr, nullptr, boxes, scores, labels, st);
 }

@@ -23,6 +23,7 @@ from .nn.tasks import YOLOv10DetectionModel
 
 DEFAULTS = dict(conf=0.25, max_det=300, classes=None, half=True, device=None, verbose=False, imgsz=640, batch=1,
                 augment=False, visualize=False, embed=None, stream=False, fp32=False)
+_HALF_WARNED = False
 CALLBACK_EVENTS = ("on_predict_start", "on_predict_batch_start", "on_predict_postprocess_end", "on_predict_batch_end",
                    "on_predict_end")
 
@@ -30,15 +31,18 @@ CALLBACK_EVENTS = ("on_predict_start", "on_predict_batch_start", "on_predict_pos
 def _chunk_plan(B):
     """Chunk sizes of a host batch: chunk i+1's H2D copy overlaps chunk i's graph replay.  A small first chunk starts the
     compute early, one large second chunk keeps the kernels efficient (measured on B200, LPC @640 B=64, uint8 source:
-    1 chunk 4.7 ms, 2 x 32 4.5 ms, 4 x 16 5.3 ms, 8 x 8 7.6 ms per step; H2D 55 GB/s).  LPC_E2E_CHUNKS=n forces n equal chunks."""
+    1 chunk 4.7 ms, 2 x 32 4.5 ms, 4 x 16 5.3 ms, 8 x 8 7.6 ms per step; H2D 55 GB/s).  LPC_E2E_CHUNKS=n forces n equal chunks,
+    LPC_E2E_PLAN=a,b,... explicit sizes (measurement)."""
     import os
-    plan = os.environ.get("LPC_E2E_PLAN")          # explicit chunk sizes, e.g. "8,24,32" (measurement)
+    if B <= 0:
+        return []
+    plan = os.environ.get("LPC_E2E_PLAN")
     if plan:
-        sizes = [int(v) for v in plan.split(",")]
+        sizes = [int(v) for v in plan.split(",") if v.strip()]
         if sum(sizes) == B and all(v > 0 for v in sizes):
             return sizes
     env = os.environ.get("LPC_E2E_CHUNKS")
-    if env and B % int(env) == 0:
+    if env and env.isdigit() and int(env) > 0 and B % int(env) == 0:
         return [B // int(env)] * int(env)
     if B >= 32 and B % 4 == 0:
         # first chunk ~5/16 of the batch: its replay then lasts as long as the copy of the rest (measured B=64, ms / step with
@@ -48,16 +52,6 @@ def _chunk_plan(B):
     if B >= 8 and B % 2 == 0:
         return [B // 2, B // 2]
     return [B]
-
-
-def _chunks(B):
-    """How many chunks a host batch is cut into so that chunk i+1's H2D copy overlaps chunk i's graph replay.
-    LPC_E2E_CHUNKS overrides (measurement)."""
-    import os
-    env = os.environ.get("LPC_E2E_CHUNKS")
-    if env and B % int(env) == 0:
-        return int(env)
-    return 4 if B % 4 == 0 and B >= 16 else (2 if B % 2 == 0 and B >= 4 else 1)
 
 
 class Profile:
@@ -189,10 +183,13 @@ class YOLOv10DetectionPredictor:
         self.model.fuse()
 
     def preprocess(self, im):
-        """predictor.py:115-133 for tensors: move to the device (no /255 for tensors)."""
+        """predictor.py:115-133 for tensors: move to the device (no /255 for float tensors; a uint8 BCHW tensor is the
+        0-255 case LoadTensor normalises, data/loaders.py:479-485)."""
         im = check_tensor_source(im)
         if not im.is_cuda:
             im = (im.pin_memory() if not im.is_pinned() else im).to(self.device, non_blocking=True)
+        if im.dtype == torch.uint8:
+            return im.float() / 255
         return im.float() if im.dtype != torch.float32 else im
 
     def inference(self, im):
@@ -201,60 +198,78 @@ class YOLOv10DetectionPredictor:
 
     # ---- host-source fast path: chunked H2D copies overlapped with CUDA-graph replays ---------------------------
     class _Graphed:
-        """Two CUDA graphs of ``model.detect`` on two static input buffers (double buffering)."""
+        """Two CUDA graphs (double buffering) of ``run(static_input)`` on two static input buffers."""
 
-        def __init__(self, model, shape, max_det):
-            dev = next(model.parameters()).device
-            self.inp = [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(2)]
-            for t in self.inp:
-                t.fill_(0.5)
+        def __init__(self, dev, make_input, run):
+            self.inp = [make_input() for _ in range(2)]
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
                 for _ in range(2):
-                    model.detect(self.inp[0], max_det, clip=True)
+                    run(self.inp[0])
             torch.cuda.current_stream(dev).wait_stream(side)
             self.graphs, self.outs = [], []
             for i in range(2):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    out = model.detect(self.inp[i], max_det, clip=True)
+                    out = run(self.inp[i])
                 self.graphs.append(g)
                 self.outs.append(out)
 
-    def inference_from_host(self, im_host):
-        """[B,3,H,W] fp32 host tensor -> [B,K,6] on the device.  The batch is cut into up to four chunks; chunk i+1's
-        host-to-device copy (copy stream) overlaps chunk i's graph replay (compute stream)."""
+    def _graph_cache(self):
+        """Captured graphs hold raw pointers to the packed weights: the cache is dropped whenever any packed-weight cache
+        was cleared since the capture (load / load_state_dict / .to(): nn/modules/base.py ``weights_epoch``)."""
+        from .nn.modules import base
+        ep = base.weights_epoch()
+        if self.__dict__.get("_graph_epoch") != ep:
+            self._graphed = {}
+            self._graph_epoch = ep
+        return self._graphed
+
+    def _replay_chunks(self, im_host, plan, gds):
+        """Chunk i+1's host-to-device copy (copy stream) overlaps chunk i's graph replay (compute stream)."""
         B = im_host.shape[0]
-        n = _chunks(B)
-        cb = B // n
-        key = (cb, tuple(im_host.shape[1:]), self.args.max_det, self.model.compute_dtype)
-        cache = self.__dict__.setdefault("_graphed", {})
-        if key not in cache:
-            cache[key] = self._Graphed(self.model, (cb, *im_host.shape[1:]), self.args.max_det)
-        gd = cache[key]
         if not im_host.is_pinned():
             im_host = im_host.pin_memory()
         cur = torch.cuda.current_stream(self.device)
         cs = self.__dict__.setdefault("_copy_stream", torch.cuda.Stream(device=self.device))
         cs.wait_stream(cur)
         preds = torch.empty((B, self.args.max_det, 6), dtype=torch.float32, device=self.device)
-        done = []
-        for i in range(n):
-            b = i & 1
+        used, done = {}, {}                           # graph object -> buffers already used in this call / replay-finished events
+        lo = 0
+        for cb, gd in zip(plan, gds):
+            b = used.get(id(gd), 0) & 1
+            used[id(gd)] = used.get(id(gd), 0) + 1
             ev = torch.cuda.Event()
             with torch.cuda.stream(cs):
-                if i >= 2:
-                    cs.wait_event(done[i - 2])           # the replay that read this buffer has finished
-                gd.inp[b].copy_(im_host[i * cb:(i + 1) * cb], non_blocking=True)
+                if (id(gd), b) in done:
+                    cs.wait_event(done[(id(gd), b)])     # the replay that read this buffer has finished
+                gd.inp[b].copy_(im_host[lo:lo + cb], non_blocking=True)
                 ev.record(cs)
             cur.wait_event(ev)
             gd.graphs[b].replay()
-            preds[i * cb:(i + 1) * cb].copy_(gd.outs[b])
+            preds[lo:lo + cb].copy_(gd.outs[b])
             d = torch.cuda.Event()
             d.record(cur)
-            done.append(d)
+            done[(id(gd), b)] = d
+            lo += cb
         return preds
+
+    def inference_from_host(self, im_host):
+        """[B,3,H,W] fp32 host tensor -> [B,K,6] on the device, through the same chunk plan as the uint8 path."""
+        B = im_host.shape[0]
+        plan = _chunk_plan(B)
+        cache = self._graph_cache()
+        model, K, dev = self.model, self.args.max_det, self.device
+        gds = []
+        for cb in plan:
+            key = ("f32", cb, tuple(im_host.shape[1:]), K, model.compute_dtype)
+            if key not in cache:
+                shape = (cb, *im_host.shape[1:])
+                cache[key] = self._Graphed(dev, lambda shape=shape: torch.full(shape, 0.5, dtype=torch.float32, device=dev),
+                                           lambda x: model.detect(x, K, clip=True))
+            gds.append(cache[key])
+        return self._replay_chunks(im_host, plan, gds)
 
     # ---- array sources: uint8 HWC (cv2 / BGR) images, SURVEY.md section 8(f) row 1 ------------------------------
     @staticmethod
@@ -273,84 +288,101 @@ class YOLOv10DetectionPredictor:
         nh, nw = new_unpad[1], new_unpad[0]
         return nh + top + bottom, nw + left + right, top, left, nh, nw
 
-    class _GraphedU8:
-        """Two CUDA graphs of pack_u8 + ``model.detect`` on two static uint8 input buffers."""
+    @staticmethod
+    def scale_back_row(geom, hs, ws):
+        """utils/ops.py:89-124 scale_boxes' constants for an image of shape (hs, ws) letterboxed to ``geom``:
+        (pad_x, pad_y, gain, orig_w, orig_h), or None when the rescale is the identity (the tail's clip then is clip_boxes)."""
+        H, W = geom[0], geom[1]
+        gain = min(H / hs, W / ws)                                        # :110
+        pad_w = round((W - ws * gain) / 2 - 0.1)                          # :111-114
+        pad_h = round((H - hs * gain) / 2 - 0.1)
+        if gain == 1.0 and pad_w == 0 and pad_h == 0:
+            return None
+        return (float(pad_w), float(pad_h), float(gain), float(ws), float(hs))
 
-        def __init__(self, model, cb, hs, ws, geom, max_det):
-            dev = next(model.parameters()).device
-            H, W, top, left, nh, nw = geom
-            self.inp = [torch.full((cb, hs, ws, 3), 114, dtype=torch.uint8, device=dev) for _ in range(2)]
-            self.net = [torch.empty((cb, H, W, 4), dtype=model.compute_dtype, device=dev) for _ in range(2)]
-            tables = F.resize_tables(hs, ws, nh, nw, dev) if (nh, nw) != (hs, ws) else None
+    def _prep_u8(self, src, geom, tables):
+        """uint8 HWC device images -> network input (LetterBox resize + border, BGR->RGB, /255, NHWC) in one kernel."""
+        H, W, top, left, nh, nw = geom
+        dt = self.model.compute_dtype
+        if tables is None:                      # LetterBox ratio 1: border + pack only
+            return F.pack_u8(src, dt, top, left, H, W, 114, True)
+        return F.letterbox_u8(src, dt, nh, nw, tables, top, left, H, W, 114, True)
 
-            def run(i):
-                if tables is None:                  # LetterBox ratio 1: border + pack only
-                    x = F.pack_u8(self.inp[i], model.compute_dtype, top, left, H, W, 114, True, out=self.net[i])
-                else:                               # cv2.resize(INTER_LINEAR) fused in front
-                    x = F.letterbox_u8(self.inp[i], model.compute_dtype, nh, nw, tables, top, left, H, W, 114, True, out=self.net[i])
-                return model.detect(x, max_det, clip=True)
-
-            side = torch.cuda.Stream(device=dev)
-            side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):
-                for _ in range(2):
-                    run(0)
-            torch.cuda.current_stream(dev).wait_stream(side)
-            self.graphs, self.outs = [], []
-            for i in range(2):
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    out = run(i)
-                self.graphs.append(g)
-                self.outs.append(out)
+    def _u8_runner(self, cb, hs, ws, geom):
+        """-> run(uint8 [cb,hs,ws,3] device tensor) -> [cb,K,6] in ORIGINAL-image coordinates (rescale fused in the tail)."""
+        dev, model, K = self.device, self.model, self.args.max_det
+        nh, nw = geom[4], geom[5]
+        tables = F.resize_tables(hs, ws, nh, nw, dev) if (nh, nw) != (hs, ws) else None
+        row = self.scale_back_row(geom, hs, ws)
+        scale = torch.tensor([row] * cb, dtype=torch.float32, device=dev) if row is not None else None
+        return lambda inp: model.detect(self._prep_u8(inp, geom, tables), K, clip=True, scale_back=scale)
 
     def inference_from_host_u8(self, im_host):
-        """[B,h,w,3] uint8 host tensor (BGR) -> [B,K,6] on the device, in network-input coordinates.  Same chunked
-        copy / replay overlap as ``inference_from_host``; the H2D copy moves 3 bytes per pixel instead of 12."""
+        """[B,h,w,3] uint8 host tensor (BGR, one shape) -> [B,K,6] on the device in original-image coordinates.  Chunked
+        copy / replay overlap; the H2D copy moves 3 bytes per pixel instead of 12."""
         B, hs, ws, _ = im_host.shape
         geom = self.letterbox_geometry((hs, ws), self.args.imgsz, int(max(self.model.stride)), auto=True)
         plan = _chunk_plan(B)
-        cache = self.__dict__.setdefault("_graphed", {})
+        cache = self._graph_cache()
+        dev = self.device
         gds = []
         for cb in plan:
             key = ("u8", cb, hs, ws, geom, self.args.max_det, self.model.compute_dtype)
             if key not in cache:
-                cache[key] = self._GraphedU8(self.model, cb, hs, ws, geom, self.args.max_det)
+                cache[key] = self._Graphed(dev, lambda cb=cb: torch.full((cb, hs, ws, 3), 114, dtype=torch.uint8, device=dev),
+                                           self._u8_runner(cb, hs, ws, geom))
             gds.append(cache[key])
-        if not im_host.is_pinned():
-            im_host = im_host.pin_memory()
-        cur = torch.cuda.current_stream(self.device)
-        cs = self.__dict__.setdefault("_copy_stream", torch.cuda.Stream(device=self.device))
-        cs.wait_stream(cur)
-        preds = torch.empty((B, self.args.max_det, 6), dtype=torch.float32, device=self.device)
-        used = {}                                     # graph object -> buffers already used in this call
-        done = {}
-        lo = 0
-        for cb, gd in zip(plan, gds):
-            b = used.get(id(gd), 0) & 1
-            used[id(gd)] = used.get(id(gd), 0) + 1
-            ev = torch.cuda.Event()
-            with torch.cuda.stream(cs):
-                if (id(gd), b) in done:
-                    cs.wait_event(done[(id(gd), b)])     # the replay that read this buffer has finished
-                gd.inp[b].copy_(im_host[lo:lo + cb], non_blocking=True)
-                ev.record(cs)
-            cur.wait_event(ev)
-            gd.graphs[b].replay()
-            preds[lo:lo + cb].copy_(gd.outs[b])
-            d = torch.cuda.Event()
-            d.record(cur)
-            done[(id(gd), b)] = d
-            lo += cb
-        self._pad = (geom[2], geom[3], hs, ws, geom[0], geom[1])
-        return preds
+        return self._replay_chunks(im_host, plan, gds)
+
+    def inference_u8_device(self, im):
+        """uint8 HWC images already on the device (one shape): no copy, eager launches."""
+        B, hs, ws, _ = im.shape
+        geom = self.letterbox_geometry((hs, ws), self.args.imgsz, int(max(self.model.stride)), auto=True)
+        return self._u8_runner(B, hs, ws, geom)(im.contiguous())
+
+    def inference_mixed_shapes(self, ims):
+        """A list of HWC uint8 arrays of DIFFERENT shapes: the reference letterboxes each image to the full imgsz x imgsz
+        square (engine/predictor.py:144-156: ``LetterBox(auto=same_shapes and pt)`` - no minimum rectangle when shapes
+        differ) and runs them as one batch.  Images are grouped by shape; each group is copied and letterboxed into its
+        rows of one network-input buffer, one forward runs over the whole batch, the rescale constants are per image."""
+        B = len(ims)
+        dev, model, K, imgsz = self.device, self.model, self.args.max_det, self.args.imgsz
+        stride = int(max(model.stride))
+        groups = {}
+        for i, a in enumerate(ims):
+            if not (isinstance(a, np.ndarray) and a.dtype == np.uint8 and a.ndim == 3 and a.shape[2] == 3):
+                raise ValueError(f"array sources must be uint8 HWC images, got {getattr(a, 'dtype', type(a))} {getattr(a, 'shape', ())}")
+            groups.setdefault(a.shape[:2], []).append(i)
+        S = (imgsz, imgsz) if isinstance(imgsz, int) else tuple(imgsz)
+        net = torch.empty((B, S[0], S[1], 4), dtype=model.compute_dtype, device=dev)
+        rows = [None] * B
+        order = []
+        pos = 0
+        for (hs, ws), idx in groups.items():
+            geom = self.letterbox_geometry((hs, ws), imgsz, stride, auto=False)
+            assert (geom[0], geom[1]) == S
+            H, W, top, left, nh, nw = geom
+            src = torch.from_numpy(np.ascontiguousarray(np.stack([ims[i] for i in idx]))).pin_memory().to(dev, non_blocking=True)
+            out = net[pos:pos + len(idx)]
+            if (nh, nw) == (hs, ws):
+                F.pack_u8(src, model.compute_dtype, top, left, H, W, 114, True, out=out)
+            else:
+                F.letterbox_u8(src, model.compute_dtype, nh, nw, F.resize_tables(hs, ws, nh, nw, dev), top, left, H, W, 114, True, out=out)
+            row = self.scale_back_row(geom, hs, ws) or (0.0, 0.0, 1.0, float(ws), float(hs))
+            for j, i in enumerate(idx):
+                rows[pos + j] = row
+                order.append(i)                   # batch row pos + j holds source image i
+            pos += len(idx)
+        scale = torch.tensor(rows, dtype=torch.float32, device=dev)
+        preds = model.detect(net.permute(0, 3, 1, 2)[:, :3], K, clip=True, scale_back=scale)
+        inv = torch.empty(B, dtype=torch.long)
+        inv[torch.tensor(order)] = torch.arange(B)
+        return preds[inv.to(dev)]
 
     @staticmethod
     def as_u8_batch(source):
-        """list of [h,w,3] uint8 arrays (one shape) / one [B,h,w,3] array / uint8 BHWC host tensor -> host tensor."""
+        """list of [h,w,3] uint8 arrays (one shape) / one [B,h,w,3] array / uint8 BHWC tensor -> one tensor."""
         if isinstance(source, (list, tuple)):
-            if len({tuple(a.shape) for a in source}) != 1:
-                raise NotImplementedError("array sources of different shapes are not batched in this round")
             source = np.stack(source)
         if isinstance(source, np.ndarray):
             if source.ndim == 3:
@@ -359,22 +391,6 @@ class YOLOv10DetectionPredictor:
         if not (torch.is_tensor(source) and source.dtype == torch.uint8 and source.dim() == 4 and source.shape[3] == 3):
             raise ValueError(f"array sources must be uint8 HWC images, got {getattr(source, 'dtype', type(source))} {tuple(getattr(source, 'shape', ()))}")
         return source.contiguous()
-
-    def scale_back(self, preds):
-        """utils/ops.py:89-124 scale_boxes (+ clip_boxes :305-324): network-input coordinates -> original image."""
-        top, left, hs, ws, H, W = self._pad
-        gain = min(H / hs, W / ws)                                        # :110
-        pad_w = round((W - ws * gain) / 2 - 0.1)                          # :111-114
-        pad_h = round((H - hs * gain) / 2 - 0.1)
-        if gain == 1.0 and pad_w == 0 and pad_h == 0:
-            return preds
-        preds = preds.clone()
-        preds[..., [0, 2]] -= pad_w
-        preds[..., [1, 3]] -= pad_h
-        preds[..., :4] /= gain
-        preds[..., [0, 2]] = preds[..., [0, 2]].clamp_(0, ws)
-        preds[..., [1, 3]] = preds[..., [1, 3]].clamp_(0, hs)
-        return preds
 
     def _host_copy(self, preds):
         """Queue ONE device->host copy of the batched detections into a reused pinned buffer (stream order: behind the last
@@ -392,8 +408,8 @@ class YOLOv10DetectionPredictor:
 
     def postprocess(self, preds, img, orig_imgs, host=None):
         """models/yolov10/predict.py:22-38: confidence / class filter, wrap in Results.  preds are already
-        [B,K,6] xyxy (the export-mode contract, head.py:521-523), clipped to the image (scale_boxes is the
-        identity + clip when source and network sizes agree)."""
+        [B,K,6] xyxy (the export-mode contract, head.py:521-523) in original-image coordinates, clipped (scale_boxes is the
+        identity + clip when source and network sizes agree; otherwise it ran inside the tail kernel)."""
         B = preds.shape[0]
         self.last_preds = preds          # batched [B,K,6] on the device (one D2H gives every detection)
         self.last_preds_host = None
@@ -419,38 +435,61 @@ class YOLOv10DetectionPredictor:
             return [Results((orig_imgs, i), f"image{i}.jpg", names, per_img[i], shape) for i in range(B)]
         return [Results(o, f"image{i}.jpg", names, per_img[i], o.shape[:2]) for i, o in enumerate(orig_imgs)]
 
+    @staticmethod
+    def _is_array_source(source):
+        """uint8 HWC images (the LoadPilAndNumpy contract): arrays / lists of arrays, or a uint8 tensor whose LAST dim is 3.
+        A uint8 tensor shaped [B,3,H,W] is a LoadTensor source (0-255 values, normalised by preprocess)."""
+        if isinstance(source, (np.ndarray, list, tuple)):
+            return True
+        return torch.is_tensor(source) and source.dtype == torch.uint8 and source.dim() in (3, 4) and source.shape[-1] == 3
+
     def __call__(self, source):
         if self.model is None:
             raise RuntimeError("setup_model() first")
+        with torch.cuda.device(self.device):          # the C library launches on the current device's streams
+            return self._call(source)
+
+    def _call(self, source):
         self.run_callbacks("on_predict_start")
         profilers = (Profile(self.device), Profile(self.device), Profile(self.device))
         self.batch = source
         self.run_callbacks("on_predict_batch_start")
         with torch.no_grad():
-            if not torch.is_tensor(source) or source.dtype == torch.uint8:
+            if self._is_array_source(source):
+                mixed = isinstance(source, (list, tuple)) and len({tuple(np.shape(a)) for a in source}) > 1
+                if isinstance(source, (list, tuple)) and len(source) == 0:
+                    raise ValueError("empty source")
                 with profilers[0]:
-                    im = self.as_u8_batch(source)
+                    im = None if mixed else self.as_u8_batch(source)
                 with profilers[1]:
-                    preds = self.scale_back(self.inference_from_host_u8(im))
+                    if mixed:
+                        preds = self.inference_mixed_shapes(list(source))
+                    elif im.is_cuda:
+                        preds = self.inference_u8_device(im)
+                    else:
+                        preds = self.inference_from_host_u8(im)
                     host = self._host_copy(preds)
-                orig = list(source) if isinstance(source, (list, tuple)) else [a for a in (source if not torch.is_tensor(source) else source.numpy())]
+                if isinstance(source, (list, tuple)):
+                    orig = list(source)
+                else:
+                    orig = [a for a in (im.cpu().numpy() if torch.is_tensor(source) else (source if source.ndim == 4 else source[None]))]
                 with profilers[2]:
                     self.results = self.postprocess(preds, im, orig, host=host)
-            elif torch.is_tensor(source) and not source.is_cuda and source.dtype == torch.float32 and source.dim() == 4:
-                with profilers[0]:
-                    im = check_tensor_source(source)
-                with profilers[1]:
-                    preds = self.inference_from_host(im)
             else:
-                with profilers[0]:
-                    im = self.preprocess(source)
-                with profilers[1]:
-                    preds = self.inference(im)
-            if torch.is_tensor(source) and source.dtype != torch.uint8:
+                if torch.is_tensor(source) and not source.is_cuda and source.dtype == torch.float32 and source.dim() == 4:
+                    with profilers[0]:
+                        im = check_tensor_source(source)
+                    with profilers[1]:
+                        preds = self.inference_from_host(im)
+                else:
+                    with profilers[0]:
+                        im = self.preprocess(source)
+                    with profilers[1]:
+                        preds = self.inference(im)
                 with profilers[2]:
                     self.results = self.postprocess(preds, im, im)
         self.run_callbacks("on_predict_postprocess_end")
-        n = len(self.results)
+        n = max(len(self.results), 1)
         speed = {"preprocess": profilers[0].dt * 1e3 / n, "inference": profilers[1].dt * 1e3 / n,
                  "postprocess": profilers[2].dt * 1e3 / n}         # per-image averages of the batch, as the reference reports
         for r in self.results:
@@ -492,12 +531,14 @@ class YOLO:
     def load(self, weights):
         """engine/model.py:278-298: transfer matching tensors from a checkpoint / state_dict."""
         checkpoint.load_into(self.model, weights)
+        self.predictor = None            # its captured CUDA graphs point at the old packed weights
         return self
 
     def add_callback(self, event, func):
         self.callbacks[event].append(func)
 
     def load_state_dict(self, sd, strict=True):
+        self.predictor = None            # its captured CUDA graphs point at the old packed weights
         return self.model.load_state_dict(sd, strict=strict)
 
     def fuse(self):
@@ -516,6 +557,13 @@ class YOLO:
             raise NotImplementedError("sources: torch.Tensor [B,3,H,W] in [0,1] (LoadTensor contract) or uint8 HWC BGR arrays "
                                       "(LoadPilAndNumpy contract); files / streams are out of scope")
         args = {**self.overrides, **kwargs}
+        global _HALF_WARNED
+        if "half" not in args and not args.get("fp32") and not _HALF_WARNED:
+            # deliberate deviation from cfg/default.yaml:53 (half: False): documented in INTEGRATION.md, said once
+            import warnings
+            warnings.warn("lpc-yolo_b200: predict() computes in bf16 by default (the reference defaults to fp32, cfg/default.yaml:53); "
+                          "pass half=False (or fp32=True) for the fp32 validation mode, half=True to silence this note", stacklevel=2)
+            _HALF_WARNED = True
         if self.predictor is None or args != getattr(self, "_last_args", None):
             self.predictor = (predictor or YOLOv10DetectionPredictor)(overrides=args, _callbacks=self.callbacks)
             self.predictor.setup_model(self.model)

@@ -235,7 +235,8 @@ def conv2d(x, pc, out=None, res=None, chan_scale=None, rowmax=None):
     use_tc = (pc.w_tc is not None and x.dtype == torch.bfloat16 and xp % 16 == 0 and yp % 16 == 0 and rp % 16 == 0
               and rld % 8 == 0 and L.lpc_conv2d_tc_supported(Cin, pc.cout, pc.k, pc.s, pc.p, xld, yld))
     flops = 2.0 * B * Ho * Wo * pc.cout * Cin * pc.k * pc.k
-    if pc.w_stem is not None and xld == 4 and chan_scale is None and res is None and yld % 8 == 0 and xp % 16 == 0 and yp % 16 == 0:
+    # (fp32 validation mode: the stem goes through conv_direct's fp64-accumulating kernel like every other dense conv)
+    if pc.w_stem is not None and x.dtype == torch.bfloat16 and xld == 4 and chan_scale is None and res is None and yld % 8 == 0 and xp % 16 == 0 and yp % 16 == 0:
         nb = x.element_size() * (B * H * W * 4 + B * Ho * Wo * pc.cout)
         with _prof("stem_conv", flops, nb, f"3->{pc.cout} k3s{pc.s} {H}x{W} B{B}"):
             check(L.lpc_stem_conv(dt_code(x.dtype), xp, B, H, W, _fp(pc.w_stem), _fp(pc.bias), pc.s, pc.cout, yp, yld, pc.act,
@@ -436,8 +437,10 @@ def topk_workspace(B, A, max_det, device):
     return torch.empty((n,), dtype=torch.uint8, device=device)
 
 
-def v10_decode_topk(raw, strides, nc, max_det=300, img_hw=None, return_index=False, ws=None, keys_ready=False):
-    """Fused decode + v10postprocess + xywh2xyxy (+clip): -> dets [B,K,6] fp32 (x1,y1,x2,y2,score,label)."""
+def v10_decode_topk(raw, strides, nc, max_det=300, img_hw=None, return_index=False, ws=None, keys_ready=False, scale_back=None):
+    """Fused decode + v10postprocess + xywh2xyxy (+clip): -> dets [B,K,6] fp32 (x1,y1,x2,y2,score,label).
+    ``scale_back``: optional fp32 device tensor [B,5] = (pad_x, pad_y, gain, orig_w, orig_h) per image: the predictor's
+    ops.scale_boxes + clip_boxes (utils/ops.py:89-124, 305-324) applied in the same kernel."""
     ptrs, ld, B, Ct, H0, W0, st = _raw_args(raw, strides)
     assert Ct == 64 + nc
     A = H0 * W0 + (H0 // 2) * (W0 // 2) + (H0 // 4) * (W0 // 4)
@@ -452,9 +455,13 @@ def v10_decode_topk(raw, strides, nc, max_det=300, img_hw=None, return_index=Fal
     ih, iw = (img_hw if img_hw is not None else (0, 0))
     # algorithmic bytes: raw maps read once + detections written
     nbytes = B * A * (64 + nc) * raw[0].element_size() + B * max_det * 6 * 4
-    def launch(keep=(raw, ws, dets, aidx)):
-        check(L.lpc_v10_decode_topk_keys(dt_code(raw[0].dtype), ptrs[0], ptrs[1], ptrs[2], ld, B, H0, W0, nc, st, max_det, ih, iw,
-                                         _fp(ws), ws_bytes, int(bool(keys_ready)), _fp(dets), _fp(aidx), _stream()), "v10_decode_topk")
+    if scale_back is not None:
+        assert scale_back.is_cuda and scale_back.dtype == torch.float32 and tuple(scale_back.shape) == (B, 5) and scale_back.is_contiguous()
+
+    def launch(keep=(raw, ws, dets, aidx, scale_back)):
+        check(L.lpc_v10_decode_topk_scaled(dt_code(raw[0].dtype), ptrs[0], ptrs[1], ptrs[2], ld, B, H0, W0, nc, st, max_det, ih, iw,
+                                           _fp(ws), ws_bytes, int(bool(keys_ready)), _fp(scale_back), _fp(dets), _fp(aidx), _stream()),
+              "v10_decode_topk")
     if REPLAY is not None:
         REPLAY.append(("v10_decode_topk", launch, 0.0, nbytes, ""))
     with _prof("v10_decode_topk", 0.0, nbytes):

@@ -9,10 +9,14 @@ is a ``YOLOv10DetectionModel`` instance, saved ``.half()``, engine/trainer.py sa
 un-pickles it by importing its own classes; this package does not contain them and must not execute them, so
 the file is read with a *restricted* unpickler:
 
-  * globals from ``torch`` / ``collections`` / ``numpy`` / ``pathlib`` / a safe ``builtins`` subset resolve
-    normally (tensors, ``nn.Conv2d``, ``nn.Sequential``, ``OrderedDict`` ...);
-  * every other global - ``ultralytics.*`` first of all - resolves to an inert placeholder class that only
-    records its constructor arguments and ``__dict__`` state.  No foreign code runs.
+  * an explicit (module, name) allowlist resolves to real objects: the tensor rebuild functions of ``torch._utils``,
+    typed storages / dtypes / ``torch.Size``, the layer CLASSES of ``torch.nn.modules.*``, ``collections.OrderedDict``,
+    numpy's array reconstruction, ``pathlib`` paths and a safe ``builtins`` subset; lookups read
+    ``sys.modules[module].__dict__[name]`` (no import, no attribute traversal) and dotted names are refused, so
+    ``('torch.serialization', 'os.system')``-style protocol-4 gadgets do not resolve;
+  * every other global - ``ultralytics.*`` first of all, but also un-listed ``torch`` functions such as ``torch.load``
+    or ``torch.hub.load`` - resolves to an inert placeholder class that only records its constructor arguments and
+    ``__dict__`` state; un-listed standard-library globals raise.  No foreign code runs.
 
 The parameter / buffer tree of the placeholder graph is then walked exactly like ``nn.Module.state_dict``
 (``_parameters``, persistent ``_buffers``, ``_modules``), the model is rebuilt from the checkpoint's own
@@ -81,21 +85,77 @@ def _dill_load_type(name):
     return _DILL_TYPES.get(name) or _placeholder("dill._dill._load_type", str(name))
 
 
+# Explicit allowlist: (module, name) pairs that may resolve to a real object.  Everything else becomes an inert placeholder.
+# Lookups go through ``sys.modules[module].__dict__[name]`` - no import, no attribute traversal: pickle protocol >= 4
+# resolves DOTTED names by walking attributes (``('torch.serialization', 'os.system')``), which is how a module-prefix
+# pass-list is bypassed; dotted names are refused outright.
+_ALLOWED_FUNCS = {
+    ("torch._utils", "_rebuild_tensor_v2"), ("torch._utils", "_rebuild_tensor"), ("torch._utils", "_rebuild_parameter"),
+    ("torch._utils", "_rebuild_parameter_with_state"),
+    ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"),
+    ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"),
+    ("_codecs", "encode"), ("copyreg", "_reconstructor"),
+}
+_ALLOWED_CLASSES = {
+    ("collections", "OrderedDict"), ("torch", "Size"), ("torch", "device"), ("torch", "Tensor"),
+    ("torch.nn.parameter", "Parameter"), ("numpy", "ndarray"), ("numpy", "dtype"),
+    ("pathlib", "PosixPath"), ("pathlib", "PurePosixPath"), ("pathlib", "PureWindowsPath"), ("pathlib", "Path"),
+    ("datetime", "datetime"), ("datetime", "date"), ("datetime", "timedelta"),
+}
+_PATH_REMAP = {("pathlib", "WindowsPath"): ("pathlib", "PureWindowsPath")}      # checkpoints written on Windows
+
+
+def _resolve_allowed(module, name):
+    """The real object for an allowlisted global, else None."""
+    import sys
+    module, name = _PATH_REMAP.get((module, name), (module, name))
+    mod = sys.modules.get(module)
+    if mod is None:
+        return None
+    obj = mod.__dict__.get(name)
+    if obj is None:
+        return None
+    if (module, name) in _ALLOWED_FUNCS:
+        return obj if callable(obj) else None
+    if (module, name) in _ALLOWED_CLASSES:
+        return obj if isinstance(obj, type) else None
+    if module == "torch":
+        # typed storages (torch.FloatStorage ...), dtype singletons (torch.float16 ...)
+        if isinstance(obj, torch.dtype):
+            return obj
+        if isinstance(obj, type) and name.endswith("Storage") and getattr(obj, "__module__", "").split(".")[0] == "torch":
+            return obj
+        return None
+    if module.startswith("torch.nn.modules."):
+        # layer classes only: un-pickling creates them with __new__ + __dict__ update (or __init__ with plain arguments)
+        if isinstance(obj, type) and issubclass(obj, torch.nn.Module) and getattr(obj, "__module__", "").startswith("torch.nn.modules."):
+            return obj
+        return None
+    return None
+
+
 class RestrictedUnpickler(pickle.Unpickler):
     def find_class(self, module, name):
+        if not isinstance(module, str) or not isinstance(name, str):
+            raise pickle.UnpicklingError("refusing a non-string global in a checkpoint")
         if (module, name) == ("dill._dill", "_load_type"):
             return _dill_load_type
         if module == "builtins":
             if name in _SAFE_BUILTINS:
-                return super().find_class(module, name)
+                return getattr(__import__("builtins"), name)
             raise pickle.UnpicklingError(f"refusing builtins.{name} in a checkpoint")
         root = module.split(".", 1)[0]
-        if root in _PASS_PREFIXES and not module.startswith("torch.utils.cpp_extension"):
-            try:
-                return super().find_class(module, name)
-            except (ImportError, AttributeError):
-                return _placeholder(module, name)      # e.g. a torch class that moved between versions
-        return _placeholder(module, name)
+        if "." in name:
+            if root in _PASS_PREFIXES or root == "builtins":
+                raise pickle.UnpicklingError(f"refusing dotted global {module}:{name} in a checkpoint")
+            return _placeholder(module, name)
+        obj = _resolve_allowed(module, name)
+        if obj is not None:
+            return obj
+        if root in _PASS_PREFIXES and root not in ("torch", "numpy"):
+            # a standard-library global that is not on the allowlist has no business in a weights file
+            raise pickle.UnpicklingError(f"refusing {module}.{name} in a checkpoint")
+        return _placeholder(module, name)      # ultralytics.*, un-listed torch / numpy names: inert
 
 
 class _PickleModule:

@@ -7,6 +7,20 @@ from ..._lib import ACT_MISH, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SILU, LpcErro
 
 COMPUTE_DTYPES = (torch.bfloat16, torch.float32)
 
+# Bumped whenever any packed-weight cache is dropped (load_state_dict, .to(), invalidate()).  Captured CUDA graphs hold raw
+# pointers to packed weights, so the engine keys its graph cache on this counter (engine.py ``_graph_cache``).
+_EPOCH = [0]
+
+
+def weights_epoch():
+    return _EPOCH[0]
+
+
+def _bump(cache):
+    if cache:
+        _EPOCH[0] += 1
+    cache.clear()
+
 
 def act_code(act):
     """Activation enum from the module's ACTUAL .act object (SURVEY.md finding 1)."""
@@ -31,16 +45,16 @@ class LpcModule(nn.Module):
     def __init__(self):
         super().__init__()
         object.__setattr__(self, "_pcache", {})
-        self.register_load_state_dict_post_hook(lambda mod, _inc: mod._pcache.clear())
+        self.register_load_state_dict_post_hook(lambda mod, _inc: _bump(mod._pcache))
 
     def _apply(self, fn, recurse=True):
-        self._pcache.clear()
+        _bump(self._pcache)
         return super()._apply(fn, recurse)
 
     def invalidate(self):
         for m in self.modules():
             if isinstance(m, LpcModule):
-                m._pcache.clear()
+                _bump(m._pcache)
 
     def _packed(self, x, builder):
         key = (x.dtype, x.device)

@@ -167,6 +167,11 @@ class BaseModel(LpcModule):
         """tasks.py:83-111.  ``tail``: optional callable applied instead of the detect head's forward."""
         if not x.is_cuda:
             raise F.LpcError("lpc-yolo_b200 runs on CUDA tensors only (no CPU fallback)")
+        if torch.cuda.current_device() != x.device.index:
+            # the C library launches on the CURRENT device's streams: a model living on cuda:1 driven from a process whose
+            # current device is cuda:0 would launch there with device-1 pointers (ADVICE r1)
+            with torch.cuda.device(x.device):
+                return self._predict_once(x, tail)
         dest, live, fold = self._plan()
         if x.dtype not in (torch.bfloat16, torch.float32) or not F.is_nhwc_view(x) or x.dtype != self.compute_dtype:
             x = F.pack_input(x.float().contiguous(), self.compute_dtype) if x.shape[1] <= 4 else F.as_act(x, self.compute_dtype)
@@ -254,7 +259,8 @@ class DetectionModel(BaseModel):
 class YOLOv10DetectionModel(DetectionModel):
     """tasks.py:639-641 (inference side)."""
 
-    def detect(self, x, max_det=300, clip=True):
-        """Fused engine path: images -> [B, max_det, 6] detections (xyxy, score, label), never building y."""
+    def detect(self, x, max_det=300, clip=True, scale_back=None):
+        """Fused engine path: images -> [B, max_det, 6] detections (xyxy, score, label), never building y.
+        ``scale_back``: optional [B,5] (pad_x, pad_y, gain, orig_w, orig_h) - boxes come back in original-image coordinates."""
         hw = tuple(x.shape[2:]) if clip else None
-        return self._predict_once(x, tail=lambda m, feats: m.detections(feats, max_det, hw))
+        return self._predict_once(x, tail=lambda m, feats: m.detections(feats, max_det, hw, scale_back))

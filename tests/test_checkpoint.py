@@ -65,6 +65,43 @@ def test_placeholders_keep_foreign_code_inert(ckpt_mod, tmp_path):
         ckpt_mod.torch_safe_load(str(tmp_path / "missing.pt"))
 
 
+def _proto4_global(module, name, arg=None):
+    """A protocol-4 pickle: STACK_GLOBAL (module, name) then REDUCE with one argument (or no argument)."""
+    import io
+    import pickletools  # noqa: F401  (documentation of the opcodes used below)
+    def short_unicode(s):
+        b = s.encode()
+        return b"\x8c" + bytes([len(b)]) + b
+    body = b"\x80\x04" + short_unicode(module) + short_unicode(name) + b"\x93"       # PROTO 4, STACK_GLOBAL
+    if arg is None:
+        body += b")R."                                                                   # EMPTY_TUPLE REDUCE STOP
+    else:
+        body += short_unicode(arg) + b"\x85R."                                           # TUPLE1 REDUCE STOP
+    return io.BytesIO(body)
+
+
+def test_dotted_and_unlisted_globals_do_not_resolve(ckpt_mod):
+    """protocol >= 4 resolves dotted names by attribute traversal, so a module-prefix pass-list lets
+    ('torch.serialization', 'os.getpid') or ('collections', '_sys.getrecursionlimit') execute.  Dotted names under the
+    trusted roots are refused, un-listed torch functions (torch.load, torch.hub.load ...) are inert placeholders, un-listed
+    standard-library globals raise."""
+    U = ckpt_mod.RestrictedUnpickler
+    for mod, name in (("torch.serialization", "os.getpid"), ("collections", "_sys.getrecursionlimit"),
+                      ("torch", "serialization.os.getpid"), ("functools", "partial"), ("copyreg", "add_extension"),
+                      ("builtins", "getattr"), ("builtins", "__import__")):
+        with pytest.raises(pickle.UnpicklingError):
+            U(_proto4_global(mod, name)).load()
+    for mod, name in (("torch", "load"), ("torch.hub", "load"), ("torch.utils.collect_env", "run"), ("torch.serialization", "load"),
+                      ("os", "system"), ("subprocess", "check_output"), ("numpy", "load"), ("torch.nn.modules.module", "register_module_forward_hook")):
+        obj = U(_proto4_global(mod, name, "echo pwned > /tmp/lpc_pwned4")).load()
+        assert isinstance(obj, ckpt_mod.Placeholder), (mod, name, obj)
+    assert not os.path.exists("/tmp/lpc_pwned4")
+    # the allowlist still resolves what real checkpoints need
+    assert U(_proto4_global("collections", "OrderedDict")).load() == {}
+    assert isinstance(U(_proto4_global("torch.nn.modules.activation", "SiLU")).load(), torch.nn.SiLU)
+    assert U(_proto4_global("torch", "float16", None).__class__(b"\x80\x04\x8c\x05torch\x8c\x07float16\x93.")).load() is torch.float16
+
+
 def test_oracle_on_ingested_weights_matches_reference_predict(pkg, oracle):
     """The checkpoint's tensors + the oracle's restatement == the reference's own predict() on that file."""
     g = np.load(NPZ)

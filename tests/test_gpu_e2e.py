@@ -1,8 +1,7 @@
 """GPU parity tests, tiers T4-T6: whole network vs the CPU oracle and the reference-generated fixtures.
 
-  T4 raw head / decoded y:  fp32 mode  max|d|/max|ref| <= 1e-5 ... measured against an fp64 run of the oracle
-                            (the reference itself sits 3e-6 from fp64); we allow 2e-5 on
-                            the deepest models where fp32 summation order alone moves the reference by 7e-5.
+  T4 raw head / decoded y:  fp32 mode  max|d|/max|ref| <= 1e-5 on all seven YAMLs, measured against an fp64 run of the
+                            oracle, and never further from fp64 than the reference's own fp32 arithmetic (3e-6 ... 5e-5).
                             bf16 mode  l2-rel <= 2.5e-2, max-normalised <= 0.1 (reference's own bf16 drift: 9.7e-3 / 7.1e-2)
   T5 detections [B,300,6]:  fp32 mode: >= 99 % matched (class equal, box within 1e-2 px, score within 1e-5);
                             bf16: match rate reported, >= 60 % required at score gaps above bf16 resolution
@@ -43,10 +42,11 @@ def _cat(raws):
 
 @pytest.mark.parametrize("name", ALL)
 def test_fp32_mode_raw_and_y(pkg, oracle, name):
-    """fp32 validation mode against an fp64 run of the oracle.  Bar: 1e-5 (north_star) wherever the reference's own
-    fp32 arithmetic is within 1e-5 of fp64 (n, s, LPC); the deeper models amplify fp32 rounding (the reference itself
-    is 1.5e-5 ... 5e-5 from fp64 on these weights, profiles/r01_numerics.md), so there the bar is 3x the reference's
-    own fp32-vs-fp64 distance measured in this test."""
+    """fp32 validation mode against an fp64 run of the oracle.  Bar (north_star): 1e-5 max-normalised on the raw head maps
+    and on the decoded y, for ALL seven YAMLs, and no further from fp64 than the reference's own fp32 arithmetic is on the
+    same weights (the oracle's fp32 run: 3e-6 ... 5e-5).  The validation kernels carry products, sums, bias, activation and
+    residual in fp64 and round to fp32 once per layer (conv_direct.cu), so what remains is the storage rounding of the
+    activations propagated through the network."""
     om, pm = _pair(pkg, oracle, name)
     pm.compute_dtype = torch.float32
     x = oracle.synth_input(2, 160)
@@ -61,10 +61,8 @@ def test_fp32_mode_raw_and_y(pkg, oracle, name):
     e_raw, _ = _norm_err(_cat(raw).double(), _cat(raw64))
     e_y, _ = _norm_err(y.double(), y64)
     print(f"{name}: fp32 raw {e_raw:.2e} (reference-equivalent fp32: {noise_raw:.2e}), y {e_y:.2e} ({noise_y:.2e})")
-    assert e_raw < max(1e-5, 3 * noise_raw), f"{name} raw: {e_raw:.2e} vs reference noise {noise_raw:.2e}"
-    assert e_y < max(1e-5, 6 * noise_y), f"{name} y: {e_y:.2e} vs reference noise {noise_y:.2e}"
-    if name in ("yolov10n", "yolov10s", "lpc"):
-        assert e_raw < 1e-5 and e_y < 1e-5
+    assert e_raw < 1e-5 and e_y < 1e-5, f"{name}: fp32 validation mode raw {e_raw:.2e} / y {e_y:.2e} vs the 1e-5 bar"
+    assert e_raw <= noise_raw and e_y <= max(noise_y, 2e-6), f"{name}: further from fp64 than the reference's own fp32 run ({noise_raw:.2e} / {noise_y:.2e})"
     # and against the reference's own output stored in the fixture (first image, same seed)
     g = np.load(os.path.join(GOLDEN, f"{name}.npz"))
     ref = torch.from_numpy(g["y_small"])

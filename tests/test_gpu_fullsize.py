@@ -1,5 +1,6 @@
-"""GPU parity at BASELINE.json's full size (LPC YAML, batch 64, 640x640, bf16) through size-independent properties -
-the oracle cannot run this size in seconds, these can:
+"""GPU parity at BASELINE.json's full size (LPC YAML, batch 64, 640x640, bf16) through size-independent properties
+(the direct oracle comparison at this size - three images of the batch, all 64 tails - is
+tests/test_gpu_baseline_sizes.py::test_config2_lpc_b64_640_bf16):
 
   * determinism: CUDA-graph replay == eager launch sequence, bit for bit (also what caught a wrong key index in the fused
     class-branch epilogue during development);

@@ -253,9 +253,11 @@ def test_scdown_sppf(B, oracle, dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("c1,hw", [(256, 10), (576, 5), (256, 20), (640, 9)])
+@pytest.mark.parametrize("c1,hw", [(256, 10), (576, 5), (256, 20), (640, 9), (512, 30), (576, 30), (640, 40), (576, 40)])
 def test_psa(B, oracle, dtype, c1, hw):
-    """PSA incl. the fused attention kernel: heads 2 (kd32/hd64), yolov10m's kd36/hd72, N not a multiple of 64."""
+    """PSA incl. the fused attention kernel: heads 2 (kd32/hd64), yolov10m's kd36/hd72, N not a multiple of 64, and the
+    token counts of BASELINE configs 4 / 5: N = 900 (yolov10b @960: c1 512, 4 heads) and N = 1600 (yolov10x @1280: c1 640,
+    5 heads), each also with the kd36/hd72 geometry (reference Attention.forward, block.py:783-795)."""
     mod = _randomize(B.PSA(c1, c1), 15)
     x = _x((2, c1, hw, hw), dtype)
     _cmp(_run(mod, x, dtype), oracle._psa(oracle._Ctx(_sd(mod, dtype)), x, "m"), dtype, f"PSA{c1}", block=True)

@@ -197,3 +197,34 @@ def test_conv_rowmax_keys_bit_exact(pkg, Fn):
     want = torch.where(u < 0, ~u, u ^ torch.tensor(-2 ** 31, dtype=torch.int32))    # fkey(): order-preserving uint32 of the float
     assert torch.equal(keys, want)
     assert int(ws[: B * A * 4].view(torch.int32).view(B, A)[:, :off].abs().sum()) == 0   # nothing written outside the slot
+
+
+def test_tal_and_ops_function_api(pkg, oracle):
+    """utils/tal.py make_anchors / dist2bbox and utils/ops.py xywh2xyxy / clip_boxes / scale_boxes (kernel-backed function
+    API) against the oracle's restatements of tal.py:294-319 and ops.py:89-124, 305-324, 402-421."""
+    tal = importlib.import_module("lpc-yolo_b200.utils.tal")
+    ops = importlib.import_module("lpc-yolo_b200.utils.ops")
+    feats = [torch.empty(2, 8, h, w, device="cuda") for h, w in ((12, 20), (6, 10), (3, 5))]
+    pts, st = tal.make_anchors(feats, [8.0, 16.0, 32.0], 0.5)
+    opts, ost = oracle.make_anchors([(12, 20), (6, 10), (3, 5)], [8.0, 16.0, 32.0])
+    assert torch.equal(pts.cpu(), opts) and torch.equal(st.cpu(), ost)
+    g = torch.Generator().manual_seed(4)
+    A = pts.shape[0]
+    dist = torch.rand(2, 4, A, generator=g) * 6
+    for xywh in (True, False):
+        got = tal.dist2bbox(dist.cuda(), pts.t().unsqueeze(0), xywh=xywh, dim=1).cpu()           # the head's call (head.py:97-101)
+        lt, rb = dist.split([2, 2], 1)
+        x1y1, x2y2 = opts.t().unsqueeze(0) - lt, opts.t().unsqueeze(0) + rb
+        want = torch.cat(((x1y1 + x2y2) / 2, x2y2 - x1y1), 1) if xywh else torch.cat((x1y1, x2y2), 1)
+        assert torch.equal(got, want)
+    b = torch.rand(3, 50, 4, generator=g) * 300
+    assert torch.equal(ops.xywh2xyxy(b.cuda()).cpu(), oracle.xywh2xyxy(b))
+    want = oracle.scale_boxes((192, 256), b.clone(), (150, 200))
+    assert torch.allclose(ops.scale_boxes((192, 256), b.clone().cuda(), (150, 200)).cpu(), want, atol=1e-4)
+    rows = torch.cat((b, torch.rand(3, 50, 2, generator=g)), -1)                                   # [.., 6] rows: only the box moves
+    got = rows.clone().cuda()
+    ops.clip_boxes(got, (100, 120))
+    assert torch.equal(got[..., 4:].cpu(), rows[..., 4:])
+    assert torch.equal(got[..., 0].cpu(), rows[..., 0].clamp(0, 120)) and torch.equal(got[..., 3].cpu(), rows[..., 3].clamp(0, 100))
+    with pytest.raises(pkg.LpcError):
+        tal.dist2bbox(dist, pts.t().unsqueeze(0).cpu(), dim=1)                                     # CPU tensors: no fallback
