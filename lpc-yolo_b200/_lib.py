@@ -67,20 +67,39 @@ class LpcError(RuntimeError):
     pass
 
 
-def build(force=False):
+def _build_mod():
     import importlib.util
     spec = importlib.util.spec_from_file_location("_lpc_build", os.path.join(_HERE, "csrc", "build.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    return mod.build(force=force)
+    return mod
+
+
+def build(force=False):
+    return _build_mod().build(force=force)
 
 
 def lib():
-    """Load (building first if sources changed and nvcc exists) and return the ctypes handle."""
+    """Load the library and return the ctypes handle.  The binary must correspond to the sources in the tree: with nvcc
+    present ``build()`` runs first (a sha1 stamp over the sources makes it a no-op when nothing changed); without nvcc the
+    shipped binary's stamp is compared with the sources and a mismatch raises (LPC_ALLOW_STALE=1 downgrades it to a warning)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH) or os.environ.get("LPC_REBUILD"):
-            build()
+        if not os.environ.get("LPC_LIB"):
+            bm = _build_mod()
+            import shutil
+            if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+                bm.build(force=bool(os.environ.get("LPC_REBUILD")))
+            elif not os.path.exists(LIB_PATH):
+                raise LpcError(f"{LIB_PATH} is missing and there is no nvcc to build it (no fallback path exists)")
+            else:
+                stamp = open(bm.STAMP).read().strip() if os.path.exists(bm.STAMP) else None
+                if stamp != bm._digest():
+                    msg = f"{LIB_PATH} was not built from the sources in this tree (stamp {stamp} != {bm._digest()})"
+                    if not os.environ.get("LPC_ALLOW_STALE"):
+                        raise LpcError(msg + "; rebuild it or set LPC_ALLOW_STALE=1")
+                    import warnings
+                    warnings.warn(msg)
         try:
             handle = C.CDLL(LIB_PATH)
         except OSError as e:  # loud failure: there is no fallback path

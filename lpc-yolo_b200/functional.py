@@ -264,7 +264,12 @@ def conv2d(x, pc, out=None, res=None, chan_scale=None, rowmax=None):
             check(L.lpc_conv2d_tc(xp, xld, B, H, W, Cin, _fp(pc.w_tc), _fp(pc.bias), pc.k, pc.s, pc.p, pc.cout, yp, yld,
                                   pc.act, _fp(chan_scale), rp or None, rld, _stream()), "conv2d_tc")
         if REPLAY is not None:
-            REPLAY.append(("conv2d_tc", launch, flops, nbytes, tag))
+            plain = None
+            if rm is not None:        # the same launch without the fused stage-1 keys (bench.py measures what they cost)
+                def plain(keep=(x, out, res, chan_scale, pc)):
+                    check(L.lpc_conv2d_tc(xp, xld, B, H, W, Cin, _fp(pc.w_tc), _fp(pc.bias), pc.k, pc.s, pc.p, pc.cout, yp, yld,
+                                          pc.act, _fp(chan_scale), rp or None, rld, _stream()), "conv2d_tc")
+            REPLAY.append(("conv2d_tc", launch, flops, nbytes, tag, plain))
         with _prof("conv2d_tc", flops, nbytes, tag):
             launch()
     else:

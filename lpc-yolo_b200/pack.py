@@ -4,7 +4,8 @@ Folding follows ``fuse_conv_and_bn`` (reference utils/torch_utils.py:171-198):  
 b' = beta - g*mean/sqrt(var+eps) (+ scaled conv bias), eps = 1e-3 (torch_utils.py:342-352) - but it is applied to
 EVERY conv+BN pair, including the Mish ``block.Conv`` ones the reference's ``fuse()`` misses (SURVEY.md finding 2),
 and RepVGGDW's 3x3 branch is merged into the 7x7 as ``RepVGGDW.fuse`` does (block.py:714-733).  The algebra is done
-in fp64 and rounded once.
+in fp64 ON THE HOST and rounded once; the device only receives the finished blobs (plain H2D copies: a profiler window
+around the first forward sees the network's own kernels, not hundreds of ATen elementwise launches).
 """
 import torch
 
@@ -14,14 +15,14 @@ from ._lib import ACT_NONE
 
 def fold_bn(conv_w, conv_b, bn):
     """-> (W' fp64 [Cout,Cin/g,kh,kw], b' fp64 [Cout]). ``bn`` may be None (plain nn.Conv2d)."""
-    w = conv_w.detach().double()
+    w = conv_w.detach().cpu().double()
     cout = w.shape[0]
-    b = conv_b.detach().double() if conv_b is not None else torch.zeros(cout, dtype=torch.float64, device=w.device)
+    b = conv_b.detach().cpu().double() if conv_b is not None else torch.zeros(cout, dtype=torch.float64)
     if bn is None:
         return w, b
-    scale = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+    scale = bn.weight.detach().cpu().double() / torch.sqrt(bn.running_var.detach().cpu().double() + bn.eps)
     w = w * scale.view(-1, 1, 1, 1)
-    b = b * scale + bn.bias.detach().double() - bn.running_mean.detach().double() * scale
+    b = b * scale + bn.bias.detach().cpu().double() - bn.running_mean.detach().cpu().double() * scale
     return w, b
 
 
@@ -30,23 +31,24 @@ class PackedConv:
 
     def __init__(self, w, b, k, s, p, act, dtype, device, out_perm=None, s2d_fold=False):
         # w: [Cout, Cin, k, k] fp64 folded; optional output-channel permutation (PSA qkv re-ordering)
+        w, b = w.cpu(), b.cpu()
         if out_perm is not None:
-            w, b = w[out_perm], b[out_perm]
+            w, b = w[out_perm.cpu()], b[out_perm.cpu()]
         self.cout, self.cin = w.shape[0], w.shape[1]
         self.k, self.s, self.p, self.act = k, s, p, act
         w32 = w.float()
-        self.bias = b.float().to(device).contiguous()
-        self.w_direct = w32.permute(2, 3, 1, 0).reshape(k * k, self.cin, self.cout).to(device=device, dtype=dtype).contiguous()
+        self.bias = b.float().contiguous().to(device)
+        self.w_direct = w32.permute(2, 3, 1, 0).reshape(k * k, self.cin, self.cout).contiguous().to(dtype).to(device)
         self.w_tc = None
         self.w_stem = None
         if self.cin == 3 and k == 3 and p == 1 and s in (1, 2) and self.cout % 8 == 0 and self.cout <= 96:
-            self.w_stem = w32.permute(2, 3, 1, 0).reshape(27, self.cout).to(device).contiguous()
+            self.w_stem = w32.permute(2, 3, 1, 0).reshape(27, self.cout).contiguous().to(device)
         if dtype == torch.bfloat16 and self.cin % 16 == 0 and self.cout % 16 == 0 and k in (1, 2, 3):
             kpad = _lib.lib().lpc_conv2d_tc_kpad(self.cin, k)
             if kpad > 0:
                 wt = torch.zeros((self.cout, kpad), dtype=torch.float32)
-                wt[:, : k * k * self.cin] = w32.permute(0, 2, 3, 1).reshape(self.cout, k * k * self.cin).cpu()
-                self.w_tc = wt.to(device=device, dtype=torch.bfloat16).contiguous()
+                wt[:, : k * k * self.cin] = w32.permute(0, 2, 3, 1).reshape(self.cout, k * k * self.cin)
+                self.w_tc = wt.to(torch.bfloat16).contiguous().to(device)
 
 
 class PackedDW:
@@ -55,8 +57,8 @@ class PackedDW:
     def __init__(self, w, b, k, s, p, d, act, device):
         c = w.shape[0]
         self.c, self.k, self.s, self.p, self.d, self.act = c, k, s, p, d, act
-        self.w = w.float()[:, 0].permute(1, 2, 0).reshape(k * k, c).to(device).contiguous()
-        self.bias = b.float().to(device).contiguous() if b is not None else None
+        self.w = w.cpu().float()[:, 0].permute(1, 2, 0).reshape(k * k, c).contiguous().to(device)
+        self.bias = b.cpu().float().contiguous().to(device) if b is not None else None
 
 
 def pack_conv_module(m, dtype, device, act, out_perm=None):
