@@ -148,8 +148,8 @@ def cpu_reference_leg(model_key, size, batch, reps, warm=1, budget_s=None):
         yolo.model.eval()
         kind = "reference"
 
-        def one(x):
-            return yolo.predict(x, conf=0.25, verbose=False)
+        def one(x):      # device="cpu": on a GPU box the reference's select_device would otherwise pick cuda:0 (torch eager / cuDNN)
+            return yolo.predict(x, conf=0.25, verbose=False, device="cpu")
     else:
         kind = "port"
 

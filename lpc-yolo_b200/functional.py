@@ -84,11 +84,13 @@ def fork_join(jobs, device):
         for j in jobs:
             j()
         return
-    key = (device.index if device.index is not None else torch.cuda.current_device())
+    main = torch.cuda.current_stream(device)
+    # one pool per (device, forking stream): a nested fork (the head's branches inside a batch-half running on a side stream)
+    # must not be handed the stream it is running on
+    key = (device.index if device.index is not None else torch.cuda.current_device(), main.cuda_stream)
     pool = _SIDE_STREAMS.setdefault(key, [])
     while len(pool) < len(jobs) - 1:
         pool.append(torch.cuda.Stream(device=device))
-    main = torch.cuda.current_stream(device)
     fork = torch.cuda.Event()
     fork.record(main)
     for j, st in zip(jobs[1:], pool):
@@ -442,7 +444,7 @@ def topk_workspace(B, A, max_det, device):
     return torch.empty((n,), dtype=torch.uint8, device=device)
 
 
-def v10_decode_topk(raw, strides, nc, max_det=300, img_hw=None, return_index=False, ws=None, keys_ready=False, scale_back=None):
+def v10_decode_topk(raw, strides, nc, max_det=300, img_hw=None, return_index=False, ws=None, keys_ready=False, scale_back=None, out=None):
     """Fused decode + v10postprocess + xywh2xyxy (+clip): -> dets [B,K,6] fp32 (x1,y1,x2,y2,score,label).
     ``scale_back``: optional fp32 device tensor [B,5] = (pad_x, pad_y, gain, orig_w, orig_h) per image: the predictor's
     ops.scale_boxes + clip_boxes (utils/ops.py:89-124, 305-324) applied in the same kernel."""
@@ -455,7 +457,8 @@ def v10_decode_topk(raw, strides, nc, max_det=300, img_hw=None, return_index=Fal
     if ws is None:
         ws, keys_ready = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev), False
     assert ws.numel() >= ws_bytes
-    dets = torch.empty((B, max_det, 6), dtype=torch.float32, device=dev)
+    dets = out if out is not None else torch.empty((B, max_det, 6), dtype=torch.float32, device=dev)
+    assert tuple(dets.shape) == (B, max_det, 6) and dets.dtype == torch.float32 and dets.is_contiguous()
     aidx = torch.empty((B, max_det), dtype=torch.int32, device=dev) if return_index else None
     ih, iw = (img_hw if img_hw is not None else (0, 0))
     # algorithmic bytes: raw maps read once + detections written

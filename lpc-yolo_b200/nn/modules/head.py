@@ -161,7 +161,7 @@ class v10Detect(Detect):
             return torch.cat(((xy1 + xy2) / 2, xy2 - xy1, d[..., 4:]), -1)
         return {"one2many": one2many, "one2one": self.inference(one2one)}
 
-    def detections(self, x, max_det=None, img_hw=None, scale_back=None):
+    def detections(self, x, max_det=None, img_hw=None, scale_back=None, out=None):
         """Engine fast path: raw one2one maps -> fused decode + top-k (+clip, + rescale to the original image when
         ``scale_back`` [B,5] is given) -> [B,K,6]; y is never built."""
         K = max_det or self.max_det
@@ -170,7 +170,7 @@ class v10Detect(Detect):
         keys = {"ws": F.topk_workspace(B, A, K, x[0].device), "A": A}
         one2one = self.forward_feat(x, self.one2one_cv2, self.one2one_cv3, keys=keys)
         return F.v10_decode_topk(one2one, [float(s) for s in self.stride], self.nc, K, img_hw, ws=keys["ws"], keys_ready=keys.get("ok", False),
-                                 scale_back=scale_back)
+                                 scale_back=scale_back, out=out)
 
     def bias_init(self):
         super().bias_init()

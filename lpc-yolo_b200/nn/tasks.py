@@ -259,8 +259,27 @@ class DetectionModel(BaseModel):
 class YOLOv10DetectionModel(DetectionModel):
     """tasks.py:639-641 (inference side)."""
 
-    def detect(self, x, max_det=300, clip=True, scale_back=None):
+    batch_streams = int(os.environ.get("LPC_BATCH_STREAMS", "1"))
+
+    def detect(self, x, max_det=300, clip=True, scale_back=None, streams=None):
         """Fused engine path: images -> [B, max_det, 6] detections (xyxy, score, label), never building y.
-        ``scale_back``: optional [B,5] (pad_x, pad_y, gain, orig_w, orig_h) - boxes come back in original-image coordinates."""
+        ``scale_back``: optional [B,5] (pad_x, pad_y, gain, orig_w, orig_h) - boxes come back in original-image coordinates.
+        ``streams`` > 1: the batch is cut into that many contiguous parts that run the whole network as independent chains on
+        parallel streams (parallel branches of a captured graph): images are independent, and while one chain sits in the
+        fixed latency of a launch boundary (pipeline fill, last-tile epilogue, dependency resolution) the other chain's
+        kernel has the SMs."""
         hw = tuple(x.shape[2:]) if clip else None
-        return self._predict_once(x, tail=lambda m, feats: m.detections(feats, max_det, hw, scale_back))
+        n = streams if streams is not None else self.batch_streams
+        B = x.shape[0]
+        if n <= 1 or B < 2 * n:
+            return self._predict_once(x, tail=lambda m, feats: m.detections(feats, max_det, hw, scale_back))
+        if x.dtype != self.compute_dtype or not F.is_nhwc_view(x):
+            x = F.pack_input(x.float().contiguous(), self.compute_dtype) if x.shape[1] <= 4 else F.as_act(x, self.compute_dtype)
+        out = torch.empty((B, max_det, 6), dtype=torch.float32, device=x.device)
+        bounds = [(B * i // n, B * (i + 1) // n) for i in range(n)]
+
+        def part(lo, hi):
+            sb = scale_back[lo:hi] if scale_back is not None else None
+            self._predict_once(x[lo:hi], tail=lambda m, feats: m.detections(feats, max_det, hw, sb, out=out[lo:hi]))
+        F.fork_join([(lambda lo=lo, hi=hi: part(lo, hi)) for lo, hi in bounds], x.device)
+        return out
