@@ -93,6 +93,19 @@ int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W, int Cin, 
 /* 1 if lpc_conv2d_tc accepts this shape, else 0. */
 int lpc_conv2d_tc_supported(int Cin, int Cout, int k, int stride, int pad, int x_ld, int y_ld);
 
+/* Depthwise 3x3 (stride 1, pad 1, bias, dw_act) -> pointwise 1x1 (C1, bias, act1) [-> pointwise 1x1 (C2, bias, act2)] as
+ * ONE tcgen05 kernel: the depthwise result is written straight into the shared-memory A operand of the 1x1 GEMM, and
+ * the first GEMM's activated output into the A operand of the second; nothing between x and y touches HBM.  Replaces
+ * the class-branch chain of v10Detect (nn/modules/head.py:504-505, three launches -> one, five -> two per level) and the
+ * dw -> 1x1 links of CIB (block.py:744-750).  bf16 NHWC; dw_w [9][Cin] fp32; w1 [C1][pad64(Cin)], w2 [C2][pad64(C1)]
+ * bf16 (lpc_conv2d_tc's 1x1 packing); C1, C2 multiples of 16 and <= 256, C2 = 0 / w2 = NULL for a single pointwise
+ * stage.  rowmax_keys: as lpc_conv2d_tc_rowmax (per-pixel key of max_c of the final outputs), or NULL.
+ * lpc_dwpw_tc_supported: 1 if the shape (incl. its shared-memory plan) is taken. */
+int lpc_dwpw_tc_supported(int Cin, int C1, int C2, int x_ld, int y_ld);
+int lpc_dwpw_tc(const void* x, int x_ld, int B, int H, int W, int Cin, const float* dw_w, const float* dw_bias, int dw_act,
+                const void* w1, const float* b1, int C1, int act1, const void* w2, const float* b2, int C2, int act2,
+                void* y, int y_ld, unsigned int* rowmax_keys, long long rowmax_img_stride, int rowmax_offset, void* stream);
+
 /* Stem: Conv(3, Cout, 3, stride, pad 1) on an NHWC input whose pixel pitch is exactly 4 (lpc_pack_input's Cpad=4).
  * bf16, stride 2, even W: tcgen05 (stem_tc.cu - the 3x3 windows of an 8x16 output tile arrive as one 3-D TMA box, builder
  * warps turn them into swizzled K-major im2col rows, K = 36 + 2 bias slots -> 48, three UMMAs per 128 pixels); other

@@ -556,6 +556,32 @@ decode_kernel(TailSrc s, int B, float* __restrict__ y) {
   const int cell = a - s.a_start[l];
   const int cy = cell / s.lvl_w[l], cx = cell - cy * s.lvl_w[l];
   const T* row = anchor_row<T>(s, b, a);
+  float* yo = y + (long long)b * (4 + s.nc) * s.A + a;
+  if (Precise<T>::value) {
+    // fp32 validation mode: softmax, expectation, box arithmetic and sigmoid in fp64, one rounding per output, so y adds
+    // nothing to the distance the raw maps already have from an fp64 run (tests/test_gpu_e2e.py::test_fp32_mode_raw_and_y)
+    double d[4];
+#pragma unroll 1
+    for (int side = 0; side < 4; ++side) {
+      double v[REG_MAX], mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < REG_MAX; ++i) { v[i] = (double)to_f(row[side * REG_MAX + i]); mx = fmax(mx, v[i]); }
+      double se = 0.0, acc = 0.0;
+#pragma unroll
+      for (int i = 0; i < REG_MAX; ++i) { v[i] = exp(v[i] - mx); se += v[i]; }
+#pragma unroll
+      for (int i = 0; i < REG_MAX; ++i) acc += (v[i] / se) * (double)i;
+      d[side] = acc;
+    }
+    const double ax = (double)cx + 0.5, ay = (double)cy + 0.5, st = (double)s.stride[l];
+    const double x1 = ax - d[0], y1 = ay - d[1], x2 = ax + d[2], y2 = ay + d[3];
+    yo[0] = (float)((x1 + x2) / 2 * st);
+    yo[(long long)s.A] = (float)((y1 + y2) / 2 * st);
+    yo[2ll * s.A] = (float)((x2 - x1) * st);
+    yo[3ll * s.A] = (float)((y2 - y1) * st);
+    for (int c = 0; c < s.nc; ++c) yo[(long long)(4 + c) * s.A] = (float)(1.0 / (1.0 + exp(-(double)to_f(row[4 * REG_MAX + c]))));
+    return;
+  }
   float d[4];
 #pragma unroll
   for (int side = 0; side < 4; ++side) {
@@ -572,7 +598,6 @@ decode_kernel(TailSrc s, int B, float* __restrict__ y) {
   }
   const float ax = (float)cx + 0.5f, ay = (float)cy + 0.5f, st = s.stride[l];
   const float x1 = ax - d[0], y1 = ay - d[1], x2 = ax + d[2], y2 = ay + d[3];
-  float* yo = y + (long long)b * (4 + s.nc) * s.A + a;
   yo[0] = (x1 + x2) / 2 * st;
   yo[(long long)s.A] = (y1 + y2) / 2 * st;
   yo[2ll * s.A] = (x2 - x1) * st;

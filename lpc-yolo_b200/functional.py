@@ -301,6 +301,58 @@ def dwconv2d(x, pd, out=None, res=None):
     return out
 
 
+FUSE_DWPW = os.environ.get("LPC_FUSE_DWPW", "1") != "0"
+
+
+def dwpw_supported(x, pd, pc1, pc2=None, out_ld=None):
+    """Can depthwise ``pd`` -> pointwise ``pc1`` [-> pointwise ``pc2``] on x run as one lpc_dwpw_tc launch?"""
+    if not FUSE_DWPW or x.dtype != torch.bfloat16 or not x.is_cuda:
+        return False
+    if not (pd.k == 3 and pd.s == 1 and pd.p == 1 and pd.d == 1 and pd.c == x.shape[1]):
+        return False
+    for pc in (pc1, pc2):
+        if pc is not None and not (pc.k == 1 and pc.s == 1 and pc.p == 0 and pc.w_tc is not None):
+            return False
+    if pc1.cin != pd.c or (pc2 is not None and pc2.cin != pc1.cout):
+        return False
+    xp, xld = view_of(x)
+    if xp % 16:
+        return False
+    cl = pc2.cout if pc2 is not None else pc1.cout
+    return bool(_lib.lib().lpc_dwpw_tc_supported(pd.c, pc1.cout, pc2.cout if pc2 is not None else 0, xld, out_ld if out_ld is not None else cl))
+
+
+def dwpw(x, pd, pc1, pc2=None, out=None, rowmax=None):
+    """act2(W2 act1(W1 dw_act(dw3x3(x)))) in one kernel (lpc_dwpw_tc); callers check ``dwpw_supported`` first."""
+    B, Cin, H, W = x.shape
+    cl = pc2.cout if pc2 is not None else pc1.cout
+    if out is None:
+        out = new_act(B, cl, H, W, x.dtype, x.device)
+    assert tuple(out.shape) == (B, cl, H, W)
+    xp, xld = view_of(x)
+    yp, yld = view_of(out)
+    L = _lib.lib()
+    rm = (None, 0, 0)
+    if rowmax is not None:
+        rm = (C.c_void_p(rowmax["ws"].data_ptr()), int(rowmax["A"]), int(rowmax["off"]))
+    flops = 2.0 * B * H * W * (9 * Cin + Cin * pc1.cout + (pc1.cout * pc2.cout if pc2 is not None else 0))
+    nbytes = x.element_size() * B * H * W * (Cin + cl)
+    tag = f"dw{Cin}->{pc1.cout}" + (f"->{pc2.cout}" if pc2 is not None else "") + f" {H}x{W} B{B}"
+
+    def launch(keep=(x, out, pd, pc1, pc2, rowmax)):
+        check(L.lpc_dwpw_tc(xp, xld, B, H, W, Cin, _fp(pd.w), _fp(pd.bias), pd.act, _fp(pc1.w_tc), _fp(pc1.bias), pc1.cout, pc1.act,
+                            _fp(pc2.w_tc) if pc2 is not None else None, _fp(pc2.bias) if pc2 is not None else None,
+                            pc2.cout if pc2 is not None else 0, pc2.act if pc2 is not None else ACT_NONE, yp, yld, rm[0], rm[1], rm[2], _stream()),
+              "dwpw_tc")
+    if REPLAY is not None:
+        REPLAY.append(("dwpw_tc", launch, flops, nbytes, tag, None))
+    with _prof("dwpw_tc", flops, nbytes, tag):
+        launch()
+    if rowmax is not None:
+        rowmax["ok"] = rowmax.get("ok", True)
+    return out
+
+
 @_profiled
 def sppf_pool(x, out):
     """out (3C channels) <- [pool5(x), pool9(x), pool13(x)]."""

@@ -132,12 +132,24 @@ class v10Detect(Detect):
             cv2[i][2](cv2[i][1](cv2[i][0](xs[i])), out=raws[i][:, :nb])
 
         def cls(i):
-            t = cv3[i][0][1](cv3[i][0][0](xs[i]))
+            # [dw3x3 + 1x1] -> [dw3x3 + 1x1] -> 1x1 (head.py:504-505).  Fused: two launches (lpc_dwpw_tc: the depthwise output and the
+            # first pointwise output never leave the SM) instead of five; shapes the fused kernel declines run link by link.
+            x0 = xs[i]
+            d0, p0 = cv3[i][0][0]._packed(x0, cv3[i][0][0]._build), cv3[i][0][1]._packed(x0, cv3[i][0][1]._build)
+            if F.dwpw_supported(x0, d0, p0):
+                t = F.dwpw(x0, d0, p0)
+            else:
+                t = cv3[i][0][1](cv3[i][0][0](x0))
+            d1, p1, p2 = cv3[i][1][0]._packed(t, cv3[i][1][0]._build), cv3[i][1][1]._packed(t, cv3[i][1][1]._build), cv3[i][2]._packed(t, cv3[i][2]._build)
+            dst = raws[i][:, nb:]
+            if F.dwpw_supported(t, d1, p1, p2, out_ld=F.view_of(dst)[1]):
+                F.dwpw(t, d1, p1, p2, out=dst, rowmax=rms[i])
+                return
             t = cv3[i][1][1](cv3[i][1][0](t))
             if rms[i] is not None:
-                cv3[i][2](t, out=raws[i][:, nb:], rowmax=rms[i])
+                cv3[i][2](t, out=dst, rowmax=rms[i])
             else:
-                cv3[i][2](t, out=raws[i][:, nb:])
+                cv3[i][2](t, out=dst)
 
         # class branches first: they are the longer chains
         F.fork_join([(lambda fn=fn, i=i: fn(i)) for i in range(self.nl) for fn in (cls, box)], xs[0].device)

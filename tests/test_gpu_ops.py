@@ -297,3 +297,84 @@ def test_error_behaviour(M, Fn, pkg):
         Fn.v10_postprocess(torch.rand(1, 100, 84, device="cuda"), 300, 80)      # A < max_det, ops.py:852 asserts too
     with pytest.raises(pkg.LpcError):
         Fn.view_of(torch.rand(2, 8, 4, 4, device="cuda"))                        # NCHW-contiguous is not an NHWC view
+
+
+# ---- fused depthwise -> pointwise (-> pointwise) ----------------------------------------------------------------------
+DWPW_CASES = [
+    # Cin, C1, C2, H, W   (C2 = 0: single pointwise stage)
+    (64, 80, 0, 80, 80),        # LPC head P3, first link
+    (80, 80, 80, 80, 80),       # LPC head P3, second link + final 1x1 (K block 64 + 16)
+    (192, 80, 0, 40, 40),       # P4: three K blocks
+    (384, 80, 0, 20, 20),       # P5: six K blocks, ring recycling
+    (80, 80, 80, 20, 20),
+    (64, 64, 64, 37, 29),       # tile-ragged map (neither 8 | W nor 16 | H)
+    (128, 128, 128, 24, 24),    # yolov10s widths, two K blocks in both GEMMs
+    (16, 32, 0, 16, 16),        # Cin below one K block (TMA zero fill)
+]
+
+
+@pytest.mark.parametrize("case", DWPW_CASES)
+@pytest.mark.parametrize("keys", [False, True])
+def test_dwpw_fused(M, Fn, oracle, pkg, case, keys):
+    """lpc_dwpw_tc against (a) the oracle's restatement of conv.Conv (depthwise, SiLU) -> conv.Conv (1x1, SiLU) [-> nn.Conv2d 1x1
+    with bias] (head.py:504-505) and (b) the unfused kernels link by link; with ``keys`` also the per-pixel max-logit keys."""
+    Cin, C1, C2, H, W = case
+    head = importlib.import_module("lpc-yolo_b200.nn.modules.head")
+    dw = _randomize(M.Conv(Cin, Cin, 3, g=Cin), 21)
+    pw = _randomize(M.Conv(Cin, C1, 1), 22)
+    pl = head._Plain1x1(C1, C2) if C2 else None
+    x = _x((2, Cin, H, W), torch.bfloat16, seed=5)
+    cx = oracle._Ctx({**{"a." + k: v.detach().clone().float() for k, v in dw.state_dict().items()},
+                      **{"b." + k: v.detach().clone().float() for k, v in pw.state_dict().items()}})
+    ref = cx.conv(cx.conv(x, "a", 3, 1, g=Cin, act="silu"), "b", 1, act="silu")
+    if pl is not None:
+        ref = torch.nn.functional.conv2d(ref, pl.weight.detach().float(), pl.bias.detach().float())
+    dw, pw = dw.cuda(), pw.cuda()
+    pl = pl.cuda() if pl is not None else None
+    xg = Fn.as_act(x.cuda().to(torch.bfloat16), torch.bfloat16)
+    with torch.no_grad():
+        pd, p1 = dw._packed(xg, dw._build), pw._packed(xg, pw._build)
+        p2 = pl._packed(xg, pl._build) if pl is not None else None
+        cl = C2 or C1
+        assert Fn.dwpw_supported(xg, pd, p1, p2)
+        A = H * W + 7
+        rm = {"ws": torch.zeros(2 * A * 4 + 256, dtype=torch.uint8, device="cuda"), "A": A, "off": 5} if keys else None
+        got = Fn.dwpw(xg, pd, p1, p2, rowmax=rm)
+        torch.cuda.synchronize()
+        # unfused chain through the same packed weights
+        t = Fn.conv2d(Fn.dwconv2d(xg, pd), p1)
+        unf = Fn.conv2d(t, p2) if p2 is not None else t
+    _cmp(got, ref, torch.bfloat16, f"dwpw {case}", block=True)
+    d = (got.float() - unf.float()).abs().max().item() / max(unf.float().abs().max().item(), 1e-9)
+    assert d < 1.2e-2, f"fused vs unfused: {d:.3e}"          # both round to bf16 after every link; the bias enters in a different place
+    if keys:
+        k32 = rm["ws"][: 2 * A * 4].view(torch.int32).view(2, A)[:, 5:5 + H * W].cpu()
+        mx = got.float().amax(1).reshape(2, H * W).cpu()
+        u = mx.contiguous().view(torch.int32)
+        want = torch.where(u < 0, ~u, u ^ torch.tensor(-2147483648, dtype=torch.int32))
+        assert torch.equal(k32, want)
+        assert rm.get("ok") is True
+
+
+def test_head_cls_branch_fused_equals_unfused(pkg, oracle, Fn):
+    """The whole LPC model with the fused class branches against the same model with LPC_FUSE_DWPW off: raw maps within one
+    bf16 rounding of each other per link, identical kept detections up to near-ties."""
+    om = oracle.build("lpc")
+    pm = pkg.YOLOv10DetectionModel(oracle.MODEL_FILES["lpc"])
+    pm.load_state_dict(om.sd, strict=True)
+    pm = pm.cuda().eval()
+    pm.compute_dtype = torch.bfloat16
+    x = oracle.synth_input(2, 320).cuda()
+    with torch.no_grad():
+        n0 = pkg.lib().lpc_launch_count()
+        fused = [r.float() for r in pm(x)["one2one"][1]]
+        n1 = pkg.lib().lpc_launch_count()
+        Fn.FUSE_DWPW = False
+        try:
+            plain = [r.float() for r in pm(x)["one2one"][1]]
+            n2 = pkg.lib().lpc_launch_count()
+        finally:
+            Fn.FUSE_DWPW = True
+    assert (n2 - n1) - (n1 - n0) == 9, (n1 - n0, n2 - n1)       # 3 levels x (5 -> 2 launches)
+    for a, b in zip(fused, plain):
+        assert ((a - b).norm() / b.norm()).item() < 1e-2
