@@ -100,8 +100,9 @@ int lpc_conv2d_tc_supported(int Cin, int Cout, int k, int stride, int pad, int x
  * dw -> 1x1 links of CIB (block.py:744-750).  bf16 NHWC; dw_w [9][Cin] fp32; w1 [C1][pad64(Cin)], w2 [C2][pad64(C1)]
  * bf16 (lpc_conv2d_tc's 1x1 packing); C1, C2 multiples of 16 and <= 256, C2 = 0 / w2 = NULL for a single pointwise
  * stage.  rowmax_keys: as lpc_conv2d_tc_rowmax (per-pixel key of max_c of the final outputs), or NULL.
- * lpc_dwpw_tc_supported: 1 if the shape (incl. its shared-memory plan) is taken. */
-int lpc_dwpw_tc_supported(int Cin, int C1, int C2, int x_ld, int y_ld);
+ * Cin a multiple of 16; dw_act == act1 in {none, SiLU, Mish}; act2 none.
+ * lpc_dwpw_tc_supported: 1 if the shape (incl. its shared-memory plan) and the activations are taken. */
+int lpc_dwpw_tc_supported(int Cin, int C1, int C2, int x_ld, int y_ld, int dw_act, int act1, int act2);
 int lpc_dwpw_tc(const void* x, int x_ld, int B, int H, int W, int Cin, const float* dw_w, const float* dw_bias, int dw_act,
                 const void* w1, const float* b1, int C1, int act1, const void* w2, const float* b2, int C2, int act2,
                 void* y, int y_ld, unsigned int* rowmax_keys, long long rowmax_img_stride, int rowmax_offset, void* stream);

@@ -301,12 +301,17 @@ def dwconv2d(x, pd, out=None, res=None):
     return out
 
 
-FUSE_DWPW = os.environ.get("LPC_FUSE_DWPW", "1") != "0"
+# "1": use lpc_dwpw_tc wherever the kernel takes the shape; "auto" (default): only where it measured faster than the unfused
+# chain on B200 (single pointwise stage, one 64-channel block, large maps: dw64->80 @80x80 B64 44 vs 53 us; every other
+# head shape loses 10-70 %, profiles/r02_e_dwpw.md - the kernel is issue-bound at 20 warps per SM); "0": never.
+FUSE_DWPW = os.environ.get("LPC_FUSE_DWPW", "auto")
 
 
 def dwpw_supported(x, pd, pc1, pc2=None, out_ld=None):
     """Can depthwise ``pd`` -> pointwise ``pc1`` [-> pointwise ``pc2``] on x run as one lpc_dwpw_tc launch?"""
-    if not FUSE_DWPW or x.dtype != torch.bfloat16 or not x.is_cuda:
+    if FUSE_DWPW in ("0", False) or x.dtype != torch.bfloat16 or not x.is_cuda:
+        return False
+    if FUSE_DWPW == "auto" and not (pc2 is None and pd.c <= 64 and x.shape[0] * x.shape[2] * x.shape[3] >= 128 * 1024):
         return False
     if not (pd.k == 3 and pd.s == 1 and pd.p == 1 and pd.d == 1 and pd.c == x.shape[1]):
         return False
@@ -319,7 +324,8 @@ def dwpw_supported(x, pd, pc1, pc2=None, out_ld=None):
     if xp % 16:
         return False
     cl = pc2.cout if pc2 is not None else pc1.cout
-    return bool(_lib.lib().lpc_dwpw_tc_supported(pd.c, pc1.cout, pc2.cout if pc2 is not None else 0, xld, out_ld if out_ld is not None else cl))
+    return bool(_lib.lib().lpc_dwpw_tc_supported(pd.c, pc1.cout, pc2.cout if pc2 is not None else 0, xld, out_ld if out_ld is not None else cl,
+                                                 pd.act, pc1.act, pc2.act if pc2 is not None else ACT_NONE))
 
 
 def dwpw(x, pd, pc1, pc2=None, out=None, rowmax=None):

@@ -336,7 +336,11 @@ def test_dwpw_fused(M, Fn, oracle, pkg, case, keys):
         pd, p1 = dw._packed(xg, dw._build), pw._packed(xg, pw._build)
         p2 = pl._packed(xg, pl._build) if pl is not None else None
         cl = C2 or C1
-        assert Fn.dwpw_supported(xg, pd, p1, p2)
+        Fn.FUSE_DWPW = "1"
+        try:
+            assert Fn.dwpw_supported(xg, pd, p1, p2)
+        finally:
+            Fn.FUSE_DWPW = "auto"
         A = H * W + 7
         rm = {"ws": torch.zeros(2 * A * 4 + 256, dtype=torch.uint8, device="cuda"), "A": A, "off": 5} if keys else None
         got = Fn.dwpw(xg, pd, p1, p2, rowmax=rm)
@@ -366,15 +370,16 @@ def test_head_cls_branch_fused_equals_unfused(pkg, oracle, Fn):
     pm.compute_dtype = torch.bfloat16
     x = oracle.synth_input(2, 320).cuda()
     with torch.no_grad():
-        n0 = pkg.lib().lpc_launch_count()
-        fused = [r.float() for r in pm(x)["one2one"][1]]
-        n1 = pkg.lib().lpc_launch_count()
-        Fn.FUSE_DWPW = False
+        Fn.FUSE_DWPW = "1"
         try:
+            n0 = pkg.lib().lpc_launch_count()
+            fused = [r.float() for r in pm(x)["one2one"][1]]
+            n1 = pkg.lib().lpc_launch_count()
+            Fn.FUSE_DWPW = "0"
             plain = [r.float() for r in pm(x)["one2one"][1]]
             n2 = pkg.lib().lpc_launch_count()
         finally:
-            Fn.FUSE_DWPW = True
+            Fn.FUSE_DWPW = "auto"
     assert (n2 - n1) - (n1 - n0) == 9, (n1 - n0, n2 - n1)       # 3 levels x (5 -> 2 launches)
     for a, b in zip(fused, plain):
         assert ((a - b).norm() / b.norm()).item() < 1e-2
