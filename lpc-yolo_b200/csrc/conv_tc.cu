@@ -762,7 +762,23 @@ extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W
       p.a_bufs = ab > MAX_STAGES ? MAX_STAGES : (ab < 2 ? 2 : ab);
     }
   }
-  if (!halo) p.n_tile = pick_ntile(Cout, 256);
+  if (!halo) {
+    // N tile of the per-tap kernel.  The widest tile minimises activation re-reads and MMA instructions, but (a) a layer with few M
+    // tiles (batch 1; 20x20 maps) then leaves most SMs idle - 128->256 k3 @40x40 at batch 1 is 13 tiles of N = 256 on 148 SMs,
+    // each walking 18 K steps alone - and (b) N = 256 needs both TMEM accumulators of an SM, i.e. one resident CTA.  Narrow
+    // the tile while the launch has fewer work items than the GPU has CTA slots (never below 64 columns).
+    // LPC_TC_NTILE_MAX caps the width outright (measurement).
+    static const int nt_cap = [] { const char* e = getenv("LPC_TC_NTILE_MAX"); return e ? atoi(e) : 256; }();
+    static const int nt_auto = [] { const char* e = getenv("LPC_TC_NTILE_AUTO"); return e ? atoi(e) : 1; }();
+    int nt = pick_ntile(Cout, nt_cap >= 16 ? nt_cap : 256);
+    if (nt == 0) nt = pick_ntile(Cout, 256);
+    if (nt_auto) {
+      const long long m_est = (k == 1) ? ((long long)B * H * W + 127) / 128
+                                       : (long long)B * (((H + 2 * pad - k) / stride + 1) * ((W + 2 * pad - k) / stride + 1) + 127) / 128;
+      while (nt > 64 && nt % 32 == 0 && m_est * (Cout / nt) < (long long)num_sms() * (nt > 128 ? 1 : 2)) nt /= 2;
+    }
+    p.n_tile = nt;
+  }
   p.n_tiles = Cout / p.n_tile;
   p.acc_cols = 32;
   while (p.acc_cols < p.n_tile) p.acc_cols <<= 1;
