@@ -294,6 +294,8 @@ def main():
     pkg = importlib.import_module("lpc-yolo_b200")
     Fn = importlib.import_module("lpc-yolo_b200.functional")
     synth = importlib.import_module("lpc-yolo_b200.utils.synth")
+    # one process per GPU: keep this rank's host staging buffers and threads on the socket next to its GPU
+    host_cpus = importlib.import_module("lpc-yolo_b200.parallel").bind_host_to_gpu(local) if world > 1 else 0
     L = pkg.lib()
     B, S, K = args.batch, args.size, 300
 
@@ -568,7 +570,7 @@ def main():
                         "source": "YOLO.predict(uint8 HWC BGR arrays in pinned host memory): H2D, /255 + BGR->RGB + NHWC pack, network, fused tail, D2H"},
                 "gpu_launches": int(launches_per_step * args.steps),
                 "roofline": roof, "roofline_tail": roof_tail, "cpu_baseline": cpu, "other_configs": others,
-                "gather_check": gather_check, "strong_scaling_config3": strong}
+                "gather_check": gather_check, "strong_scaling_config3": strong, "host_cpus_bound_per_rank": host_cpus}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

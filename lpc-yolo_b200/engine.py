@@ -101,35 +101,48 @@ class Boxes:
 
 
 class Results:
-    """engine/results.py Results (detection fields only).  ``boxes`` is built on first access: constructing 2 x B small
-    objects per batch was a tenth of a millisecond of host time behind a 2 ms device step."""
+    """engine/results.py Results (detection fields only).  Everything per-image is built on first access: ``boxes`` is a view
+    of the batch's [B,K,6] detection tensor cut at this image's kept count.  (Slicing 2 x B tensor views and constructing
+    B Boxes objects eagerly cost ~0.25 ms of host time per 64-image batch behind a 2 ms device step.)"""
 
-    __slots__ = ("_orig", "orig_shape", "_data", "_boxes", "names", "path", "speed")
+    __slots__ = ("_orig", "orig_shape", "_data", "_boxes", "names", "path", "speed", "_lazy")
 
-    def __init__(self, orig_img, path, names, boxes=None, orig_shape=None):
+    def __init__(self, orig_img, path, names, boxes=None, orig_shape=None, lazy=None):
         self._orig = orig_img
         if orig_shape is None:
             orig_shape = tuple(orig_img.shape[-2:]) if torch.is_tensor(orig_img) else orig_img.shape[:2]
         self.orig_shape = orig_shape
         self._data, self._boxes = boxes, None
+        self._lazy = lazy                        # (batch detections [B,K,6], image index, kept count)
         self.names, self.path, self.speed = names, path, _NO_SPEED
+
+    def _rows(self):
+        if self._data is None and self._lazy is not None:
+            preds, i, n = self._lazy
+            self._data = preds[i, :n]
+        return self._data
 
     @property
     def boxes(self):
-        if self._boxes is None and self._data is not None:
+        if self._boxes is None and self._rows() is not None:
             self._boxes = Boxes(self._data, self.orig_shape)
         return self._boxes
 
     @property
     def orig_img(self):
         """uint8 HWC array as ops.convert_torch2numpy_batch (utils/ops.py:826-836) yields, built on demand."""
-        if isinstance(self._orig, tuple):          # (batch tensor, index): sliced only when somebody asks for the image
+        if isinstance(self._orig, tuple):          # (batch tensor / array, index): sliced only when somebody asks for the image
             self._orig = self._orig[0][self._orig[1]]
         if torch.is_tensor(self._orig):
-            self._orig = (self._orig.permute(1, 2, 0).contiguous() * 255).clamp(0, 255).to(torch.uint8).cpu().numpy()
+            if self._orig.dtype == torch.uint8:
+                self._orig = self._orig.cpu().numpy()
+            else:
+                self._orig = (self._orig.permute(1, 2, 0).contiguous() * 255).clamp(0, 255).to(torch.uint8).cpu().numpy()
         return self._orig
 
     def __len__(self):
+        if self._lazy is not None and self._data is None:
+            return int(self._lazy[2])
         return self._data.shape[0] if self._data is not None else 0
 
 
@@ -416,24 +429,23 @@ class YOLOv10DetectionPredictor:
         if host is not None:
             host[1].synchronize()
             self.last_preds_host = host[0]
-        K = preds.shape[1]
+        names = self.model.names
+        if torch.is_tensor(orig_imgs) or (isinstance(orig_imgs, np.ndarray) and orig_imgs.ndim == 4):
+            hwc = orig_imgs.shape[-1] == 3 and orig_imgs.dtype in (torch.uint8, np.uint8)
+            shapes = [tuple(orig_imgs.shape[1:3]) if hwc else tuple(orig_imgs.shape[-2:])] * B
+            origs = [(orig_imgs, i) for i in range(B)]
+        else:
+            shapes = [o.shape[:2] for o in orig_imgs]
+            origs = orig_imgs
         if self.args.classes is None:
             # scores are sorted, so a prefix of every image survives: the B prefix lengths come from the host copy of the
-            # detections when there is one (else ONE device reduction + one small D2H), ONE split call cuts the flattened
-            # [B*K,6] tensor into (kept, dropped) pairs of views
+            # detections when there is one (else ONE device reduction + one small D2H); each Results cuts its own view lazily
             src = self.last_preds_host if self.last_preds_host is not None else preds
             counts = (src[..., 4] > self.args.conf).sum(1).tolist()
-            sizes = [v for n in counts for v in (n, K - n)]
-            per_img = preds.reshape(B * K, 6).split(sizes)[0::2]
-        else:
-            cls = torch.tensor(self.args.classes, device=preds.device, dtype=preds.dtype)
-            mask = (preds[..., 4] > self.args.conf) & (preds[..., 5:6] == cls.unsqueeze(0)).any(2)
-            per_img = [p[mask[i]] for i, p in enumerate(preds)]
-        names = self.model.names
-        if torch.is_tensor(orig_imgs):
-            shape = tuple(orig_imgs.shape[-2:])
-            return [Results((orig_imgs, i), f"image{i}.jpg", names, per_img[i], shape) for i in range(B)]
-        return [Results(o, f"image{i}.jpg", names, per_img[i], o.shape[:2]) for i, o in enumerate(orig_imgs)]
+            return [Results(origs[i], f"image{i}.jpg", names, None, shapes[i], lazy=(preds, i, counts[i])) for i in range(B)]
+        cls = torch.tensor(self.args.classes, device=preds.device, dtype=preds.dtype)
+        mask = (preds[..., 4] > self.args.conf) & (preds[..., 5:6] == cls.unsqueeze(0)).any(2)
+        return [Results(origs[i], f"image{i}.jpg", names, p[mask[i]], shapes[i]) for i, p in enumerate(preds)]
 
     @staticmethod
     def _is_array_source(source):
@@ -471,8 +483,8 @@ class YOLOv10DetectionPredictor:
                     host = self._host_copy(preds)
                 if isinstance(source, (list, tuple)):
                     orig = list(source)
-                else:
-                    orig = [a for a in (im.cpu().numpy() if torch.is_tensor(source) else (source if source.ndim == 4 else source[None]))]
+                else:                      # one [B,h,w,3] array / tensor: Results slice it on demand
+                    orig = im if torch.is_tensor(source) else (source if source.ndim == 4 else source[None])
                 with profilers[2]:
                     self.results = self.postprocess(preds, im, orig, host=host)
             else:

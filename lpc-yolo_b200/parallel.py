@@ -32,3 +32,20 @@ def gather_detections(dets, batch=None, group=None):
     out = torch.empty((world * mx, K, C), dtype=dets.dtype, device=dets.device)
     dist.all_gather_into_tensor(out, pad, group=group)
     return torch.cat([out[r * mx: r * mx + (hi - lo)] for r, (lo, hi) in enumerate(sizes)], 0)
+
+
+def bind_host_to_gpu(index):
+    """Pin the calling thread (and, through the first-touch policy, the pinned host buffers it allocates afterwards) to the
+    CPU cores next to GPU ``index`` (NVML's ideal CPU affinity for the device).  With one process per GPU on a two-socket
+    host this keeps every rank's host-to-device staging traffic on its own socket: all eight ranks reading one node's DRAM
+    is what held the end-to-end metric to 5.5x at 8 GPUs while the device-timed metric scaled 7.9x (SCALE_r01).
+    Returns the number of CPUs in the mask, or 0 when NVML / affinity control is unavailable (nothing changed)."""
+    try:
+        import pynvml as N
+        N.nvmlInit()
+        h = N.nvmlDeviceGetHandleByIndex(int(index))
+        N.nvmlDeviceSetCpuAffinity(h)
+        import os
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return 0
