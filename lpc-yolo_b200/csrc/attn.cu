@@ -375,6 +375,8 @@ constexpr size_t ATT_SMEM = sizeof(float) * (MAX_KD * (BQ + 4) + MAX_KD * (BKEY 
 
 }  // namespace
 
+int lpc_psa_attention_tc(const void* qkv, int ld, int B, int N, int heads, void* out, int out_ld, cudaStream_t stream);   // attn_tc.cu
+
 extern "C" int lpc_psa_attention(int dtype, const void* qkv, int qkv_ld, int B, int N, int heads, int kd, int hd,
                                  void* out, int out_ld, void* stream) {
   LPC_REQUIRE(qkv && out && B > 0 && N > 0 && heads > 0, "psa_attention: bad argument");
@@ -392,6 +394,9 @@ extern "C" int lpc_psa_attention(int dtype, const void* qkv, int qkv_ld, int B, 
   } else if (dtype == LPC_F32) {
     if (lpc_first_on_device(&attr_done[0])) cudaFuncSetAttribute(psa_attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM);
     lpc_launch_pdl(psa_attention_kernel<float>, grid, ATT_NT, ATT_SMEM, s, (const float*)qkv, qkv_ld, N, heads, kd, hd, (float*)out, out_ld);
+  } else if (dtype == LPC_BF16 && kd == 32 && hd == 64 && !getenv("LPC_ATT_MMA_SYNC") && qkv_ld % 8 == 0 && out_ld % 8 == 0 && aligned16(qkv) && aligned16(out)) {
+    // tcgen05 path (attn_tc.cu): S and P in tensor memory, K / V by TMA, V consumed MN-major as it lies in memory
+    return lpc_psa_attention_tc(qkv, qkv_ld, B, N, heads, out, out_ld, s);
   } else if (dtype == LPC_BF16 && ((kd == 32 && hd == 64) || (kd == 36 && hd == 72)) && qkv_ld % 8 == 0 && out_ld % 2 == 0 &&
              aligned16(qkv) && (reinterpret_cast<uintptr_t>(out) & 3) == 0) {
     // tensor-core path (the two head geometries of the YOLOv10 / LPC family)

@@ -6,7 +6,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["api.cu", "conv_direct.cu", "conv_tc.cu", "dwpw_tc.cu", "stem.cu", "stem_tc.cu", "dwconv.cu", "glue.cu", "attn.cu", "tail.cu"]
+SOURCES = ["api.cu", "conv_direct.cu", "conv_tc.cu", "dwpw_tc.cu", "stem.cu", "stem_tc.cu", "dwconv.cu", "glue.cu", "attn.cu", "attn_tc.cu", "tail.cu"]
 OUT = os.path.join(HERE, "liblpcyolo.so")
 STAMP = os.path.join(HERE, ".liblpcyolo.stamp")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

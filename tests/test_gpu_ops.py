@@ -383,3 +383,27 @@ def test_head_cls_branch_fused_equals_unfused(pkg, oracle, Fn):
     assert (n2 - n1) - (n1 - n0) == 9, (n1 - n0, n2 - n1)       # 3 levels x (5 -> 2 launches)
     for a, b in zip(fused, plain):
         assert ((a - b).norm() / b.norm()).item() < 1e-2
+
+
+@pytest.mark.parametrize("N", [25, 100, 128, 129, 400, 900, 1600])
+@pytest.mark.parametrize("heads,kd,hd", [(2, 32, 64), (5, 32, 64), (4, 36, 72)])
+def test_psa_attention_core(Fn, N, heads, kd, hd):
+    """lpc_psa_attention (bf16: the tcgen05 kernel for kd 32 / hd 64, the mma.sync kernel for kd 36 / hd 72) against the
+    reference arithmetic of Attention.forward (block.py:789-793) in fp32 on the same bf16-rounded q, k, v; N covers every
+    token count of BASELINE configs 2-5 (100 / 400 / 900 / 1600) and block-edge cases (128, 129)."""
+    g = torch.Generator().manual_seed(N * 7 + heads)
+    Ct = heads * (2 * kd + hd)
+    qkv = (torch.randn(2, N, Ct, generator=g) * 0.8).to(torch.bfloat16)
+    x = qkv.cuda().view(2, 1, N, Ct).permute(0, 3, 1, 2)                  # logical [B, Ct, 1, N], NHWC storage
+    with torch.no_grad():
+        out = Fn.psa_attention(x, heads, kd, hd)
+    got = out.permute(0, 2, 3, 1).reshape(2, N, heads * hd).float().cpu()
+    f = qkv.float()
+    q = f[..., : heads * kd].view(2, N, heads, kd)
+    k = f[..., heads * kd: 2 * heads * kd].view(2, N, heads, kd)
+    v = f[..., 2 * heads * kd:].view(2, N, heads, hd)
+    att = torch.einsum("bihc,bjhc->bhij", q, k) * kd ** -0.5
+    ref = torch.einsum("bhij,bjhd->bihd", att.softmax(-1), v).reshape(2, N, heads * hd)
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    l2 = ((got - ref).norm() / ref.norm()).item()
+    assert err < 2e-2 and l2 < 1e-2, f"attention N={N} heads={heads}: max {err:.3e} l2 {l2:.3e}"
