@@ -377,6 +377,18 @@ constexpr size_t ATT_SMEM = sizeof(float) * (MAX_KD * (BQ + 4) + MAX_KD * (BKEY 
 
 int lpc_psa_attention_tc(const void* qkv, int ld, int B, int N, int heads, void* out, int out_ld, cudaStream_t stream);   // attn_tc.cu
 
+// Which bf16 kernel serves kd 32 / hd 64.  Measured on B200 (us, tcgen05 / mma.sync, tools/run_attn.py, profiles/r02_g_attention.md):
+// N 1600 x 5 heads x B 32 (yolov10x @1280) 301 / 341; N 400 x 2 x B 64 (LPC) 31.1 / 31.1; N 400 x 4 x B 256 192 / 182; batch 1:
+// N 900 22.8 / 18.7, N 400 14.6 / 10.5.  The tensor-memory kernel wins where the key loop is long (its per-block MMA +
+// softmax hand-offs amortise), the register-fragment kernel where a CTA lives for three or four blocks: tcgen05 from
+// N > 512.  LPC_ATT_TC=1 / 0 forces one or the other (the parity tests run both on every shape).
+static bool att_use_tc(int N) {
+  const char* e = getenv("LPC_ATT_TC");
+  if (e && e[0] == '1') return true;
+  if (e && e[0] == '0') return false;
+  return N > 512;
+}
+
 extern "C" int lpc_psa_attention(int dtype, const void* qkv, int qkv_ld, int B, int N, int heads, int kd, int hd,
                                  void* out, int out_ld, void* stream) {
   LPC_REQUIRE(qkv && out && B > 0 && N > 0 && heads > 0, "psa_attention: bad argument");
@@ -394,7 +406,7 @@ extern "C" int lpc_psa_attention(int dtype, const void* qkv, int qkv_ld, int B, 
   } else if (dtype == LPC_F32) {
     if (lpc_first_on_device(&attr_done[0])) cudaFuncSetAttribute(psa_attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM);
     lpc_launch_pdl(psa_attention_kernel<float>, grid, ATT_NT, ATT_SMEM, s, (const float*)qkv, qkv_ld, N, heads, kd, hd, (float*)out, out_ld);
-  } else if (dtype == LPC_BF16 && kd == 32 && hd == 64 && !getenv("LPC_ATT_MMA_SYNC") && qkv_ld % 8 == 0 && out_ld % 8 == 0 && aligned16(qkv) && aligned16(out)) {
+  } else if (dtype == LPC_BF16 && kd == 32 && hd == 64 && att_use_tc(N) && qkv_ld % 8 == 0 && out_ld % 8 == 0 && aligned16(qkv) && aligned16(out)) {
     // tcgen05 path (attn_tc.cu): S and P in tensor memory, K / V by TMA, V consumed MN-major as it lies in memory
     return lpc_psa_attention_tc(qkv, qkv_ld, B, N, heads, out, out_ld, s);
   } else if (dtype == LPC_BF16 && ((kd == 32 && hd == 64) || (kd == 36 && hd == 72)) && qkv_ld % 8 == 0 && out_ld % 2 == 0 &&
