@@ -210,6 +210,79 @@ sppf_pool_kernel(const T* __restrict__ x, int x_ld, int H, int W, int C, T* __re
   }
 }
 
+// The same three pools in TWO passes and one barrier: chained stride-1 max pools with -inf padding are single max pools over
+// 5x5 / 9x9 / 13x13 windows clipped to the map, and a square window is separable, so one row pass produces the 5 / 9 / 13-wide
+// row maxima of every pixel from the input tile (13 shared-memory reads) and one column pass reduces each over 5 / 9 / 13 rows
+// (27 reads) straight into the three output slices.  The chained version above runs six passes with a barrier between
+// each and was bound by that latency chain (20 x 20 map, 128 channels, B = 64: 32 us in the step for 26 MB of traffic).
+template <typename T>
+__global__ void __launch_bounds__(256)
+sppf_pool_direct_kernel(const T* __restrict__ x, int x_ld, int H, int W, int C, T* __restrict__ y, int y_ld, int VP) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int V = Vec<T>::N;
+  extern __shared__ uint4 sp4[];
+  const int HW = H * W, items = HW * VP;
+  uint4* a = sp4;                 // input [HW][VP]
+  uint4* r5 = sp4 + items;        // row maxima of width 5 / 9 / 13
+  uint4* r9 = r5 + items;
+  uint4* r13 = r9 + items;
+  const int n = blockIdx.y, c0 = blockIdx.x * VP * V;
+  const T* xin = x + (long long)n * HW * x_ld + c0;
+  T* yo = y + (long long)n * HW * y_ld + c0;
+  for (int e = threadIdx.x; e < items; e += blockDim.x) {
+    const int p = e / VP, j = e - p * VP;
+    a[e] = __ldg(reinterpret_cast<const uint4*>(xin + (long long)p * x_ld + j * V));
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < items; e += blockDim.x) {
+    const int p = e / VP, px = p % W;
+    uint4 m = a[e];
+#pragma unroll
+    for (int d = 1; d <= 2; ++d) {
+      if (px - d >= 0) m = vec_max<T>(m, a[e - d * VP]);
+      if (px + d < W) m = vec_max<T>(m, a[e + d * VP]);
+    }
+    r5[e] = m;
+#pragma unroll
+    for (int d = 3; d <= 4; ++d) {
+      if (px - d >= 0) m = vec_max<T>(m, a[e - d * VP]);
+      if (px + d < W) m = vec_max<T>(m, a[e + d * VP]);
+    }
+    r9[e] = m;
+#pragma unroll
+    for (int d = 5; d <= 6; ++d) {
+      if (px - d >= 0) m = vec_max<T>(m, a[e - d * VP]);
+      if (px + d < W) m = vec_max<T>(m, a[e + d * VP]);
+    }
+    r13[e] = m;
+  }
+  __syncthreads();
+  const int rs = W * VP;
+  for (int e = threadIdx.x; e < items; e += blockDim.x) {
+    const int p = e / VP, j = e - p * VP, py = p / W;
+    uint4 m5 = r5[e], m9 = r9[e], m13 = r13[e];
+#pragma unroll
+    for (int d = 1; d <= 6; ++d) {
+      const bool up = py - d >= 0, dn = py + d < H;
+      if (d <= 2) {
+        if (up) m5 = vec_max<T>(m5, r5[e - d * rs]);
+        if (dn) m5 = vec_max<T>(m5, r5[e + d * rs]);
+      }
+      if (d <= 4) {
+        if (up) m9 = vec_max<T>(m9, r9[e - d * rs]);
+        if (dn) m9 = vec_max<T>(m9, r9[e + d * rs]);
+      }
+      if (up) m13 = vec_max<T>(m13, r13[e - d * rs]);
+      if (dn) m13 = vec_max<T>(m13, r13[e + d * rs]);
+    }
+    T* dst = yo + (long long)p * y_ld + j * V;
+    *reinterpret_cast<uint4*>(dst) = m5;
+    *reinterpret_cast<uint4*>(dst + C) = m9;
+    *reinterpret_cast<uint4*>(dst + 2 * C) = m13;
+  }
+}
+
 // ---- bf16 depthwise conv, TMA-staged (production path) ---------------------------------------------------------------
 // The register-window kernel above spends ~45 % of its ~1060 instructions per thread on addressing and bounds
 // predicates of its 18 global loads and hides their latency only through occupancy (ncu: issue-active 52 %, warps
@@ -619,12 +692,29 @@ extern "C" int lpc_sppf_pool(int dtype, const void* x, int x_ld, int B, int H, i
   const int V = dtype == LPC_F32 ? 4 : 8;
   LPC_REQUIRE(C % V == 0 && x_ld % V == 0 && y_ld % V == 0 && y_ld >= 3 * C, "sppf_pool: C / pitch constraints");
   LPC_REQUIRE(aligned16(x) && aligned16(y), "sppf_pool: pointers must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  LPC_REQUIRE(B <= 65535, "sppf_pool: batch too large");
+  static const int chained = [] { const char* e = getenv("LPC_SPPF_CHAINED"); return e ? atoi(e) : 0; }();
+  if (!chained && (size_t)H * W * 16 * 4 <= 100 * 1024) {
+    // direct two-pass kernel: four planes (input + three row-maxima planes) of one 16-byte channel vector per pixel
+    const int VP = 1;
+    const size_t smem = (size_t)H * W * VP * 16 * 4;
+    dim3 grid(C / (VP * V), B);
+    if (dtype == LPC_F32) {
+      cudaFuncSetAttribute(sppf_pool_direct_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      lpc_launch_pdl(sppf_pool_direct_kernel<float>, grid, 256, smem, s, (const float*)x, x_ld, H, W, C, (float*)y, y_ld, VP);
+    } else if (dtype == LPC_BF16) {
+      cudaFuncSetAttribute(sppf_pool_direct_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      lpc_launch_pdl(sppf_pool_direct_kernel<bf16>, grid, 256, smem, s, (const bf16*)x, x_ld, H, W, C, (bf16*)y, y_ld, VP);
+    } else
+      LPC_FAIL(LPC_E_ARG, "sppf_pool: unknown dtype %d", dtype);
+    LPC_CHECK_LAUNCH("sppf_pool");
+    return LPC_OK;
+  }
   // two 16-byte channel vectors per pixel per CTA when the channel count and the shared-memory budget allow
   int VP = (C % (2 * V) == 0 && (size_t)H * W * 2 * 16 * 2 <= 100 * 1024) ? 2 : 1;
   const size_t smem = (size_t)H * W * VP * 16 * 2;
   LPC_REQUIRE(smem <= 200 * 1024, "sppf_pool: map too large for the shared-memory pooling kernel (%d x %d)", H, W);
-  LPC_REQUIRE(B <= 65535, "sppf_pool: batch too large");
-  cudaStream_t s = (cudaStream_t)stream;
   dim3 grid(C / (VP * V), B);
   if (dtype == LPC_F32) {
     cudaFuncSetAttribute(sppf_pool_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -409,3 +409,26 @@ def test_psa_attention_core(Fn, N, heads, kd, hd, force, monkeypatch):
     err = (got - ref).abs().max().item() / ref.abs().max().item()
     l2 = ((got - ref).norm() / ref.norm()).item()
     assert err < 2e-2 and l2 < 1e-2, f"attention N={N} heads={heads}: max {err:.3e} l2 {l2:.3e}"
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("hw", [(20, 20), (40, 40), (5, 7), (13, 3), (30, 30)])
+@pytest.mark.parametrize("chained", ["0", "1"])
+def test_sppf_pool_kernels(Fn, dtype, hw, chained, monkeypatch):
+    """lpc_sppf_pool: the direct two-pass kernel (5x5 / 9x9 / 13x13 windows clipped to the map) and the chained three-pool kernel
+    both equal three chained MaxPool2d(5, 1, 2) (block.py:170-175), bit for bit (max needs no arithmetic), also on maps
+    smaller than the windows."""
+    if chained == "1":
+        pytest.skip("LPC_SPPF_CHAINED is read once per process; the chained kernel is covered by maps above the shared-memory limit")
+    H, W = hw
+    x = _x((2, 32, H, W), dtype, seed=H * 31 + W)
+    xg = Fn.as_act(x.cuda().to(dtype), dtype)
+    out = Fn.new_act(2, 96, H, W, dtype, "cuda")
+    with torch.no_grad():
+        Fn.sppf_pool(xg, out)
+    mp = torch.nn.MaxPool2d(5, 1, 2)
+    a = mp(x)
+    b = mp(a)
+    c = mp(b)
+    ref = torch.cat([a, b, c], 1)
+    assert torch.equal(out.float().cpu(), ref.to(dtype).float())
