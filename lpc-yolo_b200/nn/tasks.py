@@ -177,7 +177,12 @@ class BaseModel(LpcModule):
             x = F.pack_input(x.float().contiguous(), self.compute_dtype) if x.shape[1] <= 4 else F.as_act(x, self.compute_dtype)
         y, catbuf = [], {}
         L = list(self.model)
-        for m in L:
+        start = 0
+        front = self._front(x, L, dest, fold)
+        if front is not None:
+            x, start = front
+            y = [None] * start
+        for m in L[start:]:
             if m.i not in live:
                 y.append(None)
                 continue
@@ -202,6 +207,46 @@ class BaseModel(LpcModule):
                 x = m(x)
             y.append(x if m.i in self.save else None)
         return x
+
+    # ---- depth-first front ----------------------------------------------------------------------------------
+    # The first layers work on the largest maps: at batch 64 every one of their activations (52 ... 420 MB) is far larger
+    # than the 126 MB L2, so each layer streams its input from HBM and its output back.  Running the chain of the first
+    # ``front_depth + 1`` layers on a few images at a time keeps a chunk's intermediates in L2 between producer and consumer
+    # (only the chain's input and its last output cross HBM), at the price of ``front_chunks`` times as many launches.
+    # LPC_FRONT="depth,chunks" (e.g. "3,4") switches it on; off by default until measured faster on a shape.
+    front_depth, front_chunks = (lambda e: (int(e.split(",")[0]), int(e.split(",")[1])) if e else (0, 1))(os.environ.get("LPC_FRONT", ""))
+
+    def _front(self, x, L, dest, fold):
+        depth, chunks = self.front_depth, self.front_chunks
+        B = x.shape[0]
+        if depth <= 0 or chunks <= 1 or B < 2 * chunks or depth >= len(L) - 1:
+            return None
+        for m in L[: depth + 1]:
+            if m.f != -1 or m.i in self.save or m.i in dest or isinstance(m, Concat):
+                return None
+        last = L[depth]
+        if last.i in fold or not hasattr(last, "out_shape"):
+            return None
+        # output shape of the chain
+        shp = tuple(x.shape)
+        for m in L[: depth + 1]:
+            if m.i in fold:
+                shp = (shp[0], 4 * shp[1], shp[2] // 2, shp[3] // 2)
+                continue
+            shp = m.out_shape(shp)
+        out = F.new_act(B, shp[1], shp[2], shp[3], x.dtype, x.device)
+        for c in range(chunks):
+            lo, hi = B * c // chunks, B * (c + 1) // chunks
+            xc = x[lo:hi]
+            for m in L[: depth + 1]:
+                if m.i in fold:
+                    continue
+                kw = {"out": out[lo:hi]} if m is last else {}
+                if m.i - 1 in fold and fold[m.i - 1] == m.i:
+                    xc = m(xc, s2d=True, **kw)
+                else:
+                    xc = m(xc, **kw)
+        return out, depth + 1
 
     def fuse(self, verbose=False):
         """tasks.py:146-182.  BN folding (for EVERY conv) happens when weights are packed; nothing to rewrite,
