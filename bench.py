@@ -347,12 +347,19 @@ def main():
             got = run().clone()
             mine = out.clone() if graph is not None else model.detect(x_dev, K, clip=True)
             ok = bool(torch.equal(got[rank * B:(rank + 1) * B], mine))
+            if not ok:
+                sys.stderr.write(f"[T7] rank {rank}: own slice differs, max |d| {(got[rank * B:(rank + 1) * B] - mine).abs().max().item():.3e}\n")
             if rank == 0:
                 for r in range(1, world):
                     gr_ = torch.Generator().manual_seed(1 + r)
                     xr = Fn.pack_u8(torch.randint(0, 256, (B, S, S, 3), generator=gr_, dtype=torch.uint8).to(dev), torch.bfloat16)
-                    ok = ok and bool(torch.equal(got[r * B:(r + 1) * B], model.detect(xr, K, clip=True)))
-                    del xr
+                    dr = model.detect(xr, K, clip=True)
+                    same = bool(torch.equal(got[r * B:(r + 1) * B], dr))
+                    if not same:
+                        d_ = (got[r * B:(r + 1) * B] - dr).abs()
+                        sys.stderr.write(f"[T7] rank 0: recomputed shard {r} differs in {int((d_ > 0).sum())} of {d_.numel()} values, max |d| {d_.max().item():.3e}\n")
+                    ok = ok and same
+                    del xr, dr
             flag = torch.tensor([1 if ok else 0], device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             gather_check = "ok: gathered detections == per-rank detections in rank order (rank 0 recomputed every shard)" if flag.item() == 1 else "MISMATCH"

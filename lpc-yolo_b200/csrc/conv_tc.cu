@@ -899,7 +899,10 @@ extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W
     p.acc_shift = p.n_acc == 4 ? 2 : 1;
     p.tmem_cols = p.n_acc * p.acc_cols;
   }
-  const int ctas_per_sm = (p.tmem_cols <= 256 && smem <= 110 * 1024) ? 2 : 1;
+  // LPC_CTA_CAP=1 (measurement): one CTA per SM per launch, so that kernels of two independent chains (detect(streams=2)) can be
+  // co-resident on every SM
+  static const int cta_cap = [] { const char* e = getenv("LPC_CTA_CAP"); return e ? atoi(e) : 2; }();
+  const int ctas_per_sm = (p.tmem_cols <= 256 && smem <= 110 * 1024 && cta_cap >= 2) ? 2 : 1;
   int per_n = (num_sms() * ctas_per_sm) / p.n_tiles;
   if (per_n < 1) per_n = 1;
   if (per_n > p.m_tiles) per_n = p.m_tiles;

@@ -587,7 +587,8 @@ int launch_dw_tma(const void* x, int x_ld, int B, int H, int W, int C, const flo
   if (lpc_first_on_device(&attr_done)) cudaFuncSetAttribute(dwconv_tma_kernel<K, S, D, PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   const int per_sm = (int)((200 * 1024) / (smem + 1024));
   (void)per_sm;
-  long long gx = (2ll * dw_num_sms() + p.cblks - 1) / p.cblks;      // two resident CTAs per SM in total, split over the channel blocks
+  static const int cta_cap = [] { const char* e = getenv("LPC_CTA_CAP"); return e ? atoi(e) : 2; }();
+  long long gx = ((long long)(cta_cap >= 2 ? 2 : 1) * dw_num_sms() + p.cblks - 1) / p.cblks;      // two resident CTAs per SM in total, split over the channel blocks
   if (gx > nt) gx = nt;
   if (gx < 1) gx = 1;
   if (p.cblks > 65535) return 1;

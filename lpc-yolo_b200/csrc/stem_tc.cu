@@ -355,6 +355,7 @@ int lpc_stem_conv_tc(const void* x, int B, int H, int W, const float* w, const f
   int per_sm = 512 / p.tmem_cols;
   if (per_sm > 4) per_sm = 4;
   while (per_sm > 1 && (size_t)per_sm * (smem + 2048) > 227 * 1024) --per_sm;
+  { static const int cta_cap = [] { const char* e = getenv("LPC_CTA_CAP"); return e ? atoi(e) : 4; }(); if (per_sm > cta_cap) per_sm = cta_cap < 1 ? 1 : cta_cap; }
   long long grid = (long long)sms * per_sm;
   if (grid > tiles) grid = tiles;
   static unsigned long long* trace_buf = nullptr;

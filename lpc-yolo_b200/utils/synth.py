@@ -4,6 +4,10 @@ Name-keyed (crc32 of the parameter name seeds its generator), so any other holde
 keys - e.g. the CPU baseline in bench.py - can be given bit-identical weights by ``state_dict()`` exchange.
 Conv weights are unit-gain uniform (a = sqrt(3/fan_in)) times ``gain`` to keep activations O(1) through the
 SiLU/Mish stack without a BN calibration pass; BN gamma in [0.75,1.25], beta in [-0.2,0.2], identity stats.
+``gain`` = 1.3: measured on the oracle (LPC and yolov10s @320), 1.0 ... 1.3 keep the raw head maps within |12| and the 300
+best scores distinct; from 1.5 the activations grow through the depth (|raw| 52 ... 5e5) and every score saturates at exactly
+1.0 - round 1's default of 1.7 made the bench's top-k a 672 000-way tie (its mass-tie route), which is not what a
+trained or calibrated network gives the tail.
 """
 import math
 import zlib
@@ -12,7 +16,7 @@ import torch
 
 
 @torch.no_grad()
-def init_synthetic(model, seed=0, gain=1.7):
+def init_synthetic(model, seed=0, gain=1.3):
     sd = model.state_dict()
     for key, t in sd.items():
         g = torch.Generator().manual_seed((zlib.crc32(key.encode()) ^ (seed * 0x9E3779B1)) & 0x7FFFFFFF)
@@ -34,6 +38,12 @@ def init_synthetic(model, seed=0, gain=1.7):
             t.copy_((torch.rand(t.shape, generator=g) * 2 - 1) * a)
         elif leaf == "bias" and "cv3" in key:
             t.add_(0.5 * (torch.rand(t.shape, generator=g) - 0.5))      # per-class spread on top of bias_init
+        elif leaf == "bias" and not (".cv2." in key and key.startswith(("model.28", "model.23"))) and "one2one_cv2" not in key and ".cv2.2." not in key:
+            # every other conv bias (CBAM's fc, SPCA's pointwise ...) is left at nn.Conv2d's RANDOM default by the constructors:
+            # name-keyed values make two processes (two ranks) hold identical weights without sharing an RNG stream
+            t.copy_(0.2 * (torch.rand(t.shape, generator=g) - 0.5))
+        elif leaf == "weight" and t.dim() != 4 and t.is_floating_point():
+            t.copy_((torch.rand(t.shape, generator=g) * 2 - 1) * 0.1)
     if hasattr(model, "invalidate"):
         model.invalidate()
     return model
