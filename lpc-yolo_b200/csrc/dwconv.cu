@@ -697,8 +697,9 @@ extern "C" int lpc_sppf_pool(int dtype, const void* x, int x_ld, int B, int H, i
   LPC_REQUIRE(B <= 65535, "sppf_pool: batch too large");
   static const int chained = [] { const char* e = getenv("LPC_SPPF_CHAINED"); return e ? atoi(e) : 0; }();
   if (!chained && (size_t)H * W * 16 * 4 <= 100 * 1024) {
-    // direct two-pass kernel: four planes (input + three row-maxima planes) of one 16-byte channel vector per pixel
-    const int VP = 1;
+    // direct two-pass kernel: four planes (input + three row-maxima planes); two 16-byte channel vectors per pixel (whole 32-byte
+    // sectors on both the loads and the stores) when the planes still leave room for four CTAs per SM
+    const int VP = (C % (2 * V) == 0 && (size_t)H * W * 2 * 16 * 4 <= 56 * 1024) ? 2 : 1;
     const size_t smem = (size_t)H * W * VP * 16 * 4;
     dim3 grid(C / (VP * V), B);
     if (dtype == LPC_F32) {
