@@ -483,7 +483,9 @@ def main():
                 floors = [max(r[2] / (pk["tf_burst"] * 1e12), r[3] / (pk["hbm"] * 1e9)) for r in tcs]
                 hbm_side = sum(1 for r in tcs if r[3] / (pk["hbm"] * 1e9) >= r[2] / (pk["tf_burst"] * 1e12))
                 traffic = None
-                tpath = os.path.join(ROOT, "profiles", "r01_ncu_full_top_conv.json")
+                tpath = os.path.join(ROOT, "profiles", "r02_ncu_full_top_conv.json")
+                if not os.path.exists(tpath):
+                    tpath = os.path.join(ROOT, "profiles", "r01_ncu_full_top_conv.json")
                 if os.path.exists(tpath):
                     traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
                 roof = {"kernel": "conv_tc kernels (tcgen05 implicit-GEMM conv: taps / halo / CTA-pair halo; all dense-conv launches of one step)",
@@ -494,7 +496,7 @@ def main():
                         "hbm_achieved_gbs": round(by_tc / t_tc / 1e9, 1), "launches_hbm_side_of_ridge": hbm_side,
                         "frac_of_per_launch_rooflines": round(sum(floors) / t_tc, 4),
                         "timing": "all conv launches of one step captured in one CUDA graph, CUDA events around 10 replays",
-                        "traffic_note": "dram__bytes read+write of the largest conv launch, profiles/r01_ncu_full_top_conv.json (ncu --set full)"}
+                        "traffic_note": "dram__bytes read+write of the largest conv launch (16->32 3x3 @320x320), profiles/r02_ncu_full_top_conv.json (ncu --set full, profiles/r02_j_ncu_full.md)"}
             # what the fused stage-1 keys cost: the three class-branch convs with and without the rowmax epilogue
             rowmax_delta = None
             rm = [r for r in rec if r[0] == "conv2d_tc" and len(r) > 5 and r[5] is not None]
