@@ -8,7 +8,7 @@ The directory name carries a hyphen (it is the product name), so import it by st
     results = model.predict(images)            # images: float tensor [B,3,H,W] in [0,1]
 """
 from ._lib import LpcError, build, lib  # noqa: F401
-from .engine import YOLO, YOLOv10, Boxes, Results, YOLOv10DetectionPredictor  # noqa: F401
+from .engine import YOLO, YOLOv10, Boxes, Plan, Results, YOLOv10DetectionPredictor  # noqa: F401
 from .nn.tasks import YOLOv10DetectionModel, parse_model, yaml_model_load  # noqa: F401
 
 __version__ = "0.1.0"

@@ -24,6 +24,12 @@ SIGNATURES = {
     "lpc_last_error": (C.c_char_p, []),
     "lpc_device_arch": (_i, []),
     "lpc_launch_count": (C.c_ulonglong, []),
+    "lpc_plan_begin": (_i, []),
+    "lpc_plan_end": (_i, [C.POINTER(C.c_void_p)]),
+    "lpc_plan_size": (_i, [_p]),
+    "lpc_plan_run": (_i, [_p, _p]),
+    "lpc_plan_run_graph": (_i, [_p, _p]),
+    "lpc_plan_destroy": (None, [_p]),
     "lpc_conv2d_direct": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _f32p, _i, _i, _i, _i, _p, _i, _i, _f32p, _p, _i, _p]),
     "lpc_conv2d_tc": (_i, [_p, _i, _i, _i, _i, _i, _p, _f32p, _i, _i, _i, _i, _p, _i, _i, _f32p, _p, _i, _p]),
     "lpc_conv2d_tc_rowmax": (_i, [_p, _i, _i, _i, _i, _i, _p, _f32p, _i, _i, _i, _i, _p, _i, _i, _f32p, _p, _i, _p, _ll, _i, _p]),

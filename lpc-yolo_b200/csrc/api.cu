@@ -3,6 +3,7 @@
 #include <stdarg.h>
 
 #include <atomic>
+#include <vector>
 
 #include "common.cuh"
 
@@ -33,4 +34,85 @@ extern "C" int lpc_device_arch(void) {
   cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
   cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
   return major * 10 + minor;
+}
+
+// ---- launch plans: record a step once, replay it from C ---------------------------------------------------------------
+// The reference has no native executor (its layer loop is Python, nn/tasks.py:83-111); SURVEY.md section 8(b) proposes a
+// plan-level entry next to the per-op ones.  A plan here is the recorded launch sequence of whatever the host code issued
+// between lpc_plan_begin() and lpc_plan_end() on the calling thread (e.g. one YOLOv10DetectionModel.detect call): every
+// kernel with its grid, shared memory and argument block.  lpc_plan_run re-issues the sequence in issue order on ONE stream
+// (a valid serialisation of whatever streams the recording used); lpc_plan_run_graph captures that into a CUDA graph on its
+// first call and launches the graph afterwards.  All device buffers the recorded step used must still be alive and at the
+// same addresses (the caller records inside a private memory pool); the plan owns only host-side copies of the arguments.
+struct lpc_plan {
+  std::vector<std::function<cudaError_t(cudaStream_t)>> ops;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  cudaStream_t capture_stream = nullptr;
+};
+static thread_local lpc_plan* g_rec = nullptr;
+bool lpc_plan_recording() { return g_rec != nullptr; }
+void lpc_plan_push(std::function<cudaError_t(cudaStream_t)> op) {
+  if (g_rec) g_rec->ops.push_back(std::move(op));
+}
+
+extern "C" int lpc_plan_begin(void) {
+  if (g_rec) LPC_FAIL(LPC_E_ARG, "plan_begin: this thread is already recording");
+  g_rec = new lpc_plan();
+  return LPC_OK;
+}
+
+extern "C" int lpc_plan_end(lpc_plan** out) {
+  if (!g_rec) LPC_FAIL(LPC_E_ARG, "plan_end: this thread is not recording");
+  lpc_plan* p = g_rec;
+  g_rec = nullptr;
+  if (!out) {
+    delete p;
+    LPC_FAIL(LPC_E_ARG, "plan_end: null output");
+  }
+  *out = p;
+  return LPC_OK;
+}
+
+extern "C" int lpc_plan_size(const lpc_plan* p) { return p ? (int)p->ops.size() : LPC_E_ARG; }
+
+extern "C" int lpc_plan_run(lpc_plan* p, void* stream) {
+  LPC_REQUIRE(p, "plan_run: null plan");
+  LPC_REQUIRE(!g_rec, "plan_run: cannot replay while recording");
+  for (size_t i = 0; i < p->ops.size(); ++i) {
+    const cudaError_t e = p->ops[i]((cudaStream_t)stream);
+    if (e != cudaSuccess) LPC_FAIL(LPC_E_CUDA, "plan_run: launch %zu of %zu: %s", i, p->ops.size(), cudaGetErrorString(e));
+  }
+  return LPC_OK;
+}
+
+extern "C" int lpc_plan_run_graph(lpc_plan* p, void* stream) {
+  LPC_REQUIRE(p, "plan_run_graph: null plan");
+  LPC_REQUIRE(!g_rec, "plan_run_graph: cannot replay while recording");
+  if (!p->exec) {
+    if (cudaStreamCreateWithFlags(&p->capture_stream, cudaStreamNonBlocking) != cudaSuccess) LPC_FAIL(LPC_E_CUDA, "plan_run_graph: stream");
+    cudaError_t e = cudaStreamBeginCapture(p->capture_stream, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) LPC_FAIL(LPC_E_CUDA, "plan_run_graph: begin capture: %s", cudaGetErrorString(e));
+    cudaError_t le = cudaSuccess;
+    for (size_t i = 0; i < p->ops.size() && le == cudaSuccess; ++i) le = p->ops[i](p->capture_stream);
+    e = cudaStreamEndCapture(p->capture_stream, &p->graph);
+    if (le != cudaSuccess || e != cudaSuccess) {
+      if (p->graph) cudaGraphDestroy(p->graph);
+      p->graph = nullptr;
+      LPC_FAIL(LPC_E_CUDA, "plan_run_graph: capture: %s", cudaGetErrorString(le != cudaSuccess ? le : e));
+    }
+    e = cudaGraphInstantiate(&p->exec, p->graph, 0);
+    if (e != cudaSuccess) LPC_FAIL(LPC_E_CUDA, "plan_run_graph: instantiate: %s", cudaGetErrorString(e));
+  }
+  const cudaError_t e = cudaGraphLaunch(p->exec, (cudaStream_t)stream);
+  if (e != cudaSuccess) LPC_FAIL(LPC_E_CUDA, "plan_run_graph: launch: %s", cudaGetErrorString(e));
+  return LPC_OK;
+}
+
+extern "C" void lpc_plan_destroy(lpc_plan* p) {
+  if (!p) return;
+  if (p->exec) cudaGraphExecDestroy(p->exec);
+  if (p->graph) cudaGraphDestroy(p->graph);
+  if (p->capture_stream) cudaStreamDestroy(p->capture_stream);
+  delete p;
 }

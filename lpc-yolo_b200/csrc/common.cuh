@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <functional>
+#include <tuple>
 #include <utility>
 
 #include "../../include/lpcyolo.h"
@@ -37,7 +39,7 @@ void lpc_count_launch();
 // LPC_PDL=0 in the environment turns the attribute off (plain stream order).
 bool lpc_pdl_enabled();
 template <typename... KArgs, typename... Args>
-static inline cudaError_t lpc_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+static inline cudaError_t lpc_launch_raw(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -49,6 +51,23 @@ static inline cudaError_t lpc_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3
   cfg.attrs = attr;
   cfg.numAttrs = lpc_pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+// ---- plan recording (api.cu: lpc_plan_begin / lpc_plan_end / lpc_plan_run) -----------------------------------------
+// Every kernel of the library is launched through lpc_launch_pdl.  While the calling thread records a plan, each launch is
+// ALSO stored - kernel pointer, grid, block, shared memory and a by-value copy of the kernel arguments (parameter structs and
+// tensor maps included) - so that the whole launch sequence can be re-issued later from C, on any stream, without the host
+// code that produced it.
+bool lpc_plan_recording();
+void lpc_plan_push(std::function<cudaError_t(cudaStream_t)> op);
+template <typename... KArgs, typename... Args>
+static inline cudaError_t lpc_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  if (lpc_plan_recording()) {
+    std::tuple<std::decay_t<KArgs>...> saved(args...);
+    lpc_plan_push([kern, grid, block, smem, saved](cudaStream_t s) {
+      return std::apply([&](const auto&... a) { return lpc_launch_raw(kern, grid, block, smem, s, a...); }, saved);
+    });
+  }
+  return lpc_launch_raw(kern, grid, block, smem, stream, std::forward<Args>(args)...);
 }
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

@@ -511,6 +511,60 @@ class YOLOv10DetectionPredictor:
         return self.results
 
 
+class Plan:
+    """One recorded step of ``model.detect`` replayed from C (include/lpcyolo.h ``lpc_plan_*``): the layer loop, the concat
+    planning and the side-stream forks run ONCE in Python while the library records every launch; ``run()`` then re-issues the
+    launch sequence (as a CUDA graph captured inside the library) without any Python or torch code between the launches.
+    The recording runs inside a private torch memory pool, so every activation of the step keeps its address for the lifetime
+    of the plan; new inputs are written into ``self.x`` (the recorded input buffer), results appear in ``self.out``.
+
+        plan = Plan(yolo.model, x_example)      # x: [B,3,H,W] float in [0,1] (or an NHWC activation), on the device
+        plan.x.copy_(batch); plan.run(); dets = plan.out          # [B,max_det,6]
+    """
+
+    def __init__(self, model, x, max_det=300, clip=True):
+        import ctypes as C
+        from . import _lib
+        if not x.is_cuda:
+            raise F.LpcError("Plan: the example input must be on a CUDA device (no CPU fallback)")
+        self._L = _lib.lib()
+        self._h = C.c_void_p()
+        dev = x.device
+        with torch.no_grad(), torch.cuda.device(dev):
+            model.detect(x, max_det, clip=clip)                  # builds the packed weights outside the plan's pool
+            torch.cuda.synchronize(dev)
+            self._pool = torch.cuda.MemPool()
+            with torch.cuda.use_mem_pool(self._pool):
+                self.x = torch.empty_strided(x.shape, x.stride(), dtype=x.dtype, device=dev)      # keeps an NHWC view's pixel pitch
+                self.x.copy_(x)
+                _lib.check(self._L.lpc_plan_begin(), "plan_begin")
+                try:
+                    self.out = model.detect(self.x, max_det, clip=clip)
+                finally:
+                    _lib.check(self._L.lpc_plan_end(C.byref(self._h)), "plan_end")
+            torch.cuda.synchronize(dev)
+        self.device = dev
+        self.launches = int(self._L.lpc_plan_size(self._h))
+
+    def run(self, graph=True, stream=None):
+        """Re-issue the recorded launches on ``stream`` (default: torch's current stream of the plan's device)."""
+        import ctypes as C
+        from . import _lib
+        with torch.cuda.device(self.device):
+            st = C.c_void_p((stream or torch.cuda.current_stream(self.device)).cuda_stream)
+            fn = self._L.lpc_plan_run_graph if graph else self._L.lpc_plan_run
+            _lib.check(fn(self._h, st), "plan_run")
+        return self.out
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._L.lpc_plan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
 class YOLO:
     """models/yolo/model.py:11 YOLO / models/yolov10/model.py:10 YOLOv10 facade, predict side."""
 

@@ -232,3 +232,32 @@ def test_predict_api(pkg, oracle):
         gr.replay()
         torch.cuda.synchronize()
     assert torch.equal(out, eager)
+
+
+@pytest.mark.parametrize("name,B,S", [("lpc", 4, 320), ("yolov10n", 1, 640)])
+def test_launch_plan_replays_the_step_from_c(pkg, oracle, name, B, S):
+    """include/lpcyolo.h lpc_plan_*: one detect() recorded by the library, replayed from C (eagerly and as the library's own CUDA
+    graph) on fresh inputs == the Python-driven step, bit for bit; the plan holds exactly the step's launches."""
+    om, pm = _pair(pkg, oracle, name)
+    pm.compute_dtype = torch.bfloat16
+    x0 = oracle.synth_input(B, S).cuda()
+    x1 = oracle.synth_input(B, S, seed=7).cuda()
+    with torch.no_grad():
+        want0 = pm.detect(x0, 300).clone()
+        want1 = pm.detect(x1, 300).clone()
+        n0 = pkg.lib().lpc_launch_count()
+        pm.detect(x1, 300)
+        step_launches = pkg.lib().lpc_launch_count() - n0
+    plan = pkg.Plan(pm, x0, 300)
+    assert plan.launches == step_launches
+    assert torch.equal(plan.out, want0)                      # the recording pass itself
+    plan.x.copy_(x1)
+    assert torch.equal(plan.run(graph=False).clone(), want1)
+    plan.x.copy_(x0)
+    assert torch.equal(plan.run(graph=True).clone(), want0)
+    plan.x.copy_(x1)
+    plan.run(graph=True)
+    torch.cuda.synchronize()
+    assert torch.equal(plan.out, want1)
+    with pytest.raises(pkg.LpcError):          # not recording: plan_end reports it
+        importlib.import_module("lpc-yolo_b200._lib").check(pkg.lib().lpc_plan_end(None), "plan_end")
