@@ -228,7 +228,7 @@ int lpc_v10_postprocess(const float* preds, long long stride_b, long long stride
  * The reference's layer loop is Python (BaseModel._predict_once, nn/tasks.py:83-111).  A plan is the launch sequence of one
  * step, recorded once from whatever host code issues it and replayed from C: between lpc_plan_begin() and lpc_plan_end()
  * every kernel this thread launches through the library is stored with its grid, shared memory and a copy of its
- * arguments (the launches also run).  lpc_plan_run re-issues them in issue order on one stream; lpc_plan_run_graph
+ * arguments (the launches also run).  lpc_plan_run re-issues them with the recorded stream structure; lpc_plan_run_graph
  * captures that into a CUDA graph on first use and launches the graph afterwards.  The device buffers of the recorded
  * step must stay alive at the same addresses (record inside a private memory pool); inputs are refreshed by writing into
  * the recorded input buffer.  Returns 0 / a negative status; lpc_plan_size = number of recorded launches. */
@@ -236,6 +236,9 @@ typedef struct lpc_plan lpc_plan;
 int lpc_plan_begin(void);
 int lpc_plan_end(lpc_plan** plan);
 int lpc_plan_size(const lpc_plan* plan);
+/* while recording: stream `waiter` waits for everything issued so far on stream `signaler` (the host code's side-stream
+ * forks / joins); a no-op outside a recording */
+int lpc_plan_wait(void* waiter_stream, void* signaler_stream);
 int lpc_plan_run(lpc_plan* plan, void* stream);
 int lpc_plan_run_graph(lpc_plan* plan, void* stream);
 void lpc_plan_destroy(lpc_plan* plan);

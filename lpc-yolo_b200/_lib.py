@@ -27,6 +27,7 @@ SIGNATURES = {
     "lpc_plan_begin": (_i, []),
     "lpc_plan_end": (_i, [C.POINTER(C.c_void_p)]),
     "lpc_plan_size": (_i, [_p]),
+    "lpc_plan_wait": (_i, [_p, _p]),
     "lpc_plan_run": (_i, [_p, _p]),
     "lpc_plan_run_graph": (_i, [_p, _p]),
     "lpc_plan_destroy": (None, [_p]),

@@ -58,12 +58,12 @@ static inline cudaError_t lpc_launch_raw(void (*kern)(KArgs...), dim3 grid, dim3
 // tensor maps included) - so that the whole launch sequence can be re-issued later from C, on any stream, without the host
 // code that produced it.
 bool lpc_plan_recording();
-void lpc_plan_push(std::function<cudaError_t(cudaStream_t)> op);
+void lpc_plan_push(cudaStream_t recorded_on, std::function<cudaError_t(cudaStream_t)> op);
 template <typename... KArgs, typename... Args>
 static inline cudaError_t lpc_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
   if (lpc_plan_recording()) {
     std::tuple<std::decay_t<KArgs>...> saved(args...);
-    lpc_plan_push([kern, grid, block, smem, saved](cudaStream_t s) {
+    lpc_plan_push(stream, [kern, grid, block, smem, saved](cudaStream_t s) {
       return std::apply([&](const auto&... a) { return lpc_launch_raw(kern, grid, block, smem, s, a...); }, saved);
     });
   }
