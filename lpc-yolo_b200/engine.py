@@ -224,7 +224,9 @@ class YOLOv10DetectionPredictor:
             self.graphs, self.outs = [], []
             for i in range(2):
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                # torch.cuda.graph's default capture stream is ONE class-level stream created on whichever device was current
+                # first: capturing a cuda:1 model on it switches the current device back to cuda:0 inside the context
+                with torch.cuda.graph(g, stream=side):
                     out = run(self.inp[i])
                 self.graphs.append(g)
                 self.outs.append(out)

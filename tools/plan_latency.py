@@ -35,5 +35,5 @@ with torch.no_grad():
     t_plan = p50(lambda: plan.run(graph=True))
     t_eager = p50(lambda: plan.run(graph=False), 30)
     same = bool(torch.equal(plan.out, out))
-print(f"{name} B={B} @{S}: torch CUDA graph (multi-stream) {t_torch:.4f} ms | library plan graph (one stream, {plan.launches} launches) {t_plan:.4f} ms | "
+print(f"{name} B={B} @{S}: torch CUDA graph (multi-stream) {t_torch:.4f} ms | library plan graph ({plan.launches} launches, recorded stream structure) {t_plan:.4f} ms | "
       f"plan re-issued launch by launch from C {t_eager:.4f} ms | identical results {same}")
