@@ -853,7 +853,12 @@ extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W
     }
     const int stage_bytes = A_STAGE_BYTES + (tpair ? ((p.n_tile / 2 * 128 + 1023) & ~1023) : p.n_tile * 128);
     // two CTAs per SM when the double-buffered accumulators leave TMEM room, else one CTA with a deeper ring
-    const size_t budget = (p.tmem_cols <= 256) ? 100 * 1024 : SMEM_LIMIT;
+    // ... unless the launch has no more work items than SMs (batch 1, small maps): every CTA then walks its K loop alone, the
+    // second resident CTA would stay empty, and the loop's speed is (stages in flight) / (TMA latency) - take the deep ring.
+    static const int deep_env = [] { const char* e = getenv("LPC_TC_DEEP_RING"); return e ? atoi(e) : 1; }();
+    const long long items_est = (long long)p.tiles_x * p.tiles_y * p.B * (Cout / p.n_tile);
+    const bool few_items = deep_env && items_est <= num_sms();
+    const size_t budget = (p.tmem_cols <= 256 && !few_items) ? 100 * 1024 : SMEM_LIMIT;
     int stages = (int)(budget / stage_bytes);
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) stages = 2;
