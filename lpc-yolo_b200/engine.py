@@ -202,7 +202,9 @@ class YOLOv10DetectionPredictor:
         if not im.is_cuda:
             im = (im.pin_memory() if not im.is_pinned() else im).to(self.device, non_blocking=True)
         if im.dtype == torch.uint8:
-            return im.float() / 255
+            # tensor / tensor is an IEEE division on the device (tensor / python-scalar multiplies by the rounded reciprocal:
+            # 1 ulp off the reference's CPU ``im /= 255`` on some values)
+            return im.float() / torch.full((), 255.0, device=im.device)
         return im.float() if im.dtype != torch.float32 else im
 
     def inference(self, im):
