@@ -224,6 +224,7 @@ class YOLOv10DetectionPredictor:
                     run(self.inp[0])
             torch.cuda.current_stream(dev).wait_stream(side)
             self.graphs, self.outs = [], []
+            self.turn, self.done = 0, [None, None]      # next input buffer; "the replay that read buffer b has finished" events
             for i in range(2):
                 g = torch.cuda.CUDAGraph()
                 # torch.cuda.graph's default capture stream is ONE class-level stream created on whichever device was current
@@ -244,23 +245,24 @@ class YOLOv10DetectionPredictor:
         return self._graphed
 
     def _replay_chunks(self, im_host, plan, gds):
-        """Chunk i+1's host-to-device copy (copy stream) overlaps chunk i's graph replay (compute stream)."""
+        """Chunk i+1's host-to-device copy (copy stream) overlaps chunk i's graph replay (compute stream).  The two input
+        buffers of a graph alternate ACROSS calls and each remembers the event of the last replay that read it, so the copy
+        stream never waits for the compute stream as a whole: in a pipelined stream of batches (``stream_inference``) batch
+        k+1's copy runs under batch k's replay."""
         B = im_host.shape[0]
         if not im_host.is_pinned():
             im_host = im_host.pin_memory()
         cur = torch.cuda.current_stream(self.device)
         cs = self.__dict__.setdefault("_copy_stream", torch.cuda.Stream(device=self.device))
-        cs.wait_stream(cur)
         preds = torch.empty((B, self.args.max_det, 6), dtype=torch.float32, device=self.device)
-        used, done = {}, {}                           # graph object -> buffers already used in this call / replay-finished events
         lo = 0
         for cb, gd in zip(plan, gds):
-            b = used.get(id(gd), 0) & 1
-            used[id(gd)] = used.get(id(gd), 0) + 1
+            b = gd.turn & 1
+            gd.turn += 1
             ev = torch.cuda.Event()
             with torch.cuda.stream(cs):
-                if (id(gd), b) in done:
-                    cs.wait_event(done[(id(gd), b)])     # the replay that read this buffer has finished
+                if gd.done[b] is not None:
+                    cs.wait_event(gd.done[b])            # the replay that read this buffer has finished
                 gd.inp[b].copy_(im_host[lo:lo + cb], non_blocking=True)
                 ev.record(cs)
             cur.wait_event(ev)
@@ -268,14 +270,14 @@ class YOLOv10DetectionPredictor:
             preds[lo:lo + cb].copy_(gd.outs[b])
             d = torch.cuda.Event()
             d.record(cur)
-            done[(id(gd), b)] = d
+            gd.done[b] = d
             lo += cb
         return preds
 
-    def inference_from_host(self, im_host):
+    def inference_from_host(self, im_host, pipelined=False):
         """[B,3,H,W] fp32 host tensor -> [B,K,6] on the device, through the same chunk plan as the uint8 path."""
         B = im_host.shape[0]
-        plan = _chunk_plan(B)
+        plan = [B] if pipelined else _chunk_plan(B)
         cache = self._graph_cache()
         model, K, dev = self.model, self.args.max_det, self.device
         gds = []
@@ -334,12 +336,13 @@ class YOLOv10DetectionPredictor:
         scale = torch.tensor([row] * cb, dtype=torch.float32, device=dev) if row is not None else None
         return lambda inp: model.detect(self._prep_u8(inp, geom, tables), K, clip=True, scale_back=scale)
 
-    def inference_from_host_u8(self, im_host):
+    def inference_from_host_u8(self, im_host, pipelined=False):
         """[B,h,w,3] uint8 host tensor (BGR, one shape) -> [B,K,6] on the device in original-image coordinates.  Chunked
-        copy / replay overlap; the H2D copy moves 3 bytes per pixel instead of 12."""
+        copy / replay overlap; the H2D copy moves 3 bytes per pixel instead of 12.  ``pipelined`` (a stream of batches): one
+        whole-batch graph - the overlap then is between consecutive batches, and the second graph's fixed cost goes away."""
         B, hs, ws, _ = im_host.shape
         geom = self.letterbox_geometry((hs, ws), self.args.imgsz, int(max(self.model.stride)), auto=True)
-        plan = _chunk_plan(B)
+        plan = [B] if pipelined else _chunk_plan(B)
         cache = self._graph_cache()
         dev = self.device
         gds = []
@@ -410,14 +413,17 @@ class YOLOv10DetectionPredictor:
         return source.contiguous()
 
     def _host_copy(self, preds):
-        """Queue ONE device->host copy of the batched detections into a reused pinned buffer (stream order: behind the last
-        graph replay).  The copy gives the host path everything it needs - the per-image prefix lengths are counted from
-        it instead of by a device reduction plus a second, synchronous read - and it is what ``last_preds_host`` exposes
-        (valid until the next call)."""
-        buf = self.__dict__.get("_host_preds")
-        if buf is None or buf.shape != preds.shape or buf.dtype != preds.dtype:
-            buf = torch.empty(preds.shape, dtype=preds.dtype, pin_memory=True)
-            self._host_preds = buf
+        """Queue ONE device->host copy of the batched detections into a pinned buffer (stream order: behind the last graph
+        replay).  The copy gives the host path everything it needs - the per-image prefix lengths are counted from it
+        instead of by a device reduction plus a second, synchronous read - and it is what ``last_preds_host`` exposes.  The
+        buffers form a ring of three: a copy stays valid while the next two batches are queued (pipelined streams run one
+        batch ahead)."""
+        ring = self.__dict__.setdefault("_host_ring", [])
+        if not ring or ring[0].shape != preds.shape or ring[0].dtype != preds.dtype:
+            ring[:] = [torch.empty(preds.shape, dtype=preds.dtype, pin_memory=True) for _ in range(3)]
+            self._host_turn = 0
+        buf = ring[self._host_turn % 3]
+        self._host_turn += 1
         buf.copy_(preds, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(preds.device))
@@ -463,13 +469,55 @@ class YOLOv10DetectionPredictor:
         if self.model is None:
             raise RuntimeError("setup_model() first")
         with torch.cuda.device(self.device):          # the C library launches on the current device's streams
-            return self._call(source)
+            self.run_callbacks("on_predict_start")
+            res = self._finish(self._enqueue(source))
+            self.run_callbacks("on_predict_end")
+            return res
 
-    def _call(self, source):
+    @staticmethod
+    def source_len(source):
+        if isinstance(source, (list, tuple)):
+            return len(source)
+        if isinstance(source, np.ndarray):
+            return source.shape[0] if source.ndim == 4 else 1
+        return source.shape[0] if source.dim() == 4 else 1
+
+    def stream_inference(self, source, batch):
+        """engine/predictor.py:208-283 ``stream_inference`` for a source of MORE images than one batch: a generator of per-image
+        Results, ``batch`` images per step.  The steps are pipelined one batch ahead: batch k+1's host-to-device copy, graph
+        replay and result copy are queued before the host waits for batch k's detections, so in steady state the copy engine
+        works under the previous batch's kernels and the step time is max(copy, compute) instead of their sum.  The stage
+        timers do not synchronise the device here (``Results.speed`` holds host queueing times)."""
+        if self.model is None:
+            raise RuntimeError("setup_model() first")
+        n = self.source_len(source)
+        batch = max(1, int(batch))
+        if torch.is_tensor(source) and source.dim() == 3 or isinstance(source, np.ndarray) and source.ndim == 3:
+            source = source[None]
+        guard = lambda: torch.cuda.device(self.device)       # entered per call: a generator must not hold the caller's device
         self.run_callbacks("on_predict_start")
-        profilers = (Profile(self.device), Profile(self.device), Profile(self.device))
+        prev = None
+        for lo in range(0, n, batch):
+            with guard():
+                t = self._enqueue(source[lo:lo + batch], pipelined=True)
+            if prev is not None:
+                with guard():
+                    res = self._finish(prev)
+                yield from res
+            prev = t
+        if prev is not None:
+            with guard():
+                res = self._finish(prev)
+            yield from res
+        self.run_callbacks("on_predict_end")
+
+    def _enqueue(self, source, pipelined=False):
+        """Queue one batch (copies, launches, the result copy) without waiting for it -> ticket for ``_finish``."""
+        tdev = None if pipelined else self.device                  # pipelined: the timers must not drain the device
+        profilers = (Profile(tdev), Profile(tdev), Profile(tdev))
         self.batch = source
         self.run_callbacks("on_predict_batch_start")
+        host = None
         with torch.no_grad():
             if self._is_array_source(source):
                 mixed = isinstance(source, (list, tuple)) and len({tuple(np.shape(a)) for a in source}) > 1
@@ -483,27 +531,33 @@ class YOLOv10DetectionPredictor:
                     elif im.is_cuda:
                         preds = self.inference_u8_device(im)
                     else:
-                        preds = self.inference_from_host_u8(im)
+                        preds = self.inference_from_host_u8(im, pipelined)
                     host = self._host_copy(preds)
                 if isinstance(source, (list, tuple)):
                     orig = list(source)
                 else:                      # one [B,h,w,3] array / tensor: Results slice it on demand
                     orig = im if torch.is_tensor(source) else (source if source.ndim == 4 else source[None])
-                with profilers[2]:
-                    self.results = self.postprocess(preds, im, orig, host=host)
             else:
                 if torch.is_tensor(source) and not source.is_cuda and source.dtype == torch.float32 and source.dim() == 4:
                     with profilers[0]:
                         im = check_tensor_source(source)
                     with profilers[1]:
-                        preds = self.inference_from_host(im)
+                        preds = self.inference_from_host(im, pipelined)
+                        if pipelined:
+                            host = self._host_copy(preds)
                 else:
                     with profilers[0]:
                         im = self.preprocess(source)
                     with profilers[1]:
                         preds = self.inference(im)
-                with profilers[2]:
-                    self.results = self.postprocess(preds, im, im)
+                orig = im
+        return (preds, im, orig, host, profilers)
+
+    def _finish(self, ticket):
+        """Wait for a queued batch's detections and wrap them (postprocess + callbacks of the reference's batch loop)."""
+        preds, im, orig, host, profilers = ticket
+        with torch.no_grad(), profilers[2]:
+            self.results = self.postprocess(preds, im, orig, host=host)
         self.run_callbacks("on_predict_postprocess_end")
         n = max(len(self.results), 1)
         speed = {"preprocess": profilers[0].dt * 1e3 / n, "inference": profilers[1].dt * 1e3 / n,
@@ -511,7 +565,6 @@ class YOLOv10DetectionPredictor:
         for r in self.results:
             r.speed = speed
         self.run_callbacks("on_predict_batch_end")
-        self.run_callbacks("on_predict_end")
         return self.results
 
 
@@ -638,6 +691,15 @@ class YOLO:
             self.predictor = (predictor or YOLOv10DetectionPredictor)(overrides=args, _callbacks=self.callbacks)
             self.predictor.setup_model(self.model)
             self._last_args = dict(args)
+        # engine/predictor.py:188-206: ``stream=True`` -> generator of Results, else the list.  ``batch`` (LoadPilAndNumpy's
+        # batch size, data/build.py:157) splits a longer source into steps ONLY when it is passed: without it the whole source
+        # is one batch (the reference's default of 1 would run image by image - same detections, 64 times the launches).
+        n = self.predictor.source_len(source)
+        if "batch" in args and n > int(args["batch"]):
+            gen = self.predictor.stream_inference(source, int(args["batch"]))
+            return gen if stream else list(gen)
+        if stream:
+            return iter(self.predictor(source))
         return self.predictor(source)
 
     __call__ = predict
