@@ -8,7 +8,7 @@ synthetic batch.  N=1 workload = BASELINE.json configs[1]: the LPC-YOLO YAML, 64
   value     whole-job images/s, inputs resident in HBM (bf16 NHWC), CUDA-graph replay, CUDA-event timed, max over ranks
   e2e       same metric through YOLO(...).predict(host arrays): pinned host uint8 HWC BGR images -> H2D -> /255 + BGR->RGB +
             NHWC pack -> network -> fused tail -> D2H of [B,300,6], everything inside the timed region.  value = ONE
-            predict(source of 16 x B distinct images, batch=B, stream=True) call per 16 steps (the reference's own way to run
+            predict(source of 32 x B distinct images, batch=B, stream=True) call per 32 steps (the reference's own way to run
             many batches, engine/predictor.py:208; every step copies its own images in and its detections out, the predictor
             queues one step ahead); e2e.single_call = one synchronous predict(B images) per step
   roofline  dominant kernel = conv_tc_kernel (tcgen05 implicit GEMM): algorithmic FLOPs of the dense convs it ran in one
@@ -270,7 +270,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--other-budget", type=float, default=75.0, help="seconds for BASELINE configs 3-5 (0 = skip them)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end leg (default: max(50, --steps))")
-    ap.add_argument("--e2e-stream-batches", type=int, default=16, help="batches per streamed predict() call of the e2e leg")
+    ap.add_argument("--e2e-stream-batches", type=int, default=32, help="batches per streamed predict() call of the e2e leg")
     args = ap.parse_args()
     # stdout carries exactly ONE line, the JSON record: everything else any library writes to fd 1 (NCCL prints its version
     # banner there) goes to stderr for the rest of the process; emit() writes the record to the real stdout.

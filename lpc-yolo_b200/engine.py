@@ -24,6 +24,7 @@ from .nn.tasks import YOLOv10DetectionModel
 DEFAULTS = dict(conf=0.25, max_det=300, classes=None, half=True, device=None, verbose=False, imgsz=640, batch=1,
                 augment=False, visualize=False, embed=None, stream=False, fp32=False)
 _HALF_WARNED = False
+_SKIP_H2D = __import__("os").environ.get("LPC_E2E_SKIP_H2D") == "1"      # measurement only: what the copy costs the stream
 CALLBACK_EVENTS = ("on_predict_start", "on_predict_batch_start", "on_predict_postprocess_end", "on_predict_batch_end",
                    "on_predict_end")
 
@@ -263,7 +264,8 @@ class YOLOv10DetectionPredictor:
             with torch.cuda.stream(cs):
                 if gd.done[b] is not None:
                     cs.wait_event(gd.done[b])            # the replay that read this buffer has finished
-                gd.inp[b].copy_(im_host[lo:lo + cb], non_blocking=True)
+                if not _SKIP_H2D:
+                    gd.inp[b].copy_(im_host[lo:lo + cb], non_blocking=True)
                 ev.record(cs)
             cur.wait_event(ev)
             gd.graphs[b].replay()
@@ -494,20 +496,23 @@ class YOLOv10DetectionPredictor:
         batch = max(1, int(batch))
         if torch.is_tensor(source) and source.dim() == 3 or isinstance(source, np.ndarray) and source.ndim == 3:
             source = source[None]
+        import os
+        from collections import deque
+        depth = max(1, int(os.environ.get("LPC_STREAM_DEPTH", "1")))   # steps queued ahead of the one the host waits for (<= 2:
+        depth = min(depth, 2)                                           # three pinned result buffers, two input buffers per graph)
         guard = lambda: torch.cuda.device(self.device)       # entered per call: a generator must not hold the caller's device
         self.run_callbacks("on_predict_start")
-        prev = None
+        queued = deque()
         for lo in range(0, n, batch):
             with guard():
-                t = self._enqueue(source[lo:lo + batch], pipelined=True)
-            if prev is not None:
+                queued.append(self._enqueue(source[lo:lo + batch], pipelined=True))
+            if len(queued) > depth:
                 with guard():
-                    res = self._finish(prev)
+                    res = self._finish(queued.popleft())
                 yield from res
-            prev = t
-        if prev is not None:
+        while queued:
             with guard():
-                res = self._finish(prev)
+                res = self._finish(queued.popleft())
             yield from res
         self.run_callbacks("on_predict_end")
 
