@@ -93,6 +93,16 @@ int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W, int Cin, 
 /* 1 if lpc_conv2d_tc accepts this shape, else 0. */
 int lpc_conv2d_tc_supported(int Cin, int Cout, int k, int stride, int pad, int x_ld, int y_ld);
 
+/* Conv 3x3 s1 (Cin 16 -> 32) fused with the space_to_depth + 1x1 conv that follows it in the SPD-Conv stem of the LPC YAML
+ * (layers 1-3: conv.Conv(16,32,3,1) -> space_to_depth -> C2f.cv1; reference nn/modules/conv.py:36-54, nn/modules/block.py:4063-4070
+ * space_to_depth, block.py:226-230 C2f.forward): y[B,H/2,W/2,C2] = act2(W2 * s2d(act1(W1 * x + b1)) + b2), where w2 is the 1x1
+ * conv re-packed as a 2x2 stride-2 conv ([C2][kpad(32,2)=128], K = (ky, kx, c)) and w1 is lpc_conv2d_tc's [32][kpad(16,3)=192].
+ * The 32-channel intermediate (419 MB at 320x320 batch 64) stays in shared memory.  bf16 only; results are bit-identical to
+ * lpc_conv2d_tc(k=3) followed by lpc_conv2d_tc(k=2, s=2).  _supported: Cin == 16, C1 == 32, C2 % 16 == 0, C2 <= 64, even H and W. */
+int lpc_conv3x3_s2d_tc_supported(int Cin, int C1, int C2, int H, int W, int x_ld, int y_ld);
+int lpc_conv3x3_s2d_tc(const void* x, int x_ld, int B, int H, int W, int Cin, const void* w1, const float* bias1, int C1, int act1,
+                       const void* w2, const float* bias2, int C2, int act2, void* y, int y_ld, void* stream);
+
 /* Depthwise 3x3 (stride 1, pad 1, bias, dw_act) -> pointwise 1x1 (C1, bias, act1) [-> pointwise 1x1 (C2, bias, act2)] as
  * ONE tcgen05 kernel: the depthwise result is written straight into the shared-memory A operand of the 1x1 GEMM, and
  * the first GEMM's activated output into the A operand of the second; nothing between x and y touches HBM.  Replaces

@@ -565,6 +565,7 @@ conv_tc_halo_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
 }
 
 #include "conv_tc_pair.cuh"
+#include "conv_tc_s2d.cuh"
 
 // ---- host side -------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -977,5 +978,86 @@ extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W
       fflush(stdout);
     }
   }
+  return LPC_OK;
+}
+
+// ---- Conv 3x3 s1 fused with the following space_to_depth + 1x1 conv (= 2x2 stride-2 conv), conv_tc_s2d.cuh -------------
+extern "C" int lpc_conv3x3_s2d_tc_supported(int Cin, int C1, int C2, int H, int W, int x_ld, int y_ld) {
+  static const int on = [] { const char* e = getenv("LPC_TC_S2D"); return e ? atoi(e) : 1; }();
+  if (!on) return 0;
+  if (Cin != S2D_CIN || C1 != S2D_N1) return 0;
+  if (C2 <= 0 || C2 % 16 || C2 > 64) return 0;
+  if (H <= 0 || W <= 0 || H % 2 || W % 2) return 0;
+  if (x_ld % 8 || y_ld % 8) return 0;
+  return 1;
+}
+
+extern "C" int lpc_conv3x3_s2d_tc(const void* x, int x_ld, int B, int H, int W, int Cin, const void* w1, const float* bias1, int C1,
+                                  int act1, const void* w2, const float* bias2, int C2, int act2, void* y, int y_ld, void* stream) {
+  LPC_REQUIRE(x && w1 && w2 && y, "conv3x3_s2d_tc: null pointer");
+  LPC_REQUIRE(B > 0, "conv3x3_s2d_tc: bad shape");
+  if (!lpc_conv3x3_s2d_tc_supported(Cin, C1, C2, H, W, x_ld, y_ld))
+    LPC_FAIL(LPC_E_UNSUPPORTED, "conv3x3_s2d_tc: unsupported shape Cin=%d C1=%d C2=%d H=%d W=%d x_ld=%d y_ld=%d", Cin, C1, C2, H, W, x_ld, y_ld);
+  LPC_REQUIRE(aligned16(x) && aligned16(w1) && aligned16(w2) && aligned16(y), "conv3x3_s2d_tc: pointers must be 16-byte aligned");
+  LPC_REQUIRE((long long)H * W * x_ld < (1ll << 31), "conv3x3_s2d_tc: image too large for 32-bit offsets");
+  EncodeTiledFn enc = get_encode();
+  if (!enc) LPC_FAIL(LPC_E_CUDA, "conv3x3_s2d_tc: cuTensorMapEncodeTiled not available");
+  S2dParams p;
+  memset(&p, 0, sizeof(p));
+  TmapPack maps;
+  memset(&maps, 0, sizeof(maps));
+  p.H = H; p.W = W; p.B = B;
+  p.Ho = H / 2; p.Wo = W / 2;
+  p.st_x = (W + 2 * HALO_TW - 1) / (2 * HALO_TW);
+  p.st_y = (H + 2 * HALO_TH - 1) / (2 * HALO_TH);
+  const long long n_super = (long long)p.st_x * p.st_y * B;
+  LPC_REQUIRE(n_super < (1 << 22), "conv3x3_s2d_tc: too many tiles");
+  p.n_super = (int)n_super;
+  p.inv_per_img = 1.0f / (float)(p.st_x * p.st_y);
+  p.inv_st_x = 1.0f / (float)p.st_x;
+  p.n2 = C2;
+  p.acc2_cols = C2 <= 32 ? 32 : 64;
+  p.tmem_cols = 256;
+  p.act1 = act1; p.act2 = act2;
+  p.bias1 = bias1; p.bias2 = bias2;
+  p.y = (bf16*)y; p.y_ld = y_ld;
+  const size_t fixed = (size_t)ONES_BYTES + S2D_N1 * 32 + (size_t)C2 * 32 + 1024 + S2D_W1_BYTES + 2 * (size_t)C2 * 128 + 2 * S2D_A2_BYTES + 1024;
+  {
+    static const int ab_env = [] { const char* e = getenv("LPC_TC_S2D_ABUFS"); return e ? atoi(e) : 0; }();
+    int ab = (int)(((size_t)110 * 1024 - fixed) / S2D_PATCH_BYTES);          // two CTAs per SM
+    if (ab_env > 0) ab = ab_env;
+    p.a_bufs = ab > MAX_STAGES ? MAX_STAGES : (ab < 2 ? 2 : ab);
+  }
+  const size_t smem = fixed + (size_t)p.a_bufs * S2D_PATCH_BYTES;
+  if (int e = encode_act_map(&maps.a[0], (const bf16*)x, Cin, W, H, B, x_ld, (long long)W * x_ld, (long long)H * W * x_ld, Cin, HALO_SPW, HALO_PH,
+                             swizzle_of(Cin)))
+    return e;
+  auto weight_map = [&](CUtensorMap* m, const void* w, int kpad, int rows) -> int {
+    cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)kpad * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) LPC_FAIL(LPC_E_CUDA, "conv3x3_s2d_tc: weight tensor map encode failed (CUresult %d)", (int)r);
+    return LPC_OK;
+  };
+  if (int e = weight_map(&maps.b, w1, lpc_conv2d_tc_kpad(Cin, 3), C1)) return e;          // [32][192]
+  if (int e = weight_map(&maps.a[1], w2, lpc_conv2d_tc_kpad(C1, 2), C2)) return e;        // [C2][128], K = (ky, kx, c)
+  static unsigned long long attr_set = 0;     // per device
+  if (lpc_first_on_device(&attr_set)) {
+    const int lim = (int)SMEM_LIMIT + 16 * 1024;
+    cudaError_t e1 = cudaFuncSetAttribute(conv_tc_s2d_kernel<LPC_ACT_SILU, LPC_ACT_MISH>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(conv_tc_s2d_kernel<-1, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    if (e1 != cudaSuccess) { attr_set = 0; LPC_FAIL(LPC_E_CUDA, "conv3x3_s2d_tc: smem attribute: %s", cudaGetErrorString(e1)); }
+  }
+  const int ctas_per_sm = smem <= 110 * 1024 ? 2 : 1;
+  long long grid = (long long)num_sms() * ctas_per_sm;
+  if (grid > n_super) grid = n_super;
+  if (act1 == LPC_ACT_SILU && act2 == LPC_ACT_MISH)
+    lpc_launch_pdl(conv_tc_s2d_kernel<LPC_ACT_SILU, LPC_ACT_MISH>, (unsigned)grid, 320u, smem, (cudaStream_t)stream, maps, p);
+  else
+    lpc_launch_pdl(conv_tc_s2d_kernel<-1, -1>, (unsigned)grid, 320u, smem, (cudaStream_t)stream, maps, p);
+  LPC_CHECK_LAUNCH("conv3x3_s2d_tc");
   return LPC_OK;
 }

@@ -287,6 +287,40 @@ def conv2d(x, pc, out=None, res=None, chan_scale=None, rowmax=None):
     return out
 
 
+def conv3x3_s2d_supported(x, pc1, pc2, out_ld=None):
+    """Can conv3x3(pc1) -> space_to_depth -> conv1x1 (pc2 = its 2x2 stride-2 re-packing) run as ONE kernel (lpc_conv3x3_s2d_tc)?"""
+    if x.dtype != torch.bfloat16 or pc1.w_tc is None or pc2.w_tc is None:
+        return False
+    if (pc1.k, pc1.s, pc1.p) != (3, 1, 1) or (pc2.k, pc2.s, pc2.p) != (2, 2, 0) or pc2.cin != pc1.cout:
+        return False
+    B, Cin, H, W = x.shape
+    xp, xld = view_of(x)
+    return xp % 16 == 0 and bool(_lib.lib().lpc_conv3x3_s2d_tc_supported(Cin, pc1.cout, pc2.cout, H, W, xld, out_ld if out_ld is not None else pc2.cout))
+
+
+def conv3x3_s2d(x, pc1, pc2, out=None):
+    """act2(conv2x2s2(act1(conv3x3(x)))) without writing the 3x3 conv's output; callers check ``conv3x3_s2d_supported``."""
+    B, Cin, H, W = x.shape
+    if out is None:
+        out = new_act(B, pc2.cout, H // 2, W // 2, x.dtype, x.device)
+    assert tuple(out.shape) == (B, pc2.cout, H // 2, W // 2)
+    xp, xld = view_of(x)
+    yp, yld = view_of(out)
+    L = _lib.lib()
+    flops = 2.0 * B * H * W * pc1.cout * Cin * 9 + 2.0 * B * (H // 2) * (W // 2) * pc2.cout * pc2.cin * 4
+    nbytes = x.element_size() * (B * H * W * Cin + B * (H // 2) * (W // 2) * pc2.cout)
+    tag = f"{Cin}->{pc1.cout} k3s1 + s2d {4 * pc1.cout}->{pc2.cout} {H}x{W} B{B}"
+
+    def launch(keep=(x, out, pc1, pc2)):
+        check(L.lpc_conv3x3_s2d_tc(xp, xld, B, H, W, Cin, _fp(pc1.w_tc), _fp(pc1.bias), pc1.cout, pc1.act, _fp(pc2.w_tc), _fp(pc2.bias),
+                                   pc2.cout, pc2.act, yp, yld, _stream()), "conv3x3_s2d_tc")
+    if REPLAY is not None:
+        REPLAY.append(("conv2d_tc", launch, flops, nbytes, tag, None))
+    with _prof("conv3x3_s2d_tc", flops, nbytes, tag):
+        launch()
+    return out
+
+
 @_profiled
 def dwconv2d(x, pd, out=None, res=None):
     B, Cc, H, W = x.shape

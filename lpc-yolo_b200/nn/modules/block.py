@@ -81,9 +81,10 @@ class C2f(LpcModule):
         self.cv2 = Conv((2 + n) * self.c, c2, 1)
         self.m = nn.ModuleList(Bottleneck(self.c, self.c, shortcut, g, k=((3, 3), (3, 3)), e=1.0) for _ in range(n))
 
-    def forward(self, x, out=None, s2d=False):
+    def forward(self, x, out=None, s2d=False, pre=None):
         """``s2d=True``: x is the tensor BEFORE a space_to_depth layer; cv1 then runs as a 2x2 stride-2 conv
-        (the s2d + 1x1 fold), so the 4x-channel tensor is never written."""
+        (the s2d + 1x1 fold), so the 4x-channel tensor is never written.  ``pre`` (with s2d): the stride-1 Conv layer in
+        front of the space_to_depth, x being ITS input: conv -> s2d -> cv1 then is one kernel where the shape is taken."""
         x = self._in(x)
         B, _, H, W = x.shape
         if s2d:
@@ -91,7 +92,7 @@ class C2f(LpcModule):
         c, n = self.c, len(self.m)
         ybuf = F.new_act(B, (2 + n) * c, H, W, x.dtype, x.device)
         if s2d:
-            self.cv1.forward_s2d(x, out=ybuf[:, : 2 * c])
+            self.cv1.forward_s2d(x, out=ybuf[:, : 2 * c], pre=pre)
         else:
             self.cv1(x, out=ybuf[:, : 2 * c])
         for i, m in enumerate(self.m):

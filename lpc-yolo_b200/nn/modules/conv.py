@@ -54,16 +54,28 @@ class Conv(LpcModule):
         w2 = w.view(cout, 2, 2, c).permute(0, 3, 2, 1).contiguous()      # [co, kx, ky, c] -> [co, c, ky, kx]
         return pack.PackedConv(w2, b, 2, 2, 0, act_code(self.act), dtype, device)
 
-    def forward_s2d(self, x, out=None):
-        """conv1x1(space_to_depth(x)) without materialising the space_to_depth tensor."""
-        assert self.conv.kernel_size == (1, 1) and self.conv.groups == 1 and self.conv.in_channels == 4 * x.shape[1]
-        x = self._in(x)
-        key = ("s2d", x.dtype, x.device)
+    def _packed_s2d(self, dtype, device):
+        key = ("s2d", dtype, device)
         pk = self._pcache.get(key)
         if pk is None:
             with torch.no_grad():
-                pk = self._pcache[key] = self._build_s2d(x.dtype, x.device)
-        return F.conv2d(x, pk, out)
+                pk = self._pcache[key] = self._build_s2d(dtype, device)
+        return pk
+
+    def forward_s2d(self, x, out=None, pre=None):
+        """conv1x1(space_to_depth(x)) without materialising the space_to_depth tensor.  ``pre``: the Conv module that
+        produces x from ITS input (then x is that input): 3x3 conv -> s2d -> this 1x1 as one kernel when the shape is taken
+        (lpc_conv3x3_s2d_tc), else the two launches."""
+        x = self._in(x)
+        if pre is not None:
+            pk1 = pre._packed(x, pre._build)
+            assert self.conv.kernel_size == (1, 1) and self.conv.groups == 1 and self.conv.in_channels == 4 * pre.conv.out_channels
+            pk2 = self._packed_s2d(x.dtype, x.device)
+            if isinstance(pk1, pack.PackedConv) and F.conv3x3_s2d_supported(x, pk1, pk2, F.view_of(out)[1] if out is not None else None):
+                return F.conv3x3_s2d(x, pk1, pk2, out)
+            x = pre(x)
+        assert self.conv.kernel_size == (1, 1) and self.conv.groups == 1 and self.conv.in_channels == 4 * x.shape[1]
+        return F.conv2d(x, self._packed_s2d(x.dtype, x.device), out)
 
     def out_shape(self, s):
         B, _, H, W = s

@@ -160,7 +160,17 @@ class BaseModel(LpcModule):
                 cons = consumers[m.i]
                 if len(cons) == 1 and type(L[cons[0]]) is C2f and L[cons[0]].f == -1 and m.i not in self.save:
                     fold[m.i] = cons[0]
-        self._plan_cache = (dest, live, fold)
+        # ... and a plain stride-1 3x3 Conv whose only consumer is such a folded space_to_depth runs INSIDE that C2f call
+        # (conv -> s2d -> cv1 as one kernel where the C library takes the shape, else the same two launches as before)
+        prefold = {}
+        if self.front_depth <= 0:
+            for i, j in fold.items():
+                c = L[i - 1] if i > 0 else None
+                if (type(c) is Conv and L[i].f == -1 and c.f == -1 and consumers[i - 1] == [i] and (i - 1) not in self.save
+                        and (i - 1) not in dest and i - 1 > 0 and j == i + 1
+                        and c.conv.kernel_size == (3, 3) and c.conv.stride == (1, 1) and c.conv.groups == 1):
+                    prefold[i - 1] = j
+        self._plan_cache = (dest, live, fold, prefold)
         return self._plan_cache
 
     def _predict_once(self, x, tail=None):
@@ -172,7 +182,7 @@ class BaseModel(LpcModule):
             # current device is cuda:0 would launch there with device-1 pointers
             with torch.cuda.device(x.device):
                 return self._predict_once(x, tail)
-        dest, live, fold = self._plan()
+        dest, live, fold, prefold = self._plan()
         if x.dtype not in (torch.bfloat16, torch.float32) or not F.is_nhwc_view(x) or x.dtype != self.compute_dtype:
             x = F.pack_input(x.float().contiguous(), self.compute_dtype) if x.shape[1] <= 4 else F.as_act(x, self.compute_dtype)
         y, catbuf = [], {}
@@ -186,11 +196,11 @@ class BaseModel(LpcModule):
             if m.i not in live:
                 y.append(None)
                 continue
-            if m.i in fold:            # skipped: the consumer reads our INPUT and applies the s2d fold
+            if m.i in fold or m.i in prefold:      # skipped: the consumer reads our INPUT (s2d fold / conv + s2d fusion)
                 y.append(None)
                 continue
             if m.i - 1 in fold and fold[m.i - 1] == m.i:
-                x = m(x, s2d=True)
+                x = m(x, s2d=True, pre=L[m.i - 2] if prefold.get(m.i - 2) == m.i else None)
                 y.append(x if m.i in self.save else None)
                 continue
             if m.f != -1:

@@ -160,6 +160,44 @@ def test_conv3x3_both_tc_kernels(M, oracle, pkg, mode, case):
     _cmp(got, ref, torch.bfloat16, f"conv3x3 mode {mode} {case}")
 
 
+@pytest.mark.parametrize("case", [(2, 64, 64, 32, "mish"), (3, 48, 40, 32, "mish"), (1, 34, 18, 64, "mish"), (5, 320, 320, 32, "mish"),
+                                  (2, 96, 160, 48, "silu"), (9, 160, 96, 16, "mish")])
+def test_conv3x3_s2d_fused_equals_two_launches(M, Fn, pkg, case):
+    """lpc_conv3x3_s2d_tc (Conv 3x3 16->32 -> space_to_depth -> 1x1 conv as ONE kernel, the 32-channel map stays in shared
+    memory) against the two launches it replaces (halo 3x3 kernel, then the 2x2 stride-2 fold of s2d + 1x1): bit-identical -
+    same bf16 rounding of the intermediate, same K order in the tensor core.  Ragged maps (partial supertiles), more
+    supertiles than persistent CTAs (5 x 320 x 320 = 1000 on 296), C2 = 16 / 32 / 48 / 64, compile-time and run-time acts."""
+    B, H, W, c2, act2 = case
+    blk = importlib.import_module("lpc-yolo_b200.nn.modules.block")
+    pre = _randomize(M.Conv(16, 32, 3, 1), seed=B + H).cuda()                   # conv.Conv: SiLU
+    cv1 = _randomize((blk.Conv if act2 == "mish" else M.Conv)(128, c2, 1, 1), seed=W + c2).cuda()      # block.Conv: Mish
+    x = Fn.as_act(_x((B, 16, H, W), torch.bfloat16).cuda(), torch.bfloat16)
+    with torch.no_grad():
+        want = cv1.forward_s2d(pre(x))
+        pk1, pk2 = pre._packed(x, pre._build), cv1._packed_s2d(x.dtype, x.device)
+        assert Fn.conv3x3_s2d_supported(x, pk1, pk2)
+        got = cv1.forward_s2d(x, pre=pre)
+        buf = Fn.new_act(B, c2 + 16, H // 2, W // 2, torch.bfloat16, x.device)          # into a channel slice of a wider buffer
+        buf.fill_(7.0)
+        cv1.forward_s2d(x, out=buf[:, :c2], pre=pre)
+    torch.cuda.synchronize()
+    assert got.shape == want.shape == (B, c2, H // 2, W // 2)
+    assert torch.equal(got, want), f"max diff {(got.float() - want.float()).abs().max().item():.3e}"
+    assert torch.equal(buf[:, :c2], want) and bool((buf[:, c2:] == 7.0).all())
+
+
+def test_conv3x3_s2d_unsupported_shapes_take_two_launches(M, Fn, pkg):
+    """fp32 inputs, other channel counts and odd maps are not taken by the fused kernel: same call, two launches."""
+    blk = importlib.import_module("lpc-yolo_b200.nn.modules.block")
+    for cin, c1, H, dtype in ((32, 64, 32, torch.bfloat16), (16, 32, 32, torch.float32)):
+        pre = _randomize(M.Conv(cin, c1, 3, 1), seed=1).cuda()
+        cv1 = _randomize(blk.Conv(4 * c1, 32, 1, 1), seed=2).cuda()
+        x = Fn.as_act(_x((2, cin, H, H), dtype).cuda(), dtype)
+        with torch.no_grad():
+            assert not Fn.conv3x3_s2d_supported(x, pre._packed(x, pre._build), cv1._packed_s2d(x.dtype, x.device))
+            assert torch.equal(cv1.forward_s2d(x, pre=pre), cv1.forward_s2d(pre(x)))
+
+
 def test_conv1x1_many_tiles(M, oracle):
     """Persistent 1x1 kernel: 3200 M tiles over ~300 CTAs, two N tiles, residual epilogue."""
     mod = _randomize(M.Conv(64, 512, 1, 1), seed=5)

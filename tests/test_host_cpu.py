@@ -53,8 +53,9 @@ def test_lpc_yaml_quirks(pkg, oracle):
     m = _model(pkg, oracle, "lpc")
     det = m.model[-1]
     assert det.f == [20, 23, 26] and [s[0].conv.in_channels for s in det.cv2] == [64, 192, 384]
-    dest, live, fold = m._plan()
+    dest, live, fold, prefold = m._plan()
     assert fold == {2: 3, 5: 6, 8: 9, 11: 12}
+    assert prefold == {1: 3, 4: 6}      # a stride-1 3x3 Conv whose ONLY consumer is a folded space_to_depth runs inside the C2f call (7, 10 also feed Concats)
     assert 27 not in live                       # dead layer is skipped
     assert m.yaml["scale"] == ""                # scale falls back to the first key
     assert dest[15] == (16, 0) and dest[10][0] == 16 and dest[22] == (23, 0) and dest[17][0] == 23
