@@ -30,6 +30,7 @@ struct S2dParams {
   int st_x, st_y, n_super;   // supertiles per row / column / in total
   float inv_per_img, inv_st_x;
   int n2, acc2_cols, tmem_cols, a_bufs;
+  int l2_prefetch;           // the producer pulls the next supertile's patches into L2 ahead of their loads
   int act1, act2;
   const float* bias1;
   const float* bias2;
@@ -136,12 +137,26 @@ conv_tc_s2d_kernel(const __grid_constant__ TmapPack maps, const __grid_constant_
       for (int ks = 0; ks < 3; ++ks) tma_load_2d(w1_addr + (uint32_t)(ks * S2D_N1 * 128), &maps.b, bfull_bar, ks * 64, 0);
       for (int ks = 0; ks < 2; ++ks) tma_load_2d(w2_addr + (uint32_t)ks * w2_block, &maps.a[1], bfull_bar, ks * 64, 0);
       pdl_wait();                               // activations of the previous kernel
+      // Two patch buffers per CTA is all the shared memory leaves next to the double-buffered A2, i.e. ~2 x 9 KB in flight per
+      // CTA against an HBM latency of ~1 us: the patches of the supertile AFTER the current one are pulled into L2 ahead of
+      // time (TMA prefetch, no shared memory needed), so the loads below hit L2.
+      auto prefetch_super = [&](int s) {
+        if (s >= p.n_super || !p.l2_prefetch) return;
+        const int img = fast_div(s, per_img, p.inv_per_img);
+        const int rem = s - img * per_img;
+        const int sy = fast_div(rem, p.st_x, p.inv_st_x);
+        const int sx = rem - sy * p.st_x;
+        for (int t = 0; t < 4; ++t)
+          tma_prefetch_4d(&maps.a[0], 0, sx * (2 * HALO_TW) + (t & 1) * HALO_TW - 1, sy * (2 * HALO_TH) + (t >> 1) * HALO_TH - 1, img);
+      };
+      prefetch_super(s_first);
       int v = 0;
       for (int s = s_first; s < p.n_super; s += s_step) {
         const int img = fast_div(s, per_img, p.inv_per_img);
         const int rem = s - img * per_img;
         const int sy = fast_div(rem, p.st_x, p.inv_st_x);
         const int sx = rem - sy * p.st_x;
+        prefetch_super(s + s_step);
 #pragma unroll 1
         for (int t = 0; t < 4; ++t, ++v) {
           const int ab = v % p.a_bufs;

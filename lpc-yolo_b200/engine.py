@@ -226,6 +226,7 @@ class YOLOv10DetectionPredictor:
             torch.cuda.current_stream(dev).wait_stream(side)
             self.graphs, self.outs = [], []
             self.turn, self.done = 0, [None, None]      # next input buffer; "the replay that read buffer b has finished" events
+            self.out_done = [None, None]                # "graph b's static output has been copied out" (pipelined streams)
             for i in range(2):
                 g = torch.cuda.CUDAGraph()
                 # torch.cuda.graph's default capture stream is ONE class-level stream created on whichever device was current
@@ -245,17 +246,23 @@ class YOLOv10DetectionPredictor:
             self._graph_epoch = ep
         return self._graphed
 
-    def _replay_chunks(self, im_host, plan, gds):
+    def _replay_chunks(self, im_host, plan, gds, pipelined=False):
         """Chunk i+1's host-to-device copy (copy stream) overlaps chunk i's graph replay (compute stream).  The two input
         buffers of a graph alternate ACROSS calls and each remembers the event of the last replay that read it, so the copy
         stream never waits for the compute stream as a whole: in a pipelined stream of batches (``stream_inference``) batch
-        k+1's copy runs under batch k's replay."""
+        k+1's copy runs under batch k's replay.  ``pipelined`` also moves the small copies behind a replay (graph output ->
+        the batch's detection tensor, later the D2H copy) to a third stream, so that on the compute stream one replay
+        follows the other directly; the result then belongs to that stream (``self._out_stream``) until the caller has waited
+        for the host copy's event."""
         B = im_host.shape[0]
         if not im_host.is_pinned():
             im_host = im_host.pin_memory()
         cur = torch.cuda.current_stream(self.device)
         cs = self.__dict__.setdefault("_copy_stream", torch.cuda.Stream(device=self.device))
+        outs = self.__dict__.setdefault("_out_stream", torch.cuda.Stream(device=self.device)) if pipelined else cur
         preds = torch.empty((B, self.args.max_det, 6), dtype=torch.float32, device=self.device)
+        if pipelined:
+            preds.record_stream(outs)
         lo = 0
         for cb, gd in zip(plan, gds):
             b = gd.turn & 1
@@ -268,11 +275,21 @@ class YOLOv10DetectionPredictor:
                     gd.inp[b].copy_(im_host[lo:lo + cb], non_blocking=True)
                 ev.record(cs)
             cur.wait_event(ev)
+            if gd.out_done[b] is not None:
+                cur.wait_event(gd.out_done[b])           # the previous result of this graph has been copied out of its static output
             gd.graphs[b].replay()
-            preds[lo:lo + cb].copy_(gd.outs[b])
             d = torch.cuda.Event()
             d.record(cur)
             gd.done[b] = d
+            if pipelined:
+                outs.wait_event(d)
+                with torch.cuda.stream(outs):
+                    preds[lo:lo + cb].copy_(gd.outs[b])
+                    od = torch.cuda.Event()
+                    od.record(outs)
+                gd.out_done[b] = od
+            else:
+                preds[lo:lo + cb].copy_(gd.outs[b])
             lo += cb
         return preds
 
@@ -290,7 +307,7 @@ class YOLOv10DetectionPredictor:
                 cache[key] = self._Graphed(dev, lambda shape=shape: torch.full(shape, 0.5, dtype=torch.float32, device=dev),
                                            lambda x: model.detect(x, K, clip=True))
             gds.append(cache[key])
-        return self._replay_chunks(im_host, plan, gds)
+        return self._replay_chunks(im_host, plan, gds, pipelined)
 
     # ---- array sources: uint8 HWC (cv2 / BGR) images, SURVEY.md section 8(f) row 1 ------------------------------
     @staticmethod
@@ -354,7 +371,7 @@ class YOLOv10DetectionPredictor:
                 cache[key] = self._Graphed(dev, lambda cb=cb: torch.full((cb, hs, ws, 3), 114, dtype=torch.uint8, device=dev),
                                            self._u8_runner(cb, hs, ws, geom))
             gds.append(cache[key])
-        return self._replay_chunks(im_host, plan, gds)
+        return self._replay_chunks(im_host, plan, gds, pipelined)
 
     def inference_u8_device(self, im):
         """uint8 HWC images already on the device (one shape): no copy, eager launches."""
@@ -414,7 +431,7 @@ class YOLOv10DetectionPredictor:
             raise ValueError(f"array sources must be uint8 HWC images, got {getattr(source, 'dtype', type(source))} {tuple(getattr(source, 'shape', ()))}")
         return source.contiguous()
 
-    def _host_copy(self, preds):
+    def _host_copy(self, preds, stream=None):
         """Queue ONE device->host copy of the batched detections into a pinned buffer (stream order: behind the last graph
         replay).  The copy gives the host path everything it needs - the per-image prefix lengths are counted from it
         instead of by a device reduction plus a second, synchronous read - and it is what ``last_preds_host`` exposes.  The
@@ -426,9 +443,11 @@ class YOLOv10DetectionPredictor:
             self._host_turn = 0
         buf = ring[self._host_turn % 3]
         self._host_turn += 1
-        buf.copy_(preds, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(preds.device))
+        st = stream if stream is not None else torch.cuda.current_stream(preds.device)
+        with torch.cuda.stream(st):
+            buf.copy_(preds, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(st)
         return buf, ev
 
     def postprocess(self, preds, img, orig_imgs, host=None):
@@ -537,7 +556,8 @@ class YOLOv10DetectionPredictor:
                         preds = self.inference_u8_device(im)
                     else:
                         preds = self.inference_from_host_u8(im, pipelined)
-                    host = self._host_copy(preds)
+                    # a pipelined host batch lives on the output stream until its host copy has landed
+                    host = self._host_copy(preds, self._out_stream if (pipelined and not mixed and not im.is_cuda) else None)
                 if isinstance(source, (list, tuple)):
                     orig = list(source)
                 else:                      # one [B,h,w,3] array / tensor: Results slice it on demand
@@ -549,7 +569,7 @@ class YOLOv10DetectionPredictor:
                     with profilers[1]:
                         preds = self.inference_from_host(im, pipelined)
                         if pipelined:
-                            host = self._host_copy(preds)
+                            host = self._host_copy(preds, self._out_stream)
                 else:
                     with profilers[0]:
                         im = self.preprocess(source)
