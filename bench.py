@@ -530,7 +530,7 @@ def main():
                         "hbm_achieved_gbs": round(by_tc / t_tc / 1e9, 1), "launches_hbm_side_of_ridge": hbm_side,
                         "frac_of_per_launch_rooflines": round(sum(floors) / t_tc, 4),
                         "timing": "all conv launches of one step captured in one CUDA graph, CUDA events around 10 replays",
-                        "traffic_note": "dram__bytes read+write of the largest conv launch (16->32 3x3 @320x320), profiles/r02_ncu_full_top_conv.json (ncu --set full, profiles/r02_j_ncu_full.md)"}
+                        "traffic_note": "dram__bytes read+write of the largest conv launch (fused 16->32 3x3 @320x320 + space_to_depth + 1x1, algorithmic 315 MB), profiles/r02_ncu_full_top_conv.json (ncu --set full, profiles/r02_q_ncu_full_s2d.md)"}
             # what the fused stage-1 keys cost: the three class-branch convs with and without the rowmax epilogue
             rowmax_delta = None
             rm = [r for r in rec if r[0] == "conv2d_tc" and len(r) > 5 and r[5] is not None]
