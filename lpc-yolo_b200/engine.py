@@ -25,6 +25,7 @@ DEFAULTS = dict(conf=0.25, max_det=300, classes=None, half=True, device=None, ve
                 augment=False, visualize=False, embed=None, stream=False, fp32=False)
 _HALF_WARNED = False
 _SKIP_H2D = __import__("os").environ.get("LPC_E2E_SKIP_H2D") == "1"      # measurement only: what the copy costs the stream
+_SKIP_PREP = __import__("os").environ.get("LPC_E2E_SKIP_PREP") == "1"    # measurement only: ... and the /255 + NHWC pack
 CALLBACK_EVENTS = ("on_predict_start", "on_predict_batch_start", "on_predict_postprocess_end", "on_predict_batch_end",
                    "on_predict_end")
 
@@ -214,13 +215,21 @@ class YOLOv10DetectionPredictor:
 
     # ---- host-source fast path: chunked H2D copies overlapped with CUDA-graph replays ---------------------------
     class _Graphed:
-        """Two CUDA graphs (double buffering) of ``run(static_input)`` on two static input buffers."""
+        """Two CUDA graphs (double buffering) of ``run(static_input)`` on two static input buffers.  ``stage`` / ``prep``: the
+        host data lands in two staging buffers (``stage()``) and ``prep(staging, static_input)`` - launched on the COPY stream,
+        outside the graphs - turns it into the graph input (pipelined uint8 streams: the /255 + NHWC pack of batch k+1 then
+        runs under batch k's kernels instead of at the head of its own graph)."""
 
-        def __init__(self, dev, make_input, run):
+        def __init__(self, dev, make_input, run, stage=None, prep=None):
             self.inp = [make_input() for _ in range(2)]
+            self.stage = [stage() for _ in range(2)] if stage is not None else None
+            self.prep = prep
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
+                if prep is not None:
+                    for i in range(2):
+                        prep(self.stage[i], self.inp[i])
                 for _ in range(2):
                     run(self.inp[0])
             torch.cuda.current_stream(dev).wait_stream(side)
@@ -271,8 +280,11 @@ class YOLOv10DetectionPredictor:
             with torch.cuda.stream(cs):
                 if gd.done[b] is not None:
                     cs.wait_event(gd.done[b])            # the replay that read this buffer has finished
+                dst = gd.stage[b] if gd.prep is not None else gd.inp[b]
                 if not _SKIP_H2D:
-                    gd.inp[b].copy_(im_host[lo:lo + cb], non_blocking=True)
+                    dst.copy_(im_host[lo:lo + cb], non_blocking=True)
+                if gd.prep is not None and not _SKIP_PREP:
+                    gd.prep(dst, gd.inp[b])
                 ev.record(cs)
             cur.wait_event(ev)
             if gd.out_done[b] is not None:
@@ -338,21 +350,25 @@ class YOLOv10DetectionPredictor:
             return None
         return (float(pad_w), float(pad_h), float(gain), float(ws), float(hs))
 
-    def _prep_u8(self, src, geom, tables):
+    def _prep_u8(self, src, geom, tables, out=None):
         """uint8 HWC device images -> network input (LetterBox resize + border, BGR->RGB, /255, NHWC) in one kernel."""
         H, W, top, left, nh, nw = geom
         dt = self.model.compute_dtype
         if tables is None:                      # LetterBox ratio 1: border + pack only
-            return F.pack_u8(src, dt, top, left, H, W, 114, True)
-        return F.letterbox_u8(src, dt, nh, nw, tables, top, left, H, W, 114, True)
+            return F.pack_u8(src, dt, top, left, H, W, 114, True, out=out)
+        return F.letterbox_u8(src, dt, nh, nw, tables, top, left, H, W, 114, True, out=out)
 
-    def _u8_runner(self, cb, hs, ws, geom):
-        """-> run(uint8 [cb,hs,ws,3] device tensor) -> [cb,K,6] in ORIGINAL-image coordinates (rescale fused in the tail)."""
+    def _u8_runner(self, cb, hs, ws, geom, split=False):
+        """-> run(uint8 [cb,hs,ws,3] device tensor) -> [cb,K,6] in ORIGINAL-image coordinates (rescale fused in the tail).
+        ``split``: -> (prep(uint8 images, net buffer [cb,H,W,4]), run(net buffer)) - the pack as a launch of its own."""
         dev, model, K = self.device, self.model, self.args.max_det
         nh, nw = geom[4], geom[5]
         tables = F.resize_tables(hs, ws, nh, nw, dev) if (nh, nw) != (hs, ws) else None
         row = self.scale_back_row(geom, hs, ws)
         scale = torch.tensor([row] * cb, dtype=torch.float32, device=dev) if row is not None else None
+        if split:
+            return (lambda src, net: self._prep_u8(src, geom, tables, out=net),
+                    lambda net: model.detect(net.permute(0, 3, 1, 2)[:, :3], K, clip=True, scale_back=scale))
         return lambda inp: model.detect(self._prep_u8(inp, geom, tables), K, clip=True, scale_back=scale)
 
     def inference_from_host_u8(self, im_host, pipelined=False):
@@ -366,10 +382,15 @@ class YOLOv10DetectionPredictor:
         dev = self.device
         gds = []
         for cb in plan:
-            key = ("u8", cb, hs, ws, geom, self.args.max_det, self.model.compute_dtype)
+            key = ("u8p" if pipelined else "u8", cb, hs, ws, geom, self.args.max_det, self.model.compute_dtype)
             if key not in cache:
-                cache[key] = self._Graphed(dev, lambda cb=cb: torch.full((cb, hs, ws, 3), 114, dtype=torch.uint8, device=dev),
-                                           self._u8_runner(cb, hs, ws, geom))
+                stage = lambda cb=cb: torch.full((cb, hs, ws, 3), 114, dtype=torch.uint8, device=dev)
+                if pipelined:
+                    prep, run = self._u8_runner(cb, hs, ws, geom, split=True)
+                    net = lambda cb=cb: torch.zeros((cb, geom[0], geom[1], 4), dtype=self.model.compute_dtype, device=dev)
+                    cache[key] = self._Graphed(dev, net, run, stage=stage, prep=prep)
+                else:
+                    cache[key] = self._Graphed(dev, stage, self._u8_runner(cb, hs, ws, geom))
             gds.append(cache[key])
         return self._replay_chunks(im_host, plan, gds, pipelined)
 
