@@ -126,6 +126,16 @@ int lpc_dwpw_tc(const void* x, int x_ld, int B, int H, int W, int Cin, const flo
 int lpc_stem_conv(int dtype, const void* x, int B, int H, int W, const float* w, const float* bias, int stride,
                   int Cout, void* y, int y_ld, int act, void* stream);
 
+/* The same stem straight from the uint8 HWC image (the LoadPilAndNumpy source, [B][H][W][3] bytes, BGR when swap_rb != 0):
+ * y = act(conv3x3_s2(bf16(x / 255)) + b), bit-identical to lpc_pack_u8 (bf16) followed by lpc_stem_conv - the /255, the
+ * BGR->RGB swap and the NHWC-4 padding of predictor.preprocess (engine/predictor.py:115-133) happen while the builder
+ * warps assemble the im2col rows (the image arrives as one 112-byte x 17-row TMA box per tile), so the 4-channel bf16 copy of the batch (210 MB at B=64) is never written or read.
+ * bf16 output only; stride 2, even H, W % 16 == 0 (16-byte row pitch), Cout % 16 == 0, Cout <= 128; no LetterBox border
+ * (callers with a border or a resize use lpc_pack_u8 / lpc_letterbox_u8 + lpc_stem_conv). */
+int lpc_stem_conv_u8_supported(int H, int W, int stride, int Cout, int y_ld, int act);
+int lpc_stem_conv_u8(const void* x, int B, int H, int W, int swap_rb, const float* w, const float* bias, int stride, int Cout,
+                     void* y, int y_ld, int act, void* stream);
+
 /* ---- depthwise convolution ---------------------------------------------------------------------
  * groups == C convs: CIB / RepVGGDW (block.py:700-756; the 3x3 branch is merged into the 7x7 on the
  * host as RepVGGDW.fuse does, :714-733), SCDown.cv2 (:822), Attention.pe (:780), LPC.cv2 5x5 (:5806),

@@ -42,6 +42,8 @@ SIGNATURES = {
     "lpc_dwpw_tc_supported": (_i, [_i, _i, _i, _i, _i, _i, _i, _i]),
     "lpc_dwpw_tc": (_i, [_p, _i, _i, _i, _i, _i, _f32p, _f32p, _i, _p, _f32p, _i, _i, _p, _f32p, _i, _i, _p, _i, _p, _ll, _i, _p]),
     "lpc_stem_conv": (_i, [_i, _p, _i, _i, _i, _f32p, _f32p, _i, _i, _p, _i, _i, _p]),
+    "lpc_stem_conv_u8_supported": (_i, [_i, _i, _i, _i, _i, _i]),
+    "lpc_stem_conv_u8": (_i, [_p, _i, _i, _i, _i, _f32p, _f32p, _i, _i, _p, _i, _i, _p]),
     "lpc_dwconv2d": (_i, [_i, _p, _i, _i, _i, _i, _i, _f32p, _f32p, _i, _i, _i, _i, _p, _i, _i, _p, _i, _p]),
     "lpc_sppf_pool": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _i, _p]),
     "lpc_psa_attention": (_i, [_i, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p]),

@@ -34,6 +34,11 @@ constexpr int SB_DEPTH = 3, SB_SLOT = 80;     // input ring: tiles in flight per
 constexpr int SB_BOX_PX = 36, SB_BOX_ROWS = 2 * SB_TH + 1, SB_BOX_ROW_B = SB_BOX_PX * 8;
 constexpr int SB_BOX_BYTES = SB_BOX_ROWS * SB_BOX_ROW_B, SB_BOX_SLOT = (SB_BOX_BYTES + 127) & ~127;
 static_assert(SB_DEPTH * SB_BOX_SLOT <= SB_DEPTH * 128 * SB_SLOT, "the TMA ring reuses the cp.async ring's shared memory");
+// uint8 HWC input (lpc_stem_conv_u8): the image is [B][H][W*3 bytes]; the box of a tile starts 16 bytes before byte
+// 3 * 2*ox0 (a multiple of 96, so every box row starts on a 16-byte boundary) and is 112 bytes wide: pixel 2*ox0-1 is at
+// byte 13, pixel 2*ox0+32 ends at byte 111.  Zero fill outside the image = the conv padding (0 / 255 = 0).
+constexpr int SB_U8_ROW_B = 112, SB_U8_LEAD = 13, SB_U8_BOX_BYTES = SB_BOX_ROWS * SB_U8_ROW_B;
+static_assert(SB_U8_BOX_BYTES <= SB_BOX_SLOT, "the uint8 box fits a ring slot");
 
 
 struct StemTcParams {
@@ -47,6 +52,7 @@ struct StemTcParams {
   int acc_cols, tmem_cols;
   float inv_per_img, inv_tiles_x;
   int tma_in;          // the 3x3 stride-2 input windows of a tile arrive as ONE TMA box (else: per-thread cp.async ring)
+  int swap_rb;         // U8 kernels: the image bytes are BGR: byte 2 of a pixel goes to channel slot 0
   unsigned long long* trace;   // LPC_STEM_DBG=1: [3 roles][64 tiles][4 stamps] clock64 of CTA 0
 };
 
@@ -78,7 +84,10 @@ __device__ __forceinline__ void stem_epilogue_row(uint32_t trow, int Cout, bf16*
   }
 }
 
-template <int ACT>
+// U8: the input is the uint8 HWC image itself (always by TMA): the builders normalise (v / 255, bit-identical to lpc_pack_u8's
+// bf16 output: fma(2^23 + v, 1/255f, -2^23/255f) == v * (1/255f) exactly, and bf16_rn of that equals bf16_rn(v / 255f) for
+// all 256 values - checked exhaustively) and pad to 4 channels while they build the im2col row.
+template <int ACT, bool U8>
 __global__ void __launch_bounds__(SB_THREADS, 4)
 stem_tc_kernel(const __grid_constant__ StemTcParams p, const __grid_constant__ CUtensorMap in_map) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -104,7 +113,7 @@ stem_tc_kernel(const __grid_constant__ StemTcParams p, const __grid_constant__ C
       mbar_init(tempty(s), 4);
     }
     for (int s = 0; s < SB_DEPTH; ++s) mbar_init(ifull(s), 1);
-    if (p.tma_in) prefetch_tmap(&in_map);
+    if (U8 || p.tma_in) prefetch_tmap(&in_map);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) tmem_alloc(smem_u32(&tmem_base_slot), (uint32_t)p.tmem_cols);
@@ -141,7 +150,7 @@ stem_tc_kernel(const __grid_constant__ StemTcParams p, const __grid_constant__ C
     const int ty = r >> 4, tx = r & 15;
     const uint32_t row_addr = (uint32_t)(r * 128);
     const uint32_t sw = (uint32_t)(r & 7);
-    if (p.tma_in) {
+    if (U8 || p.tma_in) {
       // One elected builder thread fetches the whole input window of tile it + SB_DEPTH - 1 with a single TMA box; every
       // builder then reads its own 3 x (16 + 8) bytes from shared memory.  The per-thread cp.async ring below needed
       // six LSU instructions per output pixel on the global side alone and made the L1 data pipe the stem's limiter.
@@ -151,18 +160,18 @@ stem_tc_kernel(const __grid_constant__ StemTcParams p, const __grid_constant__ C
           const int img = fast_div(m, per_img, p.inv_per_img), rem = m - img * per_img;
           const int tyi = fast_div(rem, p.tiles_x, p.inv_tiles_x), txi = rem - tyi * p.tiles_x;
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_expect_tx(ifull(slot), (uint32_t)SB_BOX_BYTES);
+          mbar_expect_tx(ifull(slot), (uint32_t)(U8 ? SB_U8_BOX_BYTES : SB_BOX_BYTES));
           asm volatile(
               "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
               ::"r"(ring0 + (uint32_t)(slot * SB_BOX_SLOT)), "l"(&in_map), "r"(ifull(slot)),
-                "r"((2 * txi * SB_TW - 2) * 4), "r"(2 * tyi * SB_TH - 1), "r"(img)
+                "r"(U8 ? 2 * txi * SB_TW * 3 - 16 : (2 * txi * SB_TW - 2) * 4), "r"(2 * tyi * SB_TH - 1), "r"(img)
               : "memory");
         }
       };
       int m = blockIdx.x;
       if (r == 0)
         for (int d = 0; d < SB_DEPTH - 1; ++d) issue_box(m + d * (int)gridDim.x, d);
-      const uint32_t my_off = (uint32_t)(2 * ty * SB_BOX_ROW_B + tx * 16);
+      const uint32_t my_off = U8 ? (uint32_t)(2 * ty * SB_U8_ROW_B + SB_U8_LEAD + tx * 6) : (uint32_t)(2 * ty * SB_BOX_ROW_B + tx * 16);
       int it = 0;
       for (; m < p.m_tiles; m += gridDim.x, ++it) {
         if (r == 0) STRACE(0, it, 0);
@@ -174,10 +183,41 @@ stem_tc_kernel(const __grid_constant__ StemTcParams p, const __grid_constant__ C
         const uint32_t src = ring0 + (uint32_t)(slot * SB_BOX_SLOT) + my_off;
         uint4 e12[3];     // pixels 2ox, 2ox+1 of input row k (box pixels 2tx+2, 2tx+3)
         uint2 e0[3];      // pixel 2ox-1 (box pixel 2tx+1)
+        if (U8) {
+          // 9 bytes (3 pixels x BGR / RGB) per input row, at an arbitrary byte offset: three aligned words, two funnel shifts
+          const uint32_t al = src & ~3u, sh = (src & 3u) * 8u;
+          const float inv = 1.0f / 255.0f, off = -8388608.0f * (1.0f / 255.0f);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(e0[k].x), "=r"(e0[k].y) : "r"(src + (uint32_t)(k * SB_BOX_ROW_B + 8)));
-          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(e12[k].x), "=r"(e12[k].y), "=r"(e12[k].z), "=r"(e12[k].w) : "r"(src + (uint32_t)(k * SB_BOX_ROW_B + 16)));
+          for (int k = 0; k < 3; ++k) {
+            uint32_t w0, w1, w2;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w0) : "r"(al + (uint32_t)(k * SB_U8_ROW_B)));
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w1) : "r"(al + (uint32_t)(k * SB_U8_ROW_B + 4)));
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w2) : "r"(al + (uint32_t)(k * SB_U8_ROW_B + 8)));
+            const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh), b8 = w2 >> sh;
+            float f[9];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+              const uint32_t word = j < 4 ? lo : (j < 8 ? hi : b8);
+              // bytes -> float without I2F: 0x4B0000vv is 2^23 + v; the FMA removes the 2^23 and scales in one rounding
+              f[j] = fmaf(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u | (uint32_t)(j & 3))), inv, off);
+            }
+            if (p.swap_rb) {      // BGR bytes -> RGB channel slots (the K order, hence the accumulation order, stays the packed path's)
+#pragma unroll
+              for (int q = 0; q < 9; q += 3) { const float t = f[q]; f[q] = f[q + 2]; f[q + 2] = t; }
+            }
+            auto pk = [](float a, float b) {
+              const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+              return *reinterpret_cast<const uint32_t*>(&h);
+            };
+            e0[k] = make_uint2(pk(f[0], f[1]), pk(f[2], 0.f));
+            e12[k] = make_uint4(pk(f[3], f[4]), pk(f[5], 0.f), pk(f[6], f[7]), pk(f[8], 0.f));
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(e0[k].x), "=r"(e0[k].y) : "r"(src + (uint32_t)(k * SB_BOX_ROW_B + 8)));
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(e12[k].x), "=r"(e12[k].y), "=r"(e12[k].z), "=r"(e12[k].w) : "r"(src + (uint32_t)(k * SB_BOX_ROW_B + 16)));
+          }
         }
         const int s = it & 1;
         if (r == 0) STRACE(0, it, 1);
@@ -318,14 +358,31 @@ stem_tc_kernel(const __grid_constant__ StemTcParams p, const __grid_constant__ C
 
 }  // namespace
 
-// Returns LPC_E_UNSUPPORTED (without setting an error) when the shape is not for this kernel; lpc_stem_conv then
-// uses the CUDA-core kernel (fp32 validation mode, stride 1, odd sizes).
-int lpc_stem_conv_tc(const void* x, int B, int H, int W, const float* w, const float* bias, int Cout, void* y, int y_ld,
-                     int act, cudaStream_t stream) {
+namespace {
+
+typedef CUresult (*StemEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+StemEncodeFn stem_encode() {
+  static StemEncodeFn enc = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+    return reinterpret_cast<StemEncodeFn>(f);
+  }();
+  return enc;
+}
+
+template <bool U8>
+void (*stem_kernel_of(int act))(StemTcParams, CUtensorMap) {
+  return act == LPC_ACT_SILU ? stem_tc_kernel<LPC_ACT_SILU, U8> : act == LPC_ACT_MISH ? stem_tc_kernel<LPC_ACT_MISH, U8>
+       : act == LPC_ACT_NONE ? stem_tc_kernel<LPC_ACT_NONE, U8> : stem_tc_kernel<LPC_ACT_RELU, U8>;
+}
+
+// Common part of the two entry points: tile geometry, TMEM / CTA plan, tensor map, launch.
+int stem_launch(StemTcParams& p, bool u8, const void* x, int B, int H, int W, int Cout, int act, cudaStream_t stream) {
   if (Cout % 16 || Cout > 128 || (H & 1) || (W & 1)) return LPC_E_UNSUPPORTED;
   if (!(act == LPC_ACT_SILU || act == LPC_ACT_MISH || act == LPC_ACT_NONE || act == LPC_ACT_RELU)) return LPC_E_UNSUPPORTED;
-  StemTcParams p;
-  p.x = (const uint2*)x; p.w = w; p.bias = bias; p.y = (bf16*)y; p.y_ld = y_ld;
   p.B = B; p.H = H; p.W = W; p.Ho = H / 2; p.Wo = W / 2; p.Cout = Cout; p.act = act;
   p.tiles_x = (p.Wo + SB_TW - 1) / SB_TW;
   p.tiles_y = (p.Ho + SB_TH - 1) / SB_TH;
@@ -338,20 +395,17 @@ int lpc_stem_conv_tc(const void* x, int B, int H, int W, const float* w, const f
   while (p.acc_cols < Cout) p.acc_cols <<= 1;
   p.tmem_cols = 2 * p.acc_cols;
   const size_t smem = 2 * SB_A_BYTES + (size_t)Cout * 128 + (size_t)SB_DEPTH * 128 * SB_SLOT + 1024;
-  void (*kern)(StemTcParams, CUtensorMap) = act == LPC_ACT_SILU ? stem_tc_kernel<LPC_ACT_SILU> : act == LPC_ACT_MISH ? stem_tc_kernel<LPC_ACT_MISH>
-                              : act == LPC_ACT_NONE ? stem_tc_kernel<LPC_ACT_NONE> : stem_tc_kernel<LPC_ACT_RELU>;
   static unsigned long long attr = 0;     // per device
   if (lpc_first_on_device(&attr)) {
     const int lim = 2 * SB_A_BYTES + 128 * 128 + SB_DEPTH * 128 * SB_SLOT + 1024;
-    if (cudaFuncSetAttribute(stem_tc_kernel<LPC_ACT_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
-        cudaFuncSetAttribute(stem_tc_kernel<LPC_ACT_MISH>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
-        cudaFuncSetAttribute(stem_tc_kernel<LPC_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess ||
-        cudaFuncSetAttribute(stem_tc_kernel<LPC_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess)
-    { attr = 0; LPC_FAIL(LPC_E_CUDA, "stem_conv: smem attribute"); }
+    bool ok = true;
+    for (int a : {LPC_ACT_SILU, LPC_ACT_MISH, LPC_ACT_NONE, LPC_ACT_RELU}) {
+      ok = ok && cudaFuncSetAttribute(stem_kernel_of<false>(a), cudaFuncAttributeMaxDynamicSharedMemorySize, lim) == cudaSuccess;
+      ok = ok && cudaFuncSetAttribute(stem_kernel_of<true>(a), cudaFuncAttributeMaxDynamicSharedMemorySize, lim) == cudaSuccess;
+    }
+    if (!ok) { attr = 0; LPC_FAIL(LPC_E_CUDA, "stem_conv: smem attribute"); }
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = lpc_num_sms();
   int per_sm = 512 / p.tmem_cols;
   if (per_sm > 4) per_sm = 4;
   while (per_sm > 1 && (size_t)per_sm * (smem + 2048) > 227 * 1024) --per_sm;
@@ -366,33 +420,36 @@ int lpc_stem_conv_tc(const void* x, int B, int H, int W, const float* w, const f
     cudaMemset(trace_buf, 0, 3 * 64 * 4 * 8);
     p.trace = trace_buf;
   }
-  // input tensor map: [B][H][W*4 bf16], box = 144 elements x 17 rows (see SB_BOX_*)
   CUtensorMap in_map;
   memset(&in_map, 0, sizeof(in_map));
   p.tma_in = 0;
-  {
+  StemEncodeFn enc = stem_encode();
+  if (u8) {
+    // input tensor map: [B][H][W*3 bytes], box = 112 bytes x 17 rows (see SB_U8_*)
+    if (!enc) LPC_FAIL(LPC_E_CUDA, "stem_conv_u8: cuTensorMapEncodeTiled not available");
+    cuuint64_t dims[3] = {(cuuint64_t)W * 3, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)W * 3, (cuuint64_t)H * W * 3};
+    cuuint32_t box[3] = {(cuuint32_t)SB_U8_ROW_B, (cuuint32_t)SB_BOX_ROWS, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    const CUresult r = enc(&in_map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) LPC_FAIL(LPC_E_CUDA, "stem_conv_u8: tensor map encode failed (CUresult %d)", (int)r);
+    p.tma_in = 1;
+  } else {
+    // input tensor map: [B][H][W*4 bf16], box = 144 elements x 17 rows (see SB_BOX_*)
     static const int tma_env = [] { const char* e = getenv("LPC_STEM_TMA"); return e ? atoi(e) : 1; }();
-    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static EncodeFn enc = [] {
-      void* f = nullptr;
-      cudaDriverEntryPointQueryResult q;
-      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
-      return reinterpret_cast<EncodeFn>(f);
-    }();
-    if (tma_env && enc && W % 2 == 0 && W * 4 >= SB_BOX_PX * 4 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0) {
+    if (tma_env && enc && W % 2 == 0 && W * 4 >= SB_BOX_PX * 4 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
       cuuint64_t dims[3] = {(cuuint64_t)W * 4, (cuuint64_t)H, (cuuint64_t)B};
       cuuint64_t strides[2] = {(cuuint64_t)W * 8, (cuuint64_t)H * W * 8};
       cuuint32_t box[3] = {(cuuint32_t)SB_BOX_PX * 4, (cuuint32_t)SB_BOX_ROWS, 1};
       cuuint32_t es[3] = {1, 1, 1};
-      if (enc(&in_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<uint2*>(p.x), dims, strides, box, es,
+      if (enc(&in_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(x), dims, strides, box, es,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
         p.tma_in = 1;
     }
   }
-  lpc_launch_pdl(kern, (unsigned)grid, SB_THREADS, smem, stream, p, in_map);
+  lpc_launch_pdl(u8 ? stem_kernel_of<true>(act) : stem_kernel_of<false>(act), (unsigned)grid, SB_THREADS, smem, stream, p, in_map);
   LPC_CHECK_LAUNCH("stem_conv_tc");
   if (dbg) {
     static int calls = 0;
@@ -414,4 +471,41 @@ int lpc_stem_conv_tc(const void* x, int B, int H, int W, const float* w, const f
     }
   }
   return LPC_OK;
+}
+
+}  // namespace
+
+// Returns LPC_E_UNSUPPORTED (without setting an error) when the shape is not for this kernel; lpc_stem_conv then
+// uses the CUDA-core kernel (fp32 validation mode, stride 1, odd sizes).
+int lpc_stem_conv_tc(const void* x, int B, int H, int W, const float* w, const float* bias, int Cout, void* y, int y_ld,
+                     int act, cudaStream_t stream) {
+  StemTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = (const uint2*)x; p.w = w; p.bias = bias; p.y = (bf16*)y; p.y_ld = y_ld;
+  return stem_launch(p, false, x, B, H, W, Cout, act, stream);
+}
+
+// ---- the stem straight from the uint8 image ----------------------------------------------------------------------
+extern "C" int lpc_stem_conv_u8_supported(int H, int W, int stride, int Cout, int y_ld, int act) {
+  static const int on = [] { const char* e = getenv("LPC_STEM_U8"); return e ? atoi(e) : 1; }();
+  if (!on || stride != 2 || H <= 0 || W <= 0 || (H & 1) || W % 16) return 0;       // W * 3 bytes per row: a multiple of 16
+  if (Cout % 16 || Cout > 128 || y_ld % 8 || y_ld < Cout) return 0;
+  if (!(act == LPC_ACT_SILU || act == LPC_ACT_MISH || act == LPC_ACT_NONE || act == LPC_ACT_RELU)) return 0;
+  return 1;
+}
+
+extern "C" int lpc_stem_conv_u8(const void* x, int B, int H, int W, int swap_rb, const float* w, const float* bias, int stride, int Cout,
+                                void* y, int y_ld, int act, void* stream) {
+  LPC_REQUIRE(x && w && y, "stem_conv_u8: null pointer");
+  LPC_REQUIRE(B > 0, "stem_conv_u8: bad shape");
+  if (!lpc_stem_conv_u8_supported(H, W, stride, Cout, y_ld, act))
+    LPC_FAIL(LPC_E_UNSUPPORTED, "stem_conv_u8: unsupported shape H=%d W=%d stride=%d Cout=%d y_ld=%d act=%d", H, W, stride, Cout, y_ld, act);
+  LPC_REQUIRE(aligned16(x) && aligned16(y) && aligned16(w), "stem_conv_u8: pointers must be 16-byte aligned");
+  StemTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = nullptr; p.w = w; p.bias = bias; p.y = (bf16*)y; p.y_ld = y_ld;
+  p.swap_rb = swap_rb ? 1 : 0;
+  const int r = stem_launch(p, true, x, B, H, W, Cout, act, (cudaStream_t)stream);
+  if (r == LPC_E_UNSUPPORTED) LPC_FAIL(LPC_E_UNSUPPORTED, "stem_conv_u8: shape not taken (H=%d W=%d Cout=%d)", H, W, Cout);
+  return r;
 }

@@ -366,6 +366,12 @@ class YOLOv10DetectionPredictor:
         tables = F.resize_tables(hs, ws, nh, nw, dev) if (nh, nw) != (hs, ws) else None
         row = self.scale_back_row(geom, hs, ws)
         scale = torch.tensor([row] * cb, dtype=torch.float32, device=dev) if row is not None else None
+        H, W, top, left = geom[:4]
+        direct = (tables is None and (top, left, H, W) == (0, 0, hs, ws)
+                  and model.stem_u8_supported(torch.empty((cb, hs, ws, 3), dtype=torch.uint8, device=dev)))
+        if direct:          # no LetterBox border / resize: the stem kernel reads the uint8 image itself (no packed copy of the batch)
+            run = lambda inp: model.detect(inp, K, clip=True, scale_back=scale)
+            return (None, run) if split else run
         if split:
             return (lambda src, net: self._prep_u8(src, geom, tables, out=net),
                     lambda net: model.detect(net.permute(0, 3, 1, 2)[:, :3], K, clip=True, scale_back=scale))
@@ -388,7 +394,7 @@ class YOLOv10DetectionPredictor:
                 if pipelined:
                     prep, run = self._u8_runner(cb, hs, ws, geom, split=True)
                     net = lambda cb=cb: torch.zeros((cb, geom[0], geom[1], 4), dtype=self.model.compute_dtype, device=dev)
-                    cache[key] = self._Graphed(dev, net, run, stage=stage, prep=prep)
+                    cache[key] = self._Graphed(dev, net, run, stage=stage, prep=prep) if prep is not None else self._Graphed(dev, stage, run)
                 else:
                     cache[key] = self._Graphed(dev, stage, self._u8_runner(cb, hs, ws, geom))
             gds.append(cache[key])

@@ -287,6 +287,31 @@ def conv2d(x, pc, out=None, res=None, chan_scale=None, rowmax=None):
     return out
 
 
+def stem_u8_supported(src, pc, out_ld=None):
+    """Can the stem conv ``pc`` read the uint8 HWC images ``src`` [B,H,W,3] directly (lpc_stem_conv_u8)?"""
+    if pc.w_stem is None or not (torch.is_tensor(src) and src.is_cuda and src.dtype == torch.uint8 and src.dim() == 4 and src.shape[3] == 3):
+        return False
+    B, H, W, _ = src.shape
+    return (src.is_contiguous() and src.data_ptr() % 16 == 0 and (pc.k, pc.p) == (3, 1)
+            and bool(_lib.lib().lpc_stem_conv_u8_supported(H, W, pc.s, pc.cout, out_ld if out_ld is not None else pc.cout, pc.act)))
+
+
+def stem_conv_u8(src, pc, swap_rb=True, out=None):
+    """Stem conv on uint8 HWC images (BGR when ``swap_rb``): /255, channel swap and the conv in one kernel -> bf16 NHWC."""
+    B, H, W, _ = src.shape
+    Ho, Wo = (H + 2 - 3) // pc.s + 1, (W + 2 - 3) // pc.s + 1
+    if out is None:
+        out = new_act(B, pc.cout, Ho, Wo, torch.bfloat16, src.device)
+    assert tuple(out.shape) == (B, pc.cout, Ho, Wo) and out.dtype == torch.bfloat16
+    yp, yld = view_of(out)
+    flops = 2.0 * B * Ho * Wo * pc.cout * 27
+    nb = B * H * W * 3 + 2 * B * Ho * Wo * pc.cout
+    with _prof("stem_conv_u8", flops, nb, f"u8 3->{pc.cout} k3s{pc.s} {H}x{W} B{B}"):
+        check(_lib.lib().lpc_stem_conv_u8(_fp(src), B, H, W, int(swap_rb), _fp(pc.w_stem), _fp(pc.bias), pc.s, pc.cout, yp, yld, pc.act,
+                                         _stream()), "stem_conv_u8")
+    return out
+
+
 def conv3x3_s2d_supported(x, pc1, pc2, out_ld=None):
     """Can conv3x3(pc1) -> space_to_depth -> conv1x1 (pc2 = its 2x2 stride-2 re-packing) run as ONE kernel (lpc_conv3x3_s2d_tc)?"""
     if x.dtype != torch.bfloat16 or pc1.w_tc is None or pc2.w_tc is None:

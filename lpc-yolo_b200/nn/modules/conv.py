@@ -45,6 +45,18 @@ class Conv(LpcModule):
 
     forward_fuse = forward  # BN is always folded; kept for API parity (conv.py:52-54)
 
+    def u8_supported(self, src, dtype, out_ld=None):
+        """uint8 HWC images [B,H,W,3] as the input of this (stem) conv: does the fused /255 + conv kernel take them?"""
+        if dtype != torch.bfloat16 or self.conv.in_channels != 3 or self.conv.groups != 1:
+            return False
+        pk = self._packed(torch.empty(0, dtype=dtype, device=src.device), self._build)
+        return isinstance(pk, pack.PackedConv) and F.stem_u8_supported(src, pk, out_ld)
+
+    def forward_u8(self, src, swap_rb=True, out=None):
+        """predictor.preprocess (/255, BGR->RGB, HWC->CHW; engine/predictor.py:115-133) + this conv in one kernel."""
+        pk = self._packed(torch.empty(0, dtype=torch.bfloat16, device=src.device), self._build)
+        return F.stem_conv_u8(src, pk, swap_rb, out)
+
     def _build_s2d(self, dtype, device):
         """This 1x1 conv applied to space_to_depth(x) (block.py:4069-4070) == a 2x2 stride-2 conv on x:
         s2d channel q*C + c holds pixel (2y + (q&1), 2x + (q>>1)), so w2[co, c, ky, kx] = w1[co, (ky + 2*kx)*C + c]."""

@@ -173,6 +173,17 @@ class BaseModel(LpcModule):
         self._plan_cache = (dest, live, fold, prefold)
         return self._plan_cache
 
+    def stem_u8_supported(self, src):
+        """True when ``src`` (uint8 HWC device images [B,H,W,3]) can enter the network without a packed copy: bf16 mode, layer 0
+        a plain stride-2 3x3 stem Conv feeding only layer 1, a shape lpc_stem_conv_u8 takes."""
+        if self.compute_dtype != torch.bfloat16 or not (torch.is_tensor(src) and src.is_cuda and src.dtype == torch.uint8):
+            return False
+        dest, live, fold, prefold = self._plan()
+        m = self.model[0]
+        if type(m) is not Conv or m.f != -1 or 0 in dest or 0 in fold or 0 in prefold or self.front_depth > 0:
+            return False
+        return m.u8_supported(src, self.compute_dtype)
+
     def _predict_once(self, x, tail=None):
         """tasks.py:83-111.  ``tail``: optional callable applied instead of the detect head's forward."""
         if not x.is_cuda:
@@ -183,12 +194,19 @@ class BaseModel(LpcModule):
             with torch.cuda.device(x.device):
                 return self._predict_once(x, tail)
         dest, live, fold, prefold = self._plan()
-        if x.dtype not in (torch.bfloat16, torch.float32) or not F.is_nhwc_view(x) or x.dtype != self.compute_dtype:
-            x = F.pack_input(x.float().contiguous(), self.compute_dtype) if x.shape[1] <= 4 else F.as_act(x, self.compute_dtype)
-        y, catbuf = [], {}
         L = list(self.model)
+        y, catbuf = [], {}
         start = 0
-        front = self._front(x, L, dest, fold)
+        if x.dtype == torch.uint8:
+            # uint8 HWC images [B,H,W,3] (BGR, the array-source contract): layer 0 reads them directly - /255, BGR->RGB and the
+            # NHWC padding happen inside the stem kernel (``stem_u8_supported`` says when; callers pack otherwise)
+            if not self.stem_u8_supported(x):
+                raise F.LpcError("uint8 HWC input is only taken where the fused uint8 stem applies (model.stem_u8_supported)")
+            x = L[0].forward_u8(x, swap_rb=True)
+            y, start = [x if 0 in self.save else None], 1
+        elif x.dtype not in (torch.bfloat16, torch.float32) or not F.is_nhwc_view(x) or x.dtype != self.compute_dtype:
+            x = F.pack_input(x.float().contiguous(), self.compute_dtype) if x.shape[1] <= 4 else F.as_act(x, self.compute_dtype)
+        front = self._front(x, L, dest, fold) if start == 0 else None
         if front is not None:
             x, start = front
             y = [None] * start
@@ -323,12 +341,13 @@ class YOLOv10DetectionModel(DetectionModel):
         parallel streams (parallel branches of a captured graph): images are independent, and while one chain sits in the
         fixed latency of a launch boundary (pipeline fill, last-tile epilogue, dependency resolution) the other chain's
         kernel has the SMs."""
-        hw = tuple(x.shape[2:]) if clip else None
+        u8 = x.dtype == torch.uint8              # uint8 HWC images [B,H,W,3] where ``stem_u8_supported`` (else callers pack first)
+        hw = (tuple(x.shape[1:3]) if u8 else tuple(x.shape[2:])) if clip else None
         n = streams if streams is not None else self.batch_streams
         B = x.shape[0]
         if n <= 1 or B < 2 * n:
             return self._predict_once(x, tail=lambda m, feats: m.detections(feats, max_det, hw, scale_back))
-        if x.dtype != self.compute_dtype or not F.is_nhwc_view(x):
+        if not u8 and (x.dtype != self.compute_dtype or not F.is_nhwc_view(x)):
             x = F.pack_input(x.float().contiguous(), self.compute_dtype) if x.shape[1] <= 4 else F.as_act(x, self.compute_dtype)
         out = torch.empty((B, max_det, 6), dtype=torch.float32, device=x.device)
         bounds = [(B * i // n, B * (i + 1) // n) for i in range(n)]
