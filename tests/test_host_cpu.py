@@ -128,3 +128,45 @@ def test_chunk_plan_covers_the_batch():
         if len(plan) == 2:
             assert plan[0] <= plan[1]
     assert eng._chunk_plan(64) == [20, 44]
+
+
+def test_stream_inference_queues_one_step_ahead(monkeypatch):
+    """engine.stream_inference (host logic, no GPU): a source longer than one batch is cut into steps of ``batch`` images in
+    order (ragged last step), step k+1 is QUEUED before the host waits for step k, results come back per image in source
+    order, and the predictor callbacks fire as in the reference's loop (engine/predictor.py:208-283)."""
+    import contextlib
+    import importlib
+
+    import numpy as np
+    eng = importlib.import_module("lpc-yolo_b200.engine")
+    log = []
+
+    class Stub(eng.YOLOv10DetectionPredictor):
+        def _enqueue(self, source, pipelined=False):
+            assert pipelined
+            log.append(("enqueue", len(source)))
+            return list(source)
+
+        def _finish(self, ticket):
+            log.append(("finish", len(ticket)))
+            return [int(t[0, 0, 0]) if hasattr(t, "shape") else t for t in ticket]
+
+    monkeypatch.setattr(eng.torch.cuda, "device", lambda dev: contextlib.nullcontext())
+    p = Stub()
+    p.model, p.device = object(), "cpu"
+    events = []
+    p.add_callback("on_predict_start", lambda s: events.append("start"))
+    p.add_callback("on_predict_end", lambda s: events.append("end"))
+    src = np.arange(11, dtype=np.uint8).reshape(11, 1, 1, 1) * np.ones((1, 2, 2, 3), np.uint8)
+    gen = p.stream_inference(src, 4)
+    assert log == [] and events == []                      # a generator: nothing runs before the first next()
+    assert next(gen) == 0
+    assert log == [("enqueue", 4), ("enqueue", 4), ("finish", 4)]      # step 1 was queued before step 0 was waited for
+    assert list(gen) == list(range(1, 11))
+    assert log == [("enqueue", 4), ("enqueue", 4), ("finish", 4), ("enqueue", 3), ("finish", 4), ("finish", 3)]
+    assert events == ["start", "end"]
+    # a list source and a batch larger than the source
+    del log[:]
+    assert list(p.stream_inference([7, 8, 9], 8)) == [7, 8, 9] and log == [("enqueue", 3), ("finish", 3)]
+    assert eng.YOLOv10DetectionPredictor.source_len(src) == 11 and eng.YOLOv10DetectionPredictor.source_len(src[0]) == 1
+    assert eng.YOLOv10DetectionPredictor.source_len(torch.zeros(5, 3, 8, 8)) == 5
