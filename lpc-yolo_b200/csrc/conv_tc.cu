@@ -62,6 +62,7 @@ struct ConvTcParams {
   long long x_ld;
   int H, W;
   int pitch, slabs, slab_bytes;      // halo patch: bytes per pixel row (32/64/128), 64-channel slabs
+  int tail_c, tail_bytes;            // pair kernel, Cin = 80 / 96: the channels past the last full 64-channel slab sit in a narrow slab of their own (16 / 32 channels per pixel row, its own tensor map: maps.a[1])
   int epi_split;                     // epilogue warps = 4 * epi_split
   int epi_alt;                       // 1: the two epilogue warp groups take alternate tiles (full width each) instead of half the columns of every tile
   int dbg;                           // LPC_TC_DBG bits (profiling only): 1 skip MMAs, 4 skip the epilogue math + stores, 8 trace, 32 skip stores only
@@ -713,11 +714,15 @@ extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W
   // extent and is zero-filled, the MMA loop walks only the three real 16-channel groups of every tap (the per-tap kernel
   // needs 27 boxes of 16 channels in the slow 32-byte-swizzled layout per tile: 48->48 @160x160 B256 took 920 us).
   static const int halo48 = [] { const char* e = getenv("LPC_TC_HALO48"); return e ? atoi(e) : 1; }();
-  if (k == 3 && stride == 1 && g_force_mode != 1 && (Cin == 16 || Cin == 32 || (Cin == 48 && halo48) || Cin % 64 == 0) && Cin <= 256) {
+  // Cin = 80 / 96 (yolov10x / m): one full 64-channel slab + a narrow 16- / 32-channel slab, CTA-pair kernel only (the weights of
+  // these layers do not fit next to two patches in one CTA); LPC_TC_MIXED=0 sends them back to the per-tap kernel
+  static const int mixed_env = [] { const char* e = getenv("LPC_TC_MIXED"); return e ? atoi(e) : 1; }();
+  const bool mixed = mixed_env && (Cin == 80 || Cin == 96);
+  if (k == 3 && stride == 1 && g_force_mode != 1 && (Cin == 16 || Cin == 32 || (Cin == 48 && halo48) || Cin % 64 == 0 || mixed) && Cin <= 256) {
     const long long tiles = (long long)((Wo + HALO_TW - 1) / HALO_TW) * ((Ho + HALO_TH - 1) / HALO_TH);
     const double eff = (double)Ho * Wo / (double)(tiles * 128);
     const int pitch = (Cin > 32 ? 64 : Cin) * 2;
-    const size_t halo_bytes = (size_t)((Cin + 63) / 64) * HALO_PH * HALO_SPW * pitch;
+    const size_t halo_bytes = mixed ? (size_t)HALO_PH * HALO_SPW * (128 + (Cin - 64) * 2) : (size_t)((Cin + 63) / 64) * HALO_PH * HALO_SPW * pitch;
     // weights resident if they fit next to two halo buffers (halving the N tile once if that makes them fit: the
     // activation patch is then loaded twice, still far cheaper than re-streaming the weights for every tile),
     // else a 3-block ring with full-width N tiles
@@ -742,7 +747,7 @@ extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W
       // Cin = 48 on CTA pairs: measured 48->48 @160x160 B256 (us, single / pair): 460 / 575 plain, 700 / 675 with the residual
       // add -> off by default (LPC_TC_PAIR48=1 switches it on; gpurun_out/prof_m256_p48.txt)
       static const int pair48 = [] { const char* e = getenv("LPC_TC_PAIR48"); return e ? atoi(e) : 0; }();
-      const bool wanted = (pair_env == 2 && Cin != 48) || Cin >= 64 || (Cin == 48 && pair48);
+      const bool wanted = (pair_env == 2 && Cin != 48) || Cin >= 64 || (Cin == 48 && pair48);      // (mixed: Cin >= 64)
       if (pair_env && wanted && (eff >= 0.7 || g_force_mode == 2) && bp + 2 * halo_bytes <= SMEM_LIMIT && tot_tiles >= 4) {
         halo = pair = true;
         p.n_tile = ntp;
@@ -752,7 +757,7 @@ extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W
         p.a_bufs = ab > MAX_STAGES ? MAX_STAGES : (ab < 2 ? 2 : ab);
       }
     }
-    if (!pair && resident && (eff >= 0.7 || g_force_mode == 2) && need <= SMEM_LIMIT) {
+    if (!pair && !mixed && resident && (eff >= 0.7 || g_force_mode == 2) && need <= SMEM_LIMIT) {
       halo = true;
       p.n_tile = nt;
       p.b_resident = resident;
@@ -797,11 +802,19 @@ extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W
     p.pitch = (Cin > 32 ? 64 : Cin) * 2;
     p.slabs = (Cin + 63) / 64;
     p.slab_bytes = HALO_PH * HALO_SPW * p.pitch;
-    smem = (size_t)p.ksteps * (pair ? p.n_tile / 2 : p.n_tile) * 128 + (size_t)p.a_bufs * p.slabs * p.slab_bytes + 1024 + BIAS_REGION(p.n_tile);
+    const bool mixed_slabs = Cin > 64 && Cin % 64 != 0;          // only reached through the pair kernel (selection above)
+    if (mixed_slabs) {
+      p.slabs = Cin / 64;                          // full slabs; the tail slab follows them
+      p.tail_c = Cin % 64;
+      p.tail_bytes = HALO_PH * HALO_SPW * p.tail_c * 2;
+    }
+    smem = (size_t)p.ksteps * (pair ? p.n_tile / 2 : p.n_tile) * 128 + (size_t)p.a_bufs * ((size_t)p.slabs * p.slab_bytes + p.tail_bytes) + 1024 + BIAS_REGION(p.n_tile);
     {
       p.a_tma = 1;                                // both halo kernels receive their patches by TMA
       const int cb = Cin > 32 ? 64 : Cin;
       if (int e = encode_act_map(&maps.a[0], xb, Cin, W, H, B, x_ld, (long long)W * x_ld, (long long)H * W * x_ld, cb, HALO_SPW, HALO_PH, swizzle_of(cb))) return e;
+      if (mixed_slabs)
+        if (int e = encode_act_map(&maps.a[1], xb, Cin, W, H, B, x_ld, (long long)W * x_ld, (long long)H * W * x_ld, p.tail_c, HALO_SPW, HALO_PH, swizzle_of(p.tail_c))) return e;
     }
   } else {
     // 1x1: always 64-channel boxes in the 128B-swizzled layout; when Cin is not a multiple of 64 the last box runs past the
@@ -889,7 +902,7 @@ extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W
     const int lim = (int)SMEM_LIMIT + 16 * 1024;
 #define HALO_ATTR(C_) if (cudaFuncSetAttribute(conv_tc_halo_kernel<C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess) e2 = cudaErrorUnknown;
 #define PAIR_ATTR(C_) if (cudaFuncSetAttribute(conv_tc_halo2_kernel<C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess) e2 = cudaErrorUnknown;
-    PAIR_ATTR(0) PAIR_ATTR(16) PAIR_ATTR(32) PAIR_ATTR(48) PAIR_ATTR(64) PAIR_ATTR(128)
+    PAIR_ATTR(0) PAIR_ATTR(16) PAIR_ATTR(32) PAIR_ATTR(48) PAIR_ATTR(64) PAIR_ATTR(128) PAIR_ATTR(80) PAIR_ATTR(96)
 #undef PAIR_ATTR
     HALO_ATTR(0) HALO_ATTR(16) HALO_ATTR(32) HALO_ATTR(48) HALO_ATTR(64) HALO_ATTR(128)
 #undef HALO_ATTR
@@ -953,6 +966,8 @@ extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W
     }
     if (!pair && Cin == 48) lpc_launch_pdl(conv_tc_halo_kernel<48>, grid, th, smem, st, maps, p);
     else if (pair && Cin == 48) lpc_launch_pdl(conv_tc_halo2_kernel<48>, grid, th, smem, st, maps, p);
+    else if (pair && Cin == 80) lpc_launch_pdl(conv_tc_halo2_kernel<80>, grid, th, smem, st, maps, p);
+    else if (pair && Cin == 96) lpc_launch_pdl(conv_tc_halo2_kernel<96>, grid, th, smem, st, maps, p);
     else if (pair) { HALO_LAUNCH(conv_tc_halo2_kernel) } else { HALO_LAUNCH(conv_tc_halo_kernel) }
 #undef HALO_LAUNCH
   }

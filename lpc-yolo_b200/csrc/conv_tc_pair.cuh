@@ -26,7 +26,7 @@ conv_tc_halo2_kernel(const __grid_constant__ TmapPack maps, const __grid_constan
   const uint32_t bias_addr = ones_addr + ONES_BYTES;
   const uint32_t smem_base = (bias_addr + (uint32_t)half * 32u + 1023u) & ~1023u;
   const int b_block = half * 128;                                     // bytes of one 64-wide K step of this CTA's half
-  const int halo_bytes = p.slabs * p.slab_bytes;
+  const int halo_bytes = p.slabs * p.slab_bytes + p.tail_bytes;      // Cin = 80 / 96: full slab(s) + one narrow tail slab
   const uint32_t a_region = smem_base + (uint32_t)(p.ksteps * b_block);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(&bars[0]);
@@ -94,6 +94,8 @@ conv_tc_halo2_kernel(const __grid_constant__ TmapPack maps, const __grid_constan
           const uint32_t a_dst = a_region + (uint32_t)(ab * halo_bytes);
           for (int sl = 0; sl < p.slabs; ++sl)
             tma_load_4d_pair(a_dst + (uint32_t)(sl * p.slab_bytes), &maps.a[0], lead_bar, sl * 64, t.x0 - 1, t.y0 - 1, t.img);
+          if (p.tail_c)
+            tma_load_4d_pair(a_dst + (uint32_t)(p.slabs * p.slab_bytes), &maps.a[1], lead_bar, p.slabs * 64, t.x0 - 1, t.y0 - 1, t.img);
         }
       }
     }
@@ -117,7 +119,20 @@ conv_tc_halo2_kernel(const __grid_constant__ TmapPack maps, const __grid_constan
         const uint32_t acc = tmem_base + (uint32_t)(buf * p.acc_cols);
         const uint32_t a_lo0 = desc_lo(a_region + (uint32_t)(ab * halo_bytes), 16u);
         umma2_bf16(acc, ones_desc, bias_desc, idesc, 0u);                  // accumulator := bias
-        if (CIN > 0) {
+        if (CIN == 80 || CIN == 96) {
+          // one full slab (64 channels per pixel row, 128B swizzle) + a narrow tail slab (16 / 32 channels, 32B / 64B swizzle):
+          // per tap four slices of the first and TG of the second, in the K order of the dense weights (tap * CIN + c)
+          constexpr int TAIL = CIN - 64, TG = TAIL / 16, TP16 = TAIL * 2 / 16, SLAB16 = HALO_PH * HALO_SPW * 128 / 16;
+          const uint32_t t_hi = desc_hi((uint32_t)(HALO_SPW * TAIL * 2), TAIL == 32 ? 4u : 6u);
+#pragma unroll
+          for (int j = 0; j < 9 * (4 + TG); ++j) {
+            const int tap = j / (4 + TG), g = j % (4 + TG);
+            const int pix = (tap / 3) * HALO_SPW + tap % 3;
+            const uint64_t ad = g < 4 ? desc64(a_lo0 + (uint32_t)(pix * 8 + 2 * g), a_hi)
+                                      : desc64(a_lo0 + (uint32_t)(SLAB16 + pix * TP16 + 2 * (g - 4)), t_hi);
+            umma2_acc(acc, ad, desc64(b_lo0 + (uint32_t)(j >> 2) * bblk16 + 2u * (uint32_t)(j & 3), b_hi), idesc);
+          }
+        } else if (CIN > 0) {
           constexpr int C_ROW = CIN <= 32 ? CIN : 64, PITCH16 = C_ROW * 2 / 16, GROUPS = (CIN < 64 ? CIN : 64) / 16, SLABS = (CIN + 63) / 64;
           constexpr int SLAB16 = HALO_PH * HALO_SPW * C_ROW * 2 / 16;
 #pragma unroll

@@ -142,7 +142,8 @@ def test_conv_tc_is_used_and_slices(M, Fn, oracle, pkg):
 @pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("case", [(16, 32, 32, 32, 2), (64, 64, 40, 40, 2), (128, 128, 20, 20, 2), (80, 80, 24, 24, 2),
                                   (48, 48, 40, 40, 2), (48, 96, 72, 88, 5), (16, 16, 80, 80, 6), (48, 80, 24, 20, 3),
-                                  (16, 32, 160, 160, 8), (32, 64, 72, 88, 6), (128, 256, 40, 40, 4), (256, 64, 16, 24, 3)])
+                                  (16, 32, 160, 160, 8), (32, 64, 72, 88, 6), (128, 256, 40, 40, 4), (256, 64, 16, 24, 3),
+                                  (96, 96, 40, 40, 3), (80, 80, 72, 88, 5), (96, 96, 80, 80, 9)])
 def test_conv3x3_both_tc_kernels(M, oracle, pkg, mode, case):
     """3x3 stride-1 convs through BOTH tensor-core kernels (1 = per-tap TMA boxes, 2 = halo patch with resident or
     streamed weights), incl. shapes with many more tiles than persistent CTAs and partial edge tiles."""
@@ -267,6 +268,17 @@ def test_bottleneck_c2f(B, oracle, dtype):
     x = _x((2, 64, 24, 24), dtype)
     ref = oracle._c2f(oracle._Ctx(_sd(mod, dtype)), x, "m", 2, True)
     _cmp(_run(mod, x, dtype), ref, dtype, "C2f", block=True)
+
+
+@pytest.mark.parametrize("c", [160, 192])
+def test_c2f_with_mixed_slab_bottlenecks(B, oracle, c):
+    """C2f whose bottlenecks run on 80 / 96 channels (yolov10x / yolov10m): 3x3 convs on the CTA-pair halo kernel with one full
+    64-channel slab + a narrow 16- / 32-channel slab per patch, reading and writing channel slices of the block's buffer,
+    shortcut add in the epilogue."""
+    mod = _randomize(B.C2f(c, c, 2, True), 17)
+    x = _x((3, c, 48, 40), torch.bfloat16)
+    ref = oracle._c2f(oracle._Ctx(_sd(mod, torch.bfloat16)), x, "m", 2, True)
+    _cmp(_run(mod, x, torch.bfloat16), ref, torch.bfloat16, f"C2f c={c}", block=True)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
