@@ -371,6 +371,179 @@ psa_attention_mma_kernel(const bf16* __restrict__ qkv, int ld, int N, int heads,
   }
 }
 
+// ---- the same attention with K and V of one (image, head) RESIDENT in shared memory ---------------------------------------
+// psa_attention_mma_kernel re-loads K / V once per 64-query CTA (seven CTAs per head at N = 400) and pays one cp.async round
+// trip + two __syncthreads per 64-key tile: 28-30 us at LPC B = 64 for 4 us of HBM time and well under 1 us of math.  Here a
+// CTA owns a (image, head) pair - or a contiguous share of its query blocks when there are few pairs -, loads all N keys and
+// values once (N <= 512: <= 115 KB, two CTAs per SM at N = 400) and its eight warps walk 16-query blocks without any
+// block-level synchronisation after the load: Q fragments come straight from global memory in the mma A layout, S = QK^T,
+// online softmax and O += PV stay in registers exactly as in the kernel above.
+constexpr int RES_WARPS = 8, RES_NT = RES_WARPS * 32;
+template <int KD, int HD>
+__host__ __device__ constexpr size_t psa_res_smem(int n_pad) {
+  return (size_t)n_pad * (pitch_of((KD + 15) / 16 * 16) + pitch_of(HD)) * sizeof(bf16);
+}
+
+template <int KD, int HD>
+__global__ void __launch_bounds__(RES_NT)
+psa_attention_res_kernel(const bf16* __restrict__ qkv, int ld, int N, int heads, int n_pad, bf16* __restrict__ out, int out_ld) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int KDP = (KD + 15) / 16 * 16, KP = pitch_of(KDP), VP = pitch_of(HD);
+  constexpr int CH = (KD % 8 == 0) ? 16 : 8;
+  constexpr int KCH = KD * 2 / CH, VCH = HD * 2 / 16;
+  constexpr int KSTEPS = KDP / 16, NT_S = MK / 8, NT_O = HD / 8;
+  extern __shared__ __align__(16) unsigned char res_smem[];
+  bf16* Ks = reinterpret_cast<bf16*>(res_smem);
+  bf16* Vs = Ks + (size_t)n_pad * KP;
+
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q_off = h * KD, k_off = heads * KD + h * KD, v_off = 2 * heads * KD + h * HD;
+  const bf16* base = qkv + (long long)b * N * ld;
+
+  if (KDP > KD) {       // K padding columns, never touched by the copies
+    for (int e = tid; e < n_pad * (KDP - KD); e += RES_NT) {
+      const int r = e / (KDP - KD), c = KD + e % (KDP - KD);
+      Ks[r * KP + c] = __float2bfloat16(0.f);
+    }
+  }
+  for (int e = tid; e < n_pad * KCH; e += RES_NT) {
+    const int r = e / KCH, c = e - r * KCH;
+    const bool ok = r < N;
+    cp_async_zfill<CH>((uint32_t)__cvta_generic_to_shared(&Ks[r * KP]) + c * CH,
+                       reinterpret_cast<const char*>(base + (long long)(ok ? r : 0) * ld + k_off) + c * CH, ok);
+  }
+  for (int e = tid; e < n_pad * VCH; e += RES_NT) {
+    const int r = e / VCH, c = e - r * VCH;
+    const bool ok = r < N;
+    cp_async_zfill<16>((uint32_t)__cvta_generic_to_shared(&Vs[r * VP]) + c * 16,
+                       reinterpret_cast<const char*>(base + (long long)(ok ? r : 0) * ld + v_off) + c * 16, ok);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+
+  // this CTA's share of the 16-query blocks of the head, block-cyclic over the warps
+  const int nqb = (N + 15) / 16;
+  const int per_cta = (nqb + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int qb_lo = blockIdx.x * per_cta, qb_hi = min(nqb, qb_lo + per_cta);
+  const float sl2 = rsqrtf((float)KD) * 1.4426950408889634f;
+  const int ntiles = n_pad / MK;
+  const int g = lane >> 2, c2 = 2 * (lane & 3);
+
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  for (int qb = qb_lo + warp; qb < qb_hi; qb += RES_WARPS) {
+    // Q fragments (mma.m16n8k16 A layout: rows g / g + 8, columns c2 + {0, 1} and + 8) straight from global memory
+    uint32_t qf[KSTEPS][4];
+    const int r0 = qb * 16 + g, r1 = r0 + 8;
+    const bf16* q0p = base + (long long)min(r0, N - 1) * ld + q_off;
+    const bf16* q1p = base + (long long)min(r1, N - 1) * ld + q_off;
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+      const int ca = ks * 16 + c2, cb = ca + 8;
+      qf[ks][0] = ca < KD ? *reinterpret_cast<const uint32_t*>(q0p + ca) : 0u;
+      qf[ks][1] = ca < KD ? *reinterpret_cast<const uint32_t*>(q1p + ca) : 0u;
+      qf[ks][2] = cb < KD ? *reinterpret_cast<const uint32_t*>(q0p + cb) : 0u;
+      qf[ks][3] = cb < KD ? *reinterpret_cast<const uint32_t*>(q1p + cb) : 0u;
+    }
+    float o[NT_O][4];
+#pragma unroll
+    for (int i = 0; i < NT_O; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+
+    for (int t = 0; t < ntiles; ++t) {
+      const bf16* Kt = Ks + (size_t)t * MK * KP;
+      const bf16* Vt = Vs + (size_t)t * MK * VP;
+      float s[NT_S][4];
+#pragma unroll
+      for (int nt = 0; nt < NT_S; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        const uint32_t krow = (uint32_t)__cvta_generic_to_shared(&Kt[(nt * 8 + (lane & 7)) * KP]);
+#pragma unroll
+        for (int ks = 0; ks + 1 < KSTEPS; ks += 2) {
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4(krow + (uint32_t)(ks * 16 + (lane >> 3) * 8) * 2u, b0, b1, b2, b3);
+          mma_bf16(s[nt], qf[ks], b0, b1);
+          mma_bf16(s[nt], qf[ks + 1], b2, b3);
+        }
+        if (KSTEPS & 1) {
+          uint32_t b0, b1;
+          ldsm_x2(krow + (uint32_t)((KSTEPS - 1) * 16 + ((lane >> 3) & 1) * 8) * 2u, b0, b1);
+          mma_bf16(s[nt], qf[KSTEPS - 1], b0, b1);
+        }
+      }
+      const int jbase = t * MK + c2;
+      if ((t + 1) * MK > N) {
+#pragma unroll
+        for (int nt = 0; nt < NT_S; ++nt) {
+          if (jbase + nt * 8 >= N) s[nt][0] = s[nt][2] = -INFINITY;
+          if (jbase + nt * 8 + 1 >= N) s[nt][1] = s[nt][3] = -INFINITY;
+        }
+      }
+      float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int nt = 0; nt < NT_S; ++nt) {
+        mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+        mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+      }
+      float corr[2], msc[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+        const float m_new = fmaxf(m_run[r], mx[r]);
+        corr[r] = ex2_approx((m_run[r] - m_new) * sl2);
+        m_run[r] = m_new;
+        msc[r] = m_new * sl2;
+      }
+      float rs[2] = {0.f, 0.f};
+      uint32_t pf[NT_S / 2][4];
+#pragma unroll
+      for (int nt = 0; nt < NT_S; ++nt) {
+        const float p0 = ex2_approx(fmaf(s[nt][0], sl2, -msc[0])), p1 = ex2_approx(fmaf(s[nt][1], sl2, -msc[0]));
+        const float p2 = ex2_approx(fmaf(s[nt][2], sl2, -msc[1])), p3 = ex2_approx(fmaf(s[nt][3], sl2, -msc[1]));
+        rs[0] += p0 + p1;
+        rs[1] += p2 + p3;
+        pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+        pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) l_run[r] = l_run[r] * corr[r] + rs[r];
+#pragma unroll
+      for (int i = 0; i < NT_O; ++i) {
+        o[i][0] *= corr[0]; o[i][1] *= corr[0];
+        o[i][2] *= corr[1]; o[i][3] *= corr[1];
+      }
+#pragma unroll
+      for (int dt = 0; dt < NT_O; ++dt) {
+#pragma unroll
+        for (int kk = 0; kk < MK / 32; ++kk) {
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4_t((uint32_t)__cvta_generic_to_shared(&Vt[(kk * 32 + lane) * VP + dt * 8]), b0, b1, b2, b3);
+          mma_bf16(o[dt], pf[2 * kk], b0, b1);
+          mma_bf16(o[dt], pf[2 * kk + 1], b2, b3);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+      l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int q = qb * 16 + g + r * 8;
+      if (q >= N) continue;
+      const float inv = 1.0f / l_run[r];
+      bf16* orow = out + ((long long)b * N + q) * out_ld + h * HD + c2;
+#pragma unroll
+      for (int dt = 0; dt < NT_O; ++dt)
+        *reinterpret_cast<uint32_t*>(orow + dt * 8) = pack_bf16x2(o[dt][r * 2] * inv, o[dt][r * 2 + 1] * inv);
+    }
+  }
+}
+
 constexpr size_t ATT_SMEM = sizeof(float) * (MAX_KD * (BQ + 4) + MAX_KD * (BKEY + 4) + BKEY * MAX_HD + BQ * (BKEY + 1));
 
 }  // namespace
@@ -412,6 +585,34 @@ extern "C" int lpc_psa_attention(int dtype, const void* qkv, int qkv_ld, int B, 
   } else if (dtype == LPC_BF16 && ((kd == 32 && hd == 64) || (kd == 36 && hd == 72)) && qkv_ld % 8 == 0 && out_ld % 2 == 0 &&
              aligned16(qkv) && (reinterpret_cast<uintptr_t>(out) & 3) == 0) {
     // tensor-core path (the two head geometries of the YOLOv10 / LPC family)
+    // K / V resident per (image, head) when there are enough pairs to fill the GPU and they fit two CTAs per SM or one
+    // (LPC_ATT_RES=0 / 1 forces the streaming / the resident kernel - the parity tests run both)
+    {
+      const char* re_ = getenv("LPC_ATT_RES");            // read at every call, like LPC_ATT_TC (the parity tests switch it)
+      const int res_env = re_ ? atoi(re_) : -1;
+      const int n_pad = cdiv(N, MK) * MK;
+      const size_t sm = kd == 32 ? psa_res_smem<32, 64>(n_pad) : psa_res_smem<36, 72>(n_pad);
+      const long long pairs = (long long)B * heads;
+      const bool fits = sm <= 200 * 1024 && N >= 16;
+      bool use = res_env == 1 ? fits : (res_env == 0 ? false : (fits && pairs >= lpc_num_sms() / 2 && N <= 640));
+      if (use) {
+        if (lpc_first_on_device(&attr_done[1])) {
+          cudaFuncSetAttribute(psa_attention_res_kernel<32, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+          cudaFuncSetAttribute(psa_attention_res_kernel<36, 72>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        }
+        // few pairs: several CTAs per pair share its query blocks (each loads K / V itself)
+        const int per_sm = sm <= 110 * 1024 ? 2 : 1;
+        int split = (int)((long long)lpc_num_sms() * per_sm / pairs);
+        const int nqb = cdiv(N, 16);
+        if (split < 1) split = 1;
+        if (split > cdiv(nqb, RES_WARPS)) split = cdiv(nqb, RES_WARPS);
+        dim3 g3(split, heads, B);
+        if (kd == 32) lpc_launch_pdl(psa_attention_res_kernel<32, 64>, g3, RES_NT, sm, s, (const bf16*)qkv, qkv_ld, N, heads, n_pad, (bf16*)out, out_ld);
+        else lpc_launch_pdl(psa_attention_res_kernel<36, 72>, g3, RES_NT, sm, s, (const bf16*)qkv, qkv_ld, N, heads, n_pad, (bf16*)out, out_ld);
+        LPC_CHECK_LAUNCH("psa_attention");
+        return LPC_OK;
+      }
+    }
     dim3 g2(cdiv(N, MQ), heads, B);
     if (kd == 32) lpc_launch_pdl(psa_attention_mma_kernel<32, 64>, g2, MMA_NT, 0, s, (const bf16*)qkv, qkv_ld, N, heads, (bf16*)out, out_ld);
     else lpc_launch_pdl(psa_attention_mma_kernel<36, 72>, g2, MMA_NT, 0, s, (const bf16*)qkv, qkv_ld, N, heads, (bf16*)out, out_ld);

@@ -436,13 +436,22 @@ def test_head_cls_branch_fused_equals_unfused(pkg, oracle, Fn):
 
 
 @pytest.mark.parametrize("N", [25, 100, 128, 129, 400, 900, 1600])
-@pytest.mark.parametrize("heads,kd,hd,force", [(2, 32, 64, "1"), (5, 32, 64, "1"), (2, 32, 64, "0"), (5, 32, 64, "0"), (4, 36, 72, None)])
+@pytest.mark.parametrize("heads,kd,hd,force", [(2, 32, 64, "1"), (5, 32, 64, "1"), (2, 32, 64, "0"), (5, 32, 64, "0"), (4, 36, 72, None),
+                                               (2, 32, 64, "res"), (5, 32, 64, "res"), (4, 36, 72, "res")])
 def test_psa_attention_core(Fn, N, heads, kd, hd, force, monkeypatch):
-    """lpc_psa_attention (bf16: the tcgen05 kernel for kd 32 / hd 64, the mma.sync kernel for kd 36 / hd 72) against the
-    reference arithmetic of Attention.forward (block.py:789-793) in fp32 on the same bf16-rounded q, k, v; N covers every
-    token count of BASELINE configs 2-5 (100 / 400 / 900 / 1600) and block-edge cases (128, 129)."""
-    if force is not None:
+    """lpc_psa_attention (bf16: the tcgen05 kernel for kd 32 / hd 64, the mma.sync kernels - streaming and K/V-resident - for
+    both head geometries) against the reference arithmetic of Attention.forward (block.py:789-793) in fp32 on the same
+    bf16-rounded q, k, v; N covers every token count of BASELINE configs 2-5 (100 / 400 / 900 / 1600) and block-edge cases."""
+    if force == "res":
+        if N > 640:
+            pytest.skip("the K/V-resident kernel serves N <= 640")
+        monkeypatch.setenv("LPC_ATT_TC", "0")
+        monkeypatch.setenv("LPC_ATT_RES", "1")            # K / V resident in shared memory (read at every call)
+    elif force is not None:
         monkeypatch.setenv("LPC_ATT_TC", force)           # "1": tcgen05 kernel, "0": mma.sync kernel (read at every call)
+        monkeypatch.setenv("LPC_ATT_RES", "0")
+    else:
+        monkeypatch.setenv("LPC_ATT_RES", "0")
     g = torch.Generator().manual_seed(N * 7 + heads)
     Ct = heads * (2 * kd + hd)
     qkv = (torch.randn(2, N, Ct, generator=g) * 0.8).to(torch.bfloat16)
