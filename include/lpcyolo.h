@@ -93,6 +93,16 @@ int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W, int Cin, 
 /* 1 if lpc_conv2d_tc accepts this shape, else 0. */
 int lpc_conv2d_tc_supported(int Cin, int Cout, int k, int stride, int pad, int x_ld, int y_ld);
 
+/* 1x1 conv over cat[upsample2x(x_small), x_skip] (the neck's nn.Upsample -> Concat -> C2f.cv1, LPC YAML layers 15-17 / 18-20;
+ * reference nn/modules/conv.py:323-333 Concat, torch nn.Upsample(scale_factor=2, mode="nearest"), block.py:226-230) WITHOUT the
+ * upsampled tensor: the K chunks of the first C0 input channels are fetched from the SMALL map [B,H/2,W/2,C0] through a 5-D tensor
+ * map whose two repeat dimensions have stride 0, so every source pixel lands in the four rows of the A tile its 2x2 output pixels
+ * own; the other C1 channels come from x_skip [B,H,W,C1] as usual.  w: [Cout][C0 + C1] (lpc_conv2d_tc's 1x1 packing, upsampled
+ * channels first).  Bit-identical to lpc_upsample2x + lpc_conv2d_tc.  C0, C1 multiples of 64, even H and W (output size). */
+int lpc_conv1x1_up2cat_tc_supported(int C0, int C1, int Cout, int H, int W, int xs_ld, int xk_ld, int y_ld);
+int lpc_conv1x1_up2cat_tc(const void* x_small, int xs_ld, int C0, const void* x_skip, int xk_ld, int C1, int B, int H, int W,
+                          const void* w, const float* bias, int Cout, void* y, int y_ld, int act, void* stream);
+
 /* Conv 3x3 s1 (Cin 16 -> 32) fused with the space_to_depth + 1x1 conv that follows it in the SPD-Conv stem of the LPC YAML
  * (layers 1-3: conv.Conv(16,32,3,1) -> space_to_depth -> C2f.cv1; reference nn/modules/conv.py:36-54, nn/modules/block.py:4063-4070
  * space_to_depth, block.py:226-230 C2f.forward): y[B,H/2,W/2,C2] = act2(W2 * s2d(act1(W1 * x + b1)) + b2), where w2 is the 1x1

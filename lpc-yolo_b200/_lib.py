@@ -37,6 +37,8 @@ SIGNATURES = {
     "lpc_conv2d_tc_kpad": (_i, [_i, _i]),
     "lpc_conv2d_tc_set_mode": (_i, [_i]),
     "lpc_conv2d_tc_supported": (_i, [_i, _i, _i, _i, _i, _i, _i]),
+    "lpc_conv1x1_up2cat_tc_supported": (_i, [_i, _i, _i, _i, _i, _i, _i, _i]),
+    "lpc_conv1x1_up2cat_tc": (_i, [_p, _i, _i, _p, _i, _i, _i, _i, _i, _p, _f32p, _i, _p, _i, _i, _p]),
     "lpc_conv3x3_s2d_tc_supported": (_i, [_i, _i, _i, _i, _i, _i, _i]),
     "lpc_conv3x3_s2d_tc": (_i, [_p, _i, _i, _i, _i, _i, _p, _f32p, _i, _i, _p, _f32p, _i, _i, _p, _i, _p]),
     "lpc_dwpw_tc_supported": (_i, [_i, _i, _i, _i, _i, _i, _i, _i]),

@@ -63,6 +63,7 @@ struct ConvTcParams {
   int H, W;
   int pitch, slabs, slab_bytes;      // halo patch: bytes per pixel row (32/64/128), 64-channel slabs
   int tail_c, tail_bytes;            // pair kernel, Cin = 80 / 96: the channels past the last full 64-channel slab sit in a narrow slab of their own (16 / 32 channels per pixel row, its own tensor map: maps.a[1])
+  int up_chunks;                     // per-tap kernel, 1x1 over cat[upsample2x(small), skip]: the first up_chunks 64-channel K chunks come from the SMALL map through a 5-D tensor map that repeats every source pixel 2 x 2 (maps.a[1])
   int epi_split;                     // epilogue warps = 4 * epi_split
   int epi_alt;                       // 1: the two epilogue warp groups take alternate tiles (full width each) instead of half the columns of every tile
   int dbg;                           // LPC_TC_DBG bits (profiling only): 1 skip MMAs, 4 skip the epilogue math + stores, 8 trace, 32 skip stores only
@@ -340,6 +341,13 @@ conv_tc_taps_kernel(const __grid_constant__ TmapPack maps, const __grid_constant
             if (q >= p.real_slots) q = p.real_slots - 1;  // padded K: weights are zero there, any finite A will do
             const int tap = q / p.chunks_per_tap;
             const int c0 = (q - tap * p.chunks_per_tap) * p.kc;
+            if (p.up_chunks > 0) {
+              // 1x1 over cat[upsample2x(small), skip] (kc = 64, one chunk per K step): the box [64 ch, 2, TW/2, 2, TH/2] of the
+              // small map lands as the same 128 rows (x + TW * y) an upsampled tile would have
+              if (q < p.up_chunks) tma_load_5d(a_dst, &maps.a[1], full_bar(s), c0, 0, t.x0 >> 1, 0, t.img * (p.Ho >> 1) + (t.y0 >> 1));
+              else tma_load_4d(a_dst, &maps.a[0], full_bar(s), c0 - p.up_chunks * 64, t.x0, t.y0, t.img);
+              continue;
+            }
             tma_load_4d(a_dst + (uint32_t)(j * sub_bytes), &maps.a[p.tap_map[tap]], full_bar(s), c0, t.x0 + p.tap_dx[tap],
                         t.y0 + p.tap_dy[tap], t.img);
           }
@@ -670,10 +678,42 @@ extern "C" int lpc_conv2d_tc(const void* x, int x_ld, int B, int H, int W, int C
   return lpc_conv2d_tc_rowmax(x, x_ld, B, H, W, Cin, w, bias, k, stride, pad, Cout, y, y_ld, act, chan_scale, res, res_ld, nullptr, 0, 0, stream);
 }
 
+static int conv2d_tc_impl(const void* x, int x_ld, int B, int H, int W, int Cin, const void* w, const float* bias,
+                          int k, int stride, int pad, int Cout, void* y, int y_ld, int act,
+                          const float* chan_scale, const void* res, int res_ld,
+                          unsigned int* rowmax_keys, long long rowmax_img_stride, int rowmax_offset,
+                          const void* up_x, int up_ld, int up_c, void* stream);
+
 extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W, int Cin, const void* w, const float* bias,
                                     int k, int stride, int pad, int Cout, void* y, int y_ld, int act,
                                     const float* chan_scale, const void* res, int res_ld,
                                     unsigned int* rowmax_keys, long long rowmax_img_stride, int rowmax_offset, void* stream) {
+  return conv2d_tc_impl(x, x_ld, B, H, W, Cin, w, bias, k, stride, pad, Cout, y, y_ld, act, chan_scale, res, res_ld, rowmax_keys,
+                        rowmax_img_stride, rowmax_offset, nullptr, 0, 0, stream);
+}
+
+// 1x1 conv over cat[upsample2x(x_small), x_skip] without the upsampled tensor: conv_tc.cu taps kernel, `up_chunks`.
+extern "C" int lpc_conv1x1_up2cat_tc_supported(int C0, int C1, int Cout, int H, int W, int xs_ld, int xk_ld, int y_ld) {
+  static const int on = [] { const char* e = getenv("LPC_TC_UPCAT"); return e ? atoi(e) : 1; }();
+  if (!on || C0 <= 0 || C1 <= 0 || C0 % 64 || C1 % 64 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || xs_ld % 8) return 0;
+  return lpc_conv2d_tc_supported(C0 + C1, Cout, 1, 1, 0, xk_ld, y_ld);
+}
+
+extern "C" int lpc_conv1x1_up2cat_tc(const void* x_small, int xs_ld, int C0, const void* x_skip, int xk_ld, int C1, int B, int H, int W,
+                                     const void* w, const float* bias, int Cout, void* y, int y_ld, int act, void* stream) {
+  LPC_REQUIRE(x_small && x_skip, "conv1x1_up2cat_tc: null pointer");
+  if (!lpc_conv1x1_up2cat_tc_supported(C0, C1, Cout, H, W, xs_ld, xk_ld, y_ld))
+    LPC_FAIL(LPC_E_UNSUPPORTED, "conv1x1_up2cat_tc: unsupported shape C0=%d C1=%d Cout=%d H=%d W=%d", C0, C1, Cout, H, W);
+  LPC_REQUIRE(aligned16(x_small), "conv1x1_up2cat_tc: pointers must be 16-byte aligned");
+  return conv2d_tc_impl(x_skip, xk_ld, B, H, W, C0 + C1, w, bias, 1, 1, 0, Cout, y, y_ld, act, nullptr, nullptr, 0, nullptr, 0, 0, x_small, xs_ld, C0,
+                        stream);
+}
+
+static int conv2d_tc_impl(const void* x, int x_ld, int B, int H, int W, int Cin, const void* w, const float* bias,
+                          int k, int stride, int pad, int Cout, void* y, int y_ld, int act,
+                          const float* chan_scale, const void* res, int res_ld,
+                          unsigned int* rowmax_keys, long long rowmax_img_stride, int rowmax_offset,
+                          const void* up_x, int up_ld, int up_c, void* stream) {
   LPC_REQUIRE(x && w && y, "conv2d_tc: null pointer");
   LPC_REQUIRE(B > 0 && H > 0 && W > 0, "conv2d_tc: bad shape");
   if (!lpc_conv2d_tc_supported(Cin, Cout, k, stride, pad, x_ld, y_ld))
@@ -825,7 +865,24 @@ extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W
     p.chunks_per_tap = (Cin + p.kc - 1) / p.kc;
     p.real_slots = ntaps * p.chunks_per_tap;
     const CUtensorMapSwizzle sw = swizzle_of(p.kc);
-    if (k == 1) {
+    if (k == 1 && up_x) {
+      // spatial 16 x 8 tiles instead of the flat view: the skip half through a 4-D map over its C1 channels, the upsampled half
+      // through a 5-D map over the SMALL tensor [C0, 2 (stride 0), W/2, 2 (stride 0), B*H/2]
+      p.B = B; p.Ho = Ho; p.Wo = Wo; p.TW = 16; p.TH = 8;
+      p.tiles_x = (Wo + 15) / 16; p.tiles_y = (Ho + 7) / 8;
+      p.up_chunks = up_c / 64;
+      if (int e = encode_act_map(&maps.a[0], xb, Cin - up_c, W, H, B, x_ld, (long long)W * x_ld, (long long)H * W * x_ld, 64, 16, 8, sw)) return e;
+      {
+        const int Ws = W / 2, Hs = H / 2;
+        cuuint64_t dims[5] = {(cuuint64_t)up_c, 2, (cuuint64_t)Ws, 2, (cuuint64_t)B * Hs};
+        cuuint64_t strides[4] = {0, (cuuint64_t)up_ld * 2, 0, (cuuint64_t)Ws * up_ld * 2};
+        cuuint32_t box[5] = {64, 2, 8, 2, 4};
+        cuuint32_t es[5] = {1, 1, 1, 1, 1};
+        CUresult r = enc(&maps.a[1], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(up_x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) LPC_FAIL(LPC_E_UNSUPPORTED, "conv1x1_up2cat_tc: the repeating (stride-0) tensor map was refused (CUresult %d)", (int)r);
+      }
+    } else if (k == 1) {
       const long long M = (long long)B * H * W;
       LPC_REQUIRE(M < (1ll << 31), "conv2d_tc: too many pixels");
       p.B = 1; p.Ho = 1; p.Wo = (int)M; p.TW = 128; p.TH = 1;
@@ -863,7 +920,7 @@ extern "C" int lpc_conv2d_tc_rowmax(const void* x, int x_ld, int B, int H, int W
       static const int tp_env = [] { const char* e = getenv("LPC_TC_TPAIR"); return e ? atoi(e) : 0; }();
       const long long m_est = (long long)p.tiles_x * p.tiles_y * p.B;
       const bool wanted = tp_env == 2 || p.ksteps >= 8 || (p.n_tile >= 128 && p.ksteps >= 2);
-      tpair = tp_env && wanted && p.n_tile % 16 == 0 && m_est >= 4;
+      tpair = tp_env && wanted && p.n_tile % 16 == 0 && m_est >= 4 && !up_x;
     }
     const int stage_bytes = A_STAGE_BYTES + (tpair ? ((p.n_tile / 2 * 128 + 1023) & ~1023) : p.n_tile * 128);
     // two CTAs per SM when the double-buffered accumulators leave TMEM room, else one CTA with a deeper ring

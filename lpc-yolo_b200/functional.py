@@ -312,6 +312,45 @@ def stem_conv_u8(src, pc, swap_rb=True, out=None):
     return out
 
 
+def conv1x1_upcat_supported(x_small, x_skip, pc, out_ld=None):
+    """Can ``pc`` (a 1x1 conv over cat[upsample2x(x_small), x_skip]) run without the upsampled tensor (lpc_conv1x1_up2cat_tc)?"""
+    if x_small.dtype != torch.bfloat16 or x_skip.dtype != torch.bfloat16 or pc.w_tc is None or (pc.k, pc.s, pc.p) != (1, 1, 0):
+        return False
+    B, C0, Hs, Ws = x_small.shape
+    B1, C1, H, W = x_skip.shape
+    if B1 != B or (H, W) != (2 * Hs, 2 * Ws) or pc.cin != C0 + C1:
+        return False
+    sp, sld = view_of(x_small)
+    kp, kld = view_of(x_skip)
+    return sp % 16 == 0 and kp % 16 == 0 and bool(_lib.lib().lpc_conv1x1_up2cat_tc_supported(C0, C1, pc.cout, H, W, sld, kld,
+                                                                                            out_ld if out_ld is not None else pc.cout))
+
+
+def conv1x1_upcat(x_small, x_skip, pc, out=None):
+    """act(W * cat[upsample2x(x_small), x_skip] + b); callers check ``conv1x1_upcat_supported``."""
+    B, C0, Hs, Ws = x_small.shape
+    _, C1, H, W = x_skip.shape
+    if out is None:
+        out = new_act(B, pc.cout, H, W, x_skip.dtype, x_skip.device)
+    assert tuple(out.shape) == (B, pc.cout, H, W)
+    sp, sld = view_of(x_small)
+    kp, kld = view_of(x_skip)
+    yp, yld = view_of(out)
+    L = _lib.lib()
+    flops = 2.0 * B * H * W * pc.cout * (C0 + C1)
+    nbytes = x_skip.element_size() * (B * Hs * Ws * C0 + B * H * W * (C1 + pc.cout) + pc.cout * (C0 + C1))
+    tag = f"up2({C0})+{C1}->{pc.cout} k1s1 {H}x{W} B{B}"
+
+    def launch(keep=(x_small, x_skip, out, pc)):
+        check(L.lpc_conv1x1_up2cat_tc(sp, sld, C0, kp, kld, C1, B, H, W, _fp(pc.w_tc), _fp(pc.bias), pc.cout, yp, yld, pc.act, _stream()),
+              "conv1x1_up2cat_tc")
+    if REPLAY is not None:
+        REPLAY.append(("conv2d_tc", launch, flops, nbytes, tag, None))
+    with _prof("conv1x1_up2cat_tc", flops, nbytes, tag):
+        launch()
+    return out
+
+
 def conv3x3_s2d_supported(x, pc1, pc2, out_ld=None):
     """Can conv3x3(pc1) -> space_to_depth -> conv1x1 (pc2 = its 2x2 stride-2 re-packing) run as ONE kernel (lpc_conv3x3_s2d_tc)?"""
     if x.dtype != torch.bfloat16 or pc1.w_tc is None or pc2.w_tc is None:

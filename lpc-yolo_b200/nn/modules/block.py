@@ -81,17 +81,28 @@ class C2f(LpcModule):
         self.cv2 = Conv((2 + n) * self.c, c2, 1)
         self.m = nn.ModuleList(Bottleneck(self.c, self.c, shortcut, g, k=((3, 3), (3, 3)), e=1.0) for _ in range(n))
 
-    def forward(self, x, out=None, s2d=False, pre=None):
+    def forward(self, x, out=None, s2d=False, pre=None, up=None):
         """``s2d=True``: x is the tensor BEFORE a space_to_depth layer; cv1 then runs as a 2x2 stride-2 conv
         (the s2d + 1x1 fold), so the 4x-channel tensor is never written.  ``pre`` (with s2d): the stride-1 Conv layer in
-        front of the space_to_depth, x being ITS input: conv -> s2d -> cv1 then is one kernel where the shape is taken."""
+        front of the space_to_depth, x being ITS input: conv -> s2d -> cv1 then is one kernel where the shape is taken.  ``up``: x is a Concat buffer
+        cat[upsample2x(up), skip] whose upsampled part was NOT written (nn.Upsample -> Concat -> C2f of the neck)."""
         x = self._in(x)
         B, _, H, W = x.shape
         if s2d:
             H, W = H // 2, W // 2
         c, n = self.c, len(self.m)
         ybuf = F.new_act(B, (2 + n) * c, H, W, x.dtype, x.device)
-        if s2d:
+        if up is not None:
+            # x is the Concat buffer whose first channels WOULD hold upsample2x(up): cv1 reads them from ``up`` itself where the
+            # C library takes the shape, else the upsampled tensor is materialised into its slice first
+            c0 = up.shape[1]
+            pk = self.cv1._packed(x, self.cv1._build)
+            if isinstance(pk, pack.PackedConv) and F.conv1x1_upcat_supported(up, x[:, c0:], pk, F.view_of(ybuf[:, : 2 * c])[1]):
+                F.conv1x1_upcat(up, x[:, c0:], pk, out=ybuf[:, : 2 * c])
+            else:
+                F.upsample2x(up, out=x[:, :c0])
+                self.cv1(x, out=ybuf[:, : 2 * c])
+        elif s2d:
             self.cv1.forward_s2d(x, out=ybuf[:, : 2 * c], pre=pre)
         else:
             self.cv1(x, out=ybuf[:, : 2 * c])

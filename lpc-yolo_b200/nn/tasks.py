@@ -121,6 +121,7 @@ class BaseModel(LpcModule):
 
     compute_dtype = torch.bfloat16
     fold_s2d = True      # space_to_depth + C2f.cv1 -> one 2x2 stride-2 conv (exact same arithmetic)
+    fold_upsample = os.environ.get("LPC_FOLD_UPSAMPLE", "1") != "0"      # Upsample + Concat + C2f.cv1 without the upsampled tensor
 
     def forward(self, x, *args, **kwargs):
         return self.predict(x, *args, **kwargs)
@@ -170,7 +171,19 @@ class BaseModel(LpcModule):
                         and (i - 1) not in dest and i - 1 > 0 and j == i + 1
                         and c.conv.kernel_size == (3, 3) and c.conv.stride == (1, 1) and c.conv.groups == 1):
                     prefold[i - 1] = j
-        self._plan_cache = (dest, live, fold, prefold)
+        # nn.Upsample -> Concat([-1, j]) -> C2f: the C2f's first 1x1 conv can read the upsampled half of the Concat buffer from the
+        # SMALL map (lpc_conv1x1_up2cat_tc), so the Upsample launch and its 4x larger copy disappear.  upfold[i] = index of the C2f.
+        upfold = {}
+        if self.front_depth <= 0 and self.fold_upsample:
+            for m in L:
+                i = m.i
+                if (isinstance(m, Upsample) and m.f == -1 and i + 2 < len(L) and isinstance(L[i + 1], Concat) and isinstance(L[i + 1].f, list)
+                        and len(L[i + 1].f) == 2 and L[i + 1].f[0] == -1 and L[i + 1].f[1] not in (-1, i) and type(L[i + 2]) is C2f
+                        and L[i + 2].f == -1 and consumers[i] == [i + 1] and consumers[i + 1] == [i + 2] and i not in self.save
+                        and (i + 1) not in self.save and (i + 1) not in dest and dest.get(i) == (i + 1, 0) and (i + 1) not in fold
+                        and L[i + 1].f[1] in dest and dest[L[i + 1].f[1]][0] == i + 1):
+                    upfold[i] = i + 2
+        self._plan_cache = (dest, live, fold, prefold, upfold)
         return self._plan_cache
 
     def stem_u8_supported(self, src):
@@ -178,7 +191,7 @@ class BaseModel(LpcModule):
         a plain stride-2 3x3 stem Conv feeding only layer 1, a shape lpc_stem_conv_u8 takes."""
         if self.compute_dtype != torch.bfloat16 or not (torch.is_tensor(src) and src.is_cuda and src.dtype == torch.uint8):
             return False
-        dest, live, fold, prefold = self._plan()
+        dest, live, fold, prefold, upfold = self._plan()
         m = self.model[0]
         if type(m) is not Conv or m.f != -1 or 0 in dest or 0 in fold or 0 in prefold or self.front_depth > 0:
             return False
@@ -193,10 +206,11 @@ class BaseModel(LpcModule):
             # current device is cuda:0 would launch there with device-1 pointers
             with torch.cuda.device(x.device):
                 return self._predict_once(x, tail)
-        dest, live, fold, prefold = self._plan()
+        dest, live, fold, prefold, upfold = self._plan()
         L = list(self.model)
         y, catbuf = [], {}
         start = 0
+        up_small = None
         if x.dtype == torch.uint8:
             # uint8 HWC images [B,H,W,3] (BGR, the array-source contract): layer 0 reads them directly - /255, BGR->RGB and the
             # NHWC padding happen inside the stem kernel (``stem_u8_supported`` says when; callers pack otherwise)
@@ -217,6 +231,17 @@ class BaseModel(LpcModule):
             if m.i in fold or m.i in prefold:      # skipped: the consumer reads our INPUT (s2d fold / conv + s2d fusion)
                 y.append(None)
                 continue
+            if m.i in upfold and (m.i + 1) in catbuf:      # Upsample folded into the C2f two layers on: x stays the SMALL map
+                up_small = x
+                y.append(None)
+                continue
+            if m.i - 1 in upfold and up_small is not None:        # its Concat: the buffer the skip source already wrote into
+                x = catbuf[m.i]
+                y.append(None)
+                continue
+            extra = {}
+            if m.i - 2 in upfold and up_small is not None:        # the C2f: cv1 reads cat[upsample2x(up_small), skip]
+                extra, up_small = {"up": up_small}, None
             if m.i - 1 in fold and fold[m.i - 1] == m.i:
                 x = m(x, s2d=True, pre=L[m.i - 2] if prefold.get(m.i - 2) == m.i else None)
                 y.append(x if m.i in self.save else None)
@@ -228,11 +253,11 @@ class BaseModel(LpcModule):
                 B, c, H, W = m.out_shape(x.shape)
                 if j not in catbuf:
                     catbuf[j] = F.new_act(B, self._out_ch[j], H, W, x.dtype, x.device)
-                x = m(x, out=catbuf[j][:, off:off + c])
+                x = m(x, out=catbuf[j][:, off:off + c], **extra)
             elif tail is not None and m is L[-1]:
                 x = tail(m, x)
             else:
-                x = m(x)
+                x = m(x, **extra)
             y.append(x if m.i in self.save else None)
         return x
 

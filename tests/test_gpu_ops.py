@@ -199,6 +199,59 @@ def test_conv3x3_s2d_unsupported_shapes_take_two_launches(M, Fn, pkg):
             assert torch.equal(cv1.forward_s2d(x, pre=pre), cv1.forward_s2d(pre(x)))
 
 
+@pytest.mark.parametrize("case", [(2, 128, 128, 64, 40, 40, "mish"), (3, 256, 256, 128, 20, 20, "mish"), (2, 64, 128, 96, 18, 18, "silu"),
+                                  (5, 128, 64, 256, 40, 24, "mish"), (1, 64, 64, 64, 3, 5, "silu")])
+def test_conv1x1_over_upsample_concat_without_the_upsampled_tensor(M, Fn, pkg, case):
+    """lpc_conv1x1_up2cat_tc (nn.Upsample -> Concat -> C2f.cv1 of the neck: the upsampled half of the 1x1 conv's input is read from
+    the SMALL map through a tensor map that repeats every pixel 2 x 2) against upsample2x + the plain 1x1 conv on the
+    materialised concat buffer: bit-identical (same operand values, same K order).  Ragged tiles, maps smaller than a tile,
+    a skip half that is a channel slice of a wider buffer, and an output slice."""
+    B, c0, c1, cout, Hs, Ws, act = case
+    blk = importlib.import_module("lpc-yolo_b200.nn.modules.block")
+    cv = _randomize((blk.Conv if act == "mish" else M.Conv)(c0 + c1, cout, 1, 1), seed=c0 + Hs).cuda()
+    small = Fn.as_act(_x((B, c0, Hs, Ws), torch.bfloat16, seed=3).cuda(), torch.bfloat16)
+    cat = Fn.new_act(B, c0 + c1, 2 * Hs, 2 * Ws, torch.bfloat16, "cuda")
+    cat[:, c0:].copy_(Fn.as_act(_x((B, c1, 2 * Hs, 2 * Ws), torch.bfloat16, seed=4).cuda(), torch.bfloat16))
+    cat[:, :c0].fill_(float("nan"))                      # the fused path must not read the upsampled slots
+    with torch.no_grad():
+        pk = cv._packed(cat, cv._build)
+        assert Fn.conv1x1_upcat_supported(small, cat[:, c0:], pk)
+        wide = Fn.new_act(B, cout + 16, 2 * Hs, 2 * Ws, torch.bfloat16, "cuda")
+        wide.fill_(7.0)
+        got = Fn.conv1x1_upcat(small, cat[:, c0:], pk, out=wide[:, :cout])
+        Fn.upsample2x(small, out=cat[:, :c0])
+        want = cv(cat)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want), f"max diff {(got.float() - want.float()).abs().max().item():.3e}"
+    assert bool((wide[:, cout:].float() == 7.0).all())
+
+
+def test_neck_upsample_fold_changes_nothing_but_the_launches(pkg):
+    """The whole LPC model with the two neck Upsample layers folded into their C2f (default) and with the fold switched off:
+    identical detections and raw head maps, two launches fewer."""
+    synth = importlib.import_module("lpc-yolo_b200.utils.synth")
+    bench = importlib.import_module("bench")
+    yolo = pkg.YOLO(bench.FILES["lpc"])
+    synth.init_synthetic(yolo.model)
+    m = yolo.model.cuda().eval()
+    m.compute_dtype = torch.bfloat16
+    x = torch.rand(2, 3, 320, 320, generator=torch.Generator().manual_seed(5)).cuda()
+    with torch.no_grad():
+        assert m._plan()[4] == {15: 17, 18: 20}
+        n0 = pkg.lib().lpc_launch_count()
+        a = m.detect(x, 300)
+        n1 = pkg.lib().lpc_launch_count()
+        m.fold_upsample, m._plan_cache = False, None
+        try:
+            assert m._plan()[4] == {}
+            b = m.detect(x, 300)
+            n2 = pkg.lib().lpc_launch_count()
+        finally:
+            m.fold_upsample, m._plan_cache = True, None
+    assert torch.equal(a, b)
+    assert (n2 - n1) - (n1 - n0) == 2
+
+
 def test_conv1x1_many_tiles(M, oracle):
     """Persistent 1x1 kernel: 3200 M tiles over ~300 CTAs, two N tiles, residual epilogue."""
     mod = _randomize(M.Conv(64, 512, 1, 1), seed=5)

@@ -53,7 +53,8 @@ def test_lpc_yaml_quirks(pkg, oracle):
     m = _model(pkg, oracle, "lpc")
     det = m.model[-1]
     assert det.f == [20, 23, 26] and [s[0].conv.in_channels for s in det.cv2] == [64, 192, 384]
-    dest, live, fold, prefold = m._plan()
+    dest, live, fold, prefold, upfold = m._plan()
+    assert upfold == {15: 17, 18: 20}      # both neck Upsample layers fold into the C2f behind their Concat
     assert fold == {2: 3, 5: 6, 8: 9, 11: 12}
     assert prefold == {1: 3, 4: 6}      # a stride-1 3x3 Conv whose ONLY consumer is a folded space_to_depth runs inside the C2f call (7, 10 also feed Concats)
     assert 27 not in live                       # dead layer is skipped
