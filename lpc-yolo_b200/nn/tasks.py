@@ -178,7 +178,7 @@ class BaseModel(LpcModule):
             for m in L:
                 i = m.i
                 if (isinstance(m, Upsample) and m.f == -1 and i + 2 < len(L) and isinstance(L[i + 1], Concat) and isinstance(L[i + 1].f, list)
-                        and len(L[i + 1].f) == 2 and L[i + 1].f[0] == -1 and L[i + 1].f[1] not in (-1, i) and type(L[i + 2]) is C2f
+                        and len(L[i + 1].f) == 2 and L[i + 1].f[0] == -1 and L[i + 1].f[1] not in (-1, i) and isinstance(L[i + 2], C2f)     # (C2fCIB shares C2f.forward)
                         and L[i + 2].f == -1 and consumers[i] == [i + 1] and consumers[i + 1] == [i + 2] and i not in self.save
                         and (i + 1) not in self.save and (i + 1) not in dest and dest.get(i) == (i + 1, 0) and (i + 1) not in fold
                         and L[i + 1].f[1] in dest and dest[L[i + 1].f[1]][0] == i + 1):
