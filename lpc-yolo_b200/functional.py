@@ -312,9 +312,12 @@ def stem_conv_u8(src, pc, swap_rb=True, out=None):
     return out
 
 
+_UPCAT_REFUSED = False      # set when cuTensorMapEncodeTiled refused the stride-0 map once (then the fold is off for the process)
+
+
 def conv1x1_upcat_supported(x_small, x_skip, pc, out_ld=None):
     """Can ``pc`` (a 1x1 conv over cat[upsample2x(x_small), x_skip]) run without the upsampled tensor (lpc_conv1x1_up2cat_tc)?"""
-    if x_small.dtype != torch.bfloat16 or x_skip.dtype != torch.bfloat16 or pc.w_tc is None or (pc.k, pc.s, pc.p) != (1, 1, 0):
+    if _UPCAT_REFUSED or x_small.dtype != torch.bfloat16 or x_skip.dtype != torch.bfloat16 or pc.w_tc is None or (pc.k, pc.s, pc.p) != (1, 1, 0):
         return False
     B, C0, Hs, Ws = x_small.shape
     B1, C1, H, W = x_skip.shape
@@ -327,7 +330,8 @@ def conv1x1_upcat_supported(x_small, x_skip, pc, out_ld=None):
 
 
 def conv1x1_upcat(x_small, x_skip, pc, out=None):
-    """act(W * cat[upsample2x(x_small), x_skip] + b); callers check ``conv1x1_upcat_supported``."""
+    """act(W * cat[upsample2x(x_small), x_skip] + b); callers check ``conv1x1_upcat_supported``.  -> None when the driver refuses
+    the repeating tensor map (nothing launched)."""
     B, C0, Hs, Ws = x_small.shape
     _, C1, H, W = x_skip.shape
     if out is None:
@@ -342,12 +346,20 @@ def conv1x1_upcat(x_small, x_skip, pc, out=None):
     tag = f"up2({C0})+{C1}->{pc.cout} k1s1 {H}x{W} B{B}"
 
     def launch(keep=(x_small, x_skip, out, pc)):
-        check(L.lpc_conv1x1_up2cat_tc(sp, sld, C0, kp, kld, C1, B, H, W, _fp(pc.w_tc), _fp(pc.bias), pc.cout, yp, yld, pc.act, _stream()),
-              "conv1x1_up2cat_tc")
+        st = L.lpc_conv1x1_up2cat_tc(sp, sld, C0, kp, kld, C1, B, H, W, _fp(pc.w_tc), _fp(pc.bias), pc.cout, yp, yld, pc.act, _stream())
+        if st == _lib.E_UNSUPPORTED:
+            return False
+        check(st, "conv1x1_up2cat_tc")
+        return True
+    with _prof("conv1x1_up2cat_tc", flops, nbytes, tag):
+        ok = launch()
+    if not ok:
+        # the driver refused the repeating (stride-0) tensor map: nothing was launched; the caller materialises the upsampled half
+        global _UPCAT_REFUSED
+        _UPCAT_REFUSED = True
+        return None
     if REPLAY is not None:
         REPLAY.append(("conv2d_tc", launch, flops, nbytes, tag, None))
-    with _prof("conv1x1_up2cat_tc", flops, nbytes, tag):
-        launch()
     return out
 
 

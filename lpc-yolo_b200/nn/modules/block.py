@@ -97,9 +97,10 @@ class C2f(LpcModule):
             # C library takes the shape, else the upsampled tensor is materialised into its slice first
             c0 = up.shape[1]
             pk = self.cv1._packed(x, self.cv1._build)
+            done = None
             if isinstance(pk, pack.PackedConv) and F.conv1x1_upcat_supported(up, x[:, c0:], pk, F.view_of(ybuf[:, : 2 * c])[1]):
-                F.conv1x1_upcat(up, x[:, c0:], pk, out=ybuf[:, : 2 * c])
-            else:
+                done = F.conv1x1_upcat(up, x[:, c0:], pk, out=ybuf[:, : 2 * c])
+            if done is None:
                 F.upsample2x(up, out=x[:, :c0])
                 self.cv1(x, out=ybuf[:, : 2 * c])
         elif s2d:
