@@ -22,7 +22,7 @@ Fn = importlib.import_module("lpc-yolo_b200.functional")
 libmod = importlib.import_module("lpc-yolo_b200._lib")
 synth = importlib.import_module("lpc-yolo_b200.utils.synth")
 
-LAUNCHING = {"lpc_conv2d_direct", "lpc_conv2d_tc", "lpc_conv3x3_s2d_tc", "lpc_dwpw_tc", "lpc_conv2d_tc_rowmax", "lpc_stem_conv", "lpc_dwconv2d", "lpc_sppf_pool", "lpc_psa_attention",
+LAUNCHING = {"lpc_conv2d_direct", "lpc_conv2d_tc", "lpc_conv3x3_s2d_tc", "lpc_conv1x1_up2cat_tc", "lpc_stem_conv_u8", "lpc_dwpw_tc", "lpc_conv2d_tc_rowmax", "lpc_stem_conv", "lpc_dwconv2d", "lpc_sppf_pool", "lpc_psa_attention",
              "lpc_upsample2x", "lpc_copy_channels", "lpc_space_to_depth", "lpc_channel_deinterleave", "lpc_pack_input", "lpc_pack_u8",
              "lpc_letterbox_u8", "lpc_global_avgpool", "lpc_channel_mlp", "lpc_cbam_stats", "lpc_cbam_apply", "lpc_v10_decode",
              "lpc_v10_decode_topk", "lpc_v10_decode_topk_keys", "lpc_v10_decode_topk_scaled", "lpc_v10_postprocess"}
