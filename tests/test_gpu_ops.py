@@ -8,6 +8,7 @@ Tolerances (max|d| / max|ref| unless noted):
                                 2e-2 normalised max, 1e-2 l2-relative (T2 row).
 """
 import importlib
+import os
 
 import pytest
 import torch
@@ -168,6 +169,8 @@ def test_conv3x3_s2d_fused_equals_two_launches(M, Fn, pkg, case):
     memory) against the two launches it replaces (halo 3x3 kernel, then the 2x2 stride-2 fold of s2d + 1x1): bit-identical -
     same bf16 rounding of the intermediate, same K order in the tensor core.  Ragged maps (partial supertiles), more
     supertiles than persistent CTAs (5 x 320 x 320 = 1000 on 296), C2 = 16 / 32 / 48 / 64, compile-time and run-time acts."""
+    if os.environ.get("LPC_TC_S2D") == "0":
+        pytest.skip("the conv + space_to_depth fusion is switched off (LPC_TC_S2D=0)")
     B, H, W, c2, act2 = case
     blk = importlib.import_module("lpc-yolo_b200.nn.modules.block")
     pre = _randomize(M.Conv(16, 32, 3, 1), seed=B + H).cuda()                   # conv.Conv: SiLU
@@ -206,6 +209,8 @@ def test_conv1x1_over_upsample_concat_without_the_upsampled_tensor(M, Fn, pkg, c
     the SMALL map through a tensor map that repeats every pixel 2 x 2) against upsample2x + the plain 1x1 conv on the
     materialised concat buffer: bit-identical (same operand values, same K order).  Ragged tiles, maps smaller than a tile,
     a skip half that is a channel slice of a wider buffer, and an output slice."""
+    if os.environ.get("LPC_TC_UPCAT") == "0":
+        pytest.skip("the upsample fold is switched off in the C library (LPC_TC_UPCAT=0)")
     B, c0, c1, cout, Hs, Ws, act = case
     blk = importlib.import_module("lpc-yolo_b200.nn.modules.block")
     cv = _randomize((blk.Conv if act == "mish" else M.Conv)(c0 + c1, cout, 1, 1), seed=c0 + Hs).cuda()
@@ -229,6 +234,8 @@ def test_conv1x1_over_upsample_concat_without_the_upsampled_tensor(M, Fn, pkg, c
 def test_neck_upsample_fold_changes_nothing_but_the_launches(pkg):
     """The whole LPC model with the two neck Upsample layers folded into their C2f (default) and with the fold switched off:
     identical detections and raw head maps, two launches fewer."""
+    if os.environ.get("LPC_FOLD_UPSAMPLE") == "0" or os.environ.get("LPC_TC_UPCAT") == "0":
+        pytest.skip("the upsample fold is switched off")
     synth = importlib.import_module("lpc-yolo_b200.utils.synth")
     bench = importlib.import_module("bench")
     yolo = pkg.YOLO(bench.FILES["lpc"])
