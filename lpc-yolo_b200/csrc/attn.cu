@@ -569,7 +569,7 @@ extern "C" int lpc_psa_attention(int dtype, const void* qkv, int qkv_ld, int B, 
   LPC_REQUIRE(qkv_ld >= heads * (2 * kd + hd) && out_ld >= heads * hd, "psa_attention: pitch too small");
   dim3 grid(cdiv(N, BQ), heads, B);
   cudaStream_t s = (cudaStream_t)stream;
-  static unsigned long long attr_done[2] = {0, 0};     // per device
+  static unsigned long long attr_done[3] = {0, 0, 0};  // per device: generic fp32 / generic bf16 / K-V-resident kernels
   if (dtype == LPC_F32 && !getenv("LPC_ATT_F32_FAST")) {
     const size_t sm = (size_t)VAL_WARPS * N * sizeof(double);
     LPC_REQUIRE(sm <= 200 * 1024, "psa_attention (fp32 validation): N = %d too large", N);
@@ -596,7 +596,7 @@ extern "C" int lpc_psa_attention(int dtype, const void* qkv, int qkv_ld, int B, 
       const bool fits = sm <= 200 * 1024 && N >= 16;
       bool use = res_env == 1 ? fits : (res_env == 0 ? false : (fits && pairs >= lpc_num_sms() / 2 && N <= 640));
       if (use) {
-        if (lpc_first_on_device(&attr_done[1])) {
+        if (lpc_first_on_device(&attr_done[2])) {
           cudaFuncSetAttribute(psa_attention_res_kernel<32, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
           cudaFuncSetAttribute(psa_attention_res_kernel<36, 72>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         }
