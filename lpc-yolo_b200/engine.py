@@ -368,7 +368,7 @@ class YOLOv10DetectionPredictor:
         scale = torch.tensor([row] * cb, dtype=torch.float32, device=dev) if row is not None else None
         H, W, top, left = geom[:4]
         direct = (tables is None and (top, left, H, W) == (0, 0, hs, ws)
-                  and model.stem_u8_supported(torch.empty((cb, hs, ws, 3), dtype=torch.uint8, device=dev)))
+                  and model.stem_u8_supported(torch.empty((1, hs, ws, 3), dtype=torch.uint8, device=dev)))      # (the answer does not depend on the batch)
         if direct:          # no LetterBox border / resize: the stem kernel reads the uint8 image itself (no packed copy of the batch)
             run = lambda inp: model.detect(inp, K, clip=True, scale_back=scale)
             return (None, run) if split else run
