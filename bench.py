@@ -622,7 +622,7 @@ def main():
                                   "per step H2D of that step's images, /255 + BGR->RGB + NHWC pack, network, fused tail, D2H of its "
                                   "[B,300,6]; the predictor queues one step ahead (copy under the previous step's kernels)",
                         "single_call": {"value": round(e2e_single_ips, 2), "unit": "img/s", "steps": e_steps,
-                                        "source": "one synchronous YOLO.predict(64 images) per step (chunked 20+44 copy/compute overlap "
+                                        "source": "one synchronous YOLO.predict(64 images) per step (chunked 24+40 copy/compute overlap "
                                                   "inside the call, nothing in flight between calls)"}},
                 "gpu_launches": int(launches_per_step * args.steps),
                 "roofline": roof, "roofline_tail": roof_tail, "cpu_baseline": cpu, "other_configs": others,

@@ -47,9 +47,10 @@ def _chunk_plan(B):
     if env and env.isdigit() and int(env) > 0 and B % int(env) == 0:
         return [B // int(env)] * int(env)
     if B >= 32 and B % 4 == 0:
-        # first chunk ~5/16 of the batch: its replay then lasts as long as the copy of the rest (measured B=64, ms / step with
-        # the end-of-round kernels: 12+52 3.85, 16+48 3.69, 20+44 3.55, 24+40 3.64)
-        first = max(4, (B * 5 // 16) // 4 * 4)
+        # first chunk ~3/8 of the batch: its replay then lasts as long as the copy of the rest (measured B=64, ms / step: round 1
+        # kernels 12+52 3.85, 16+48 3.69, 20+44 3.55, 24+40 3.64; end of round 2 - faster kernels, same copy - 16+48 3.68,
+        # 20+44 3.34, 24+40 3.30, 28+36 3.39, 32+32 3.49, three chunks 3.48-3.59, one chunk 3.80)
+        first = max(4, (B * 3 // 8) // 4 * 4)
         return [first, B - first]
     if B >= 8 and B % 2 == 0:
         return [B // 2, B // 2]

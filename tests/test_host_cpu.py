@@ -128,7 +128,7 @@ def test_chunk_plan_covers_the_batch():
         assert sum(plan) == B and all(v > 0 for v in plan)
         if len(plan) == 2:
             assert plan[0] <= plan[1]
-    assert eng._chunk_plan(64) == [20, 44]
+    assert eng._chunk_plan(64) == [24, 40]
 
 
 def test_stream_inference_queues_one_step_ahead(monkeypatch):
